@@ -1,0 +1,99 @@
+"""Reference problem -> IR.
+
+Walks the smooth problem the reference builds in ``NLPsolver.apply``
+(cvxpy/reductions/solvers/nlp_solvers/nlp_solver.py:61-79) and emits
+``dnlp_b200.ir`` nodes.  Dispatch is on class *names*, so this module never
+imports cvxpy: it works with whichever copy of the reference the caller has
+loaded, and the rest of the package stays importable without it.
+"""
+import numpy as np
+import scipy.sparse as sp
+
+from . import ir
+
+_ELEMENTWISE = {name: name for name in ir.ELEMENTWISE_UNARY if name != "power"}
+_SIMPLE = {
+    "AddExpression": "add", "NegExpression": "neg", "Promote": "promote",
+    "multiply": "multiply", "MulExpression": "matmul", "QuadForm": "quad_form",
+    "quad_over_lin": "quad_over_lin", "rel_entr": "rel_entr",
+}
+_SIMPLE.update(_ELEMENTWISE)
+
+
+def _const(expr):
+    v = expr.value
+    if v is None:
+        raise ValueError("constant/parameter without a value: %s" % expr)
+    if sp.issparse(v):
+        node = ir.Constant(v)
+    else:
+        node = ir.Constant(np.asarray(v, dtype=np.float64))
+    # the reference's shape wins (e.g. a (n,) constant stored as a column)
+    if node.shape != tuple(expr.shape) and node.size == int(np.prod(expr.shape, dtype=np.int64)):
+        node = ir.Node("const", (), expr.shape,
+                       value=np.reshape(node.attrs["value"] if not sp.issparse(node.attrs["value"])
+                                        else node.attrs["value"].toarray(), expr.shape, order="F"))
+    return node
+
+
+def expr_to_ir(expr, memo):
+    key = id(expr)
+    if key in memo:
+        return memo[key]
+    cls = type(expr).__name__
+    if cls == "Variable":
+        bounds = getattr(expr, "bounds", None)
+        node = ir.Node("var", (), expr.shape, id=int(expr.id), name=expr.name(),
+                       lb=None if not bounds else bounds[0], ub=None if not bounds else bounds[1],
+                       value=None if expr.value is None else np.asarray(expr.value, np.float64))
+    elif expr.is_constant():
+        node = _const(expr)
+    else:
+        args = [expr_to_ir(a, memo) for a in expr.args]
+        if cls in _SIMPLE:
+            node = ir.Node(_SIMPLE[cls], args, expr.shape)
+        elif cls == "Sum":
+            node = ir.Node("sum", args, expr.shape, axis=expr.axis, keepdims=bool(expr.keepdims))
+        elif cls == "index":
+            fkey = [(int(s.start), None if s.stop is None else int(s.stop), int(s.step))
+                    for s in expr.key]
+            node = ir.Node("index", args, expr.shape, key=fkey,
+                           orig_key=ir._encode_key(expr._orig_key))
+        elif cls == "special_index":
+            node = ir.Node("special_index", args, expr.shape,
+                           select=np.asarray(expr._select_mat, dtype=np.int64))
+        elif cls == "reshape":
+            node = ir.Node("reshape", args, expr.shape, order=expr.order)
+        elif cls in ("transpose",):
+            axes = getattr(expr, "axes", None)
+            node = ir.Node("transpose", args, expr.shape,
+                           axes=None if axes is None else tuple(int(a) for a in axes))
+        elif cls == "broadcast_to":
+            node = ir.Node("broadcast_to", args, expr.shape)
+        elif cls == "power":
+            p = expr.p.value
+            if p is None and expr.p_rational is None:
+                raise ValueError("Argument error in jacobian for atom power.")
+            node = ir.Node("power", args, expr.shape,
+                           p=float(p), p_rational=expr.p_rational)
+        else:
+            raise NotImplementedError(
+                "Atom %s does not have a Jacobian, or it has not been implemented yet." % cls)
+        if node.is_affine() != bool(expr.is_affine()):
+            raise AssertionError("affine classification differs from the reference for %s" % cls)
+    memo[key] = node
+    return node
+
+
+def problem_to_ir(problem, cl=None, cu=None, lb=None, ub=None, x0=None):
+    """``problem`` is ``Bounds.new_problem`` (constraints already Zero/NonNeg)."""
+    memo = {}
+    obj = expr_to_ir(problem.objective.args[0], memo)
+    cons = [expr_to_ir(c.args[0], memo) for c in problem.constraints]
+    variables = [expr_to_ir(v, memo) for v in problem.variables()]
+    return ir.ProblemIR(obj, cons, variables, cl, cu, lb, ub, x0)
+
+
+def data_to_ir(data):
+    """From the dict returned by the reference's ``NLPsolver.apply`` chain."""
+    return problem_to_ir(data["problem"], data["cl"], data["cu"], data["lb"], data["ub"], data["x0"])
