@@ -1,0 +1,148 @@
+"""DAG compiler: smooth problem IR -> flat tape + fixed triplet patterns.
+
+Runs once per ``NLPsolver.apply`` (where the reference builds its ``Oracles``
+object, reductions/solvers/nlp_solvers/nlp_solver.py:61-79).  It replays, on
+symbolic values, exactly what the reference's seven callbacks do numerically on
+every call:
+
+  objective      nlp_solver.py:212-216
+  gradient       nlp_solver.py:218-235   scatter-ASSIGN of the objective Jacobian
+  constraints    nlp_solver.py:237-244
+  jacobian       nlp_solver.py:246-307   per constraint, per variable in main_var order;
+                                         duplicate-summed CSR sampling when any constraint
+                                         is non-affine (insert_missing_zeros_jacobian)
+  hessian        nlp_solver.py:337-421   sum_coo (row-major sort + duplicate sum), then the
+                                         lower triangle of the structure is sampled
+
+The structures come out bit-identical to the reference's NaN-evaluation passes
+(nlp_solver.py:309-335, 374-392) because the index arithmetic is the same and the
+SciPy-routed orderings are produced by the same SciPy calls (see rules.py).
+"""
+import numpy as np
+
+from . import tape as T
+from .rules import Builder
+from .symvec import SymVec
+
+
+def _closure(tape, root_ids):
+    need, stack = set(), list(root_ids)
+    while stack:
+        i = stack.pop()
+        if i in need:
+            continue
+        need.add(i)
+        stack.extend(tape.instrs[i].deps)
+    return sorted(need)
+
+
+def _emit_output(b, sv, space):
+    """Split an output vector into its compile-time constant part and a POLY instruction
+    for the entries that depend on x / lambda.  Returns (const_values, instr or None)."""
+    sv = sv.simplify()
+    cmask = sv.is_const_mask()
+    const = np.where(cmask, sv.const_values(), 0.0)
+    dyn = np.where(~cmask)[0]
+    if dyn.size == 0:
+        return const, None
+    if dyn.size == sv.K:
+        ins = b.emit_poly(sv, space, 0, pos=None)
+    else:
+        ins = b.emit_poly(sv.gather(dyn), space, 0, pos=dyn.astype(np.int64))
+    return const, ins
+
+
+def compile_problem(prob):
+    """ProblemIR -> Tape (host arrays only; ``GpuOracles`` uploads it through the C-ABI)."""
+    b = Builder(prob)
+    tape = b.tape
+    n, m = prob.n, prob.m
+    var_ids = [v.attrs["id"] for v in prob.variables]
+    off = b.var_off
+
+    # ---- objective value ------------------------------------------------------
+    fv = b.value(prob.objective)
+    if fv.K != 1:
+        raise ValueError("objective must be scalar")
+    f_const, f_ins = _emit_output(b, fv, T.DST_F)
+    tape.f_const = float(f_const[0])
+
+    # ---- constraint values ------------------------------------------------------
+    gv = SymVec.concat([b.value(c) for c in prob.constraints]) if prob.constraints else SymVec.zeros(0)
+    tape.g_const, g_ins = _emit_output(b, gv, T.DST_G)
+
+    # ---- gradient: grad_obj[offset + cols] = vals (assignment, last write wins) ----
+    gd = b.jac(prob.objective)
+    grad = SymVec.zeros(n)
+    if gd:
+        cols_all, parts = [], []
+        for vid in var_ids:
+            if vid in gd:
+                _, c, v = gd[vid]
+                cols_all.append(c + off[vid])
+                parts.append(v)
+        cols_all = np.concatenate(cols_all)
+        vals = SymVec.concat(parts)
+        last = np.full(n, -1, dtype=np.int64)
+        last[cols_all] = np.arange(cols_all.size)
+        dst = np.where(last >= 0)[0]
+        grad = vals.gather(last[dst]).scatter_into(n, dst)
+    tape.grad_const, grad_ins = _emit_output(b, grad, T.DST_GRAD)
+
+    # ---- Jacobian triplets in emission order ----------------------------------
+    R, C, V = [], [], []
+    affine = [c.is_affine() for c in prob.constraints]
+    coff = 0
+    for con in prob.constraints:
+        jd = b.jac(con)
+        for vid in var_ids:
+            if vid in jd:
+                r, c, v = jd[vid]
+                R.append(r + coff)
+                C.append(c + off[vid])
+                V.append(v)
+        coff += con.size
+    R = np.concatenate(R) if R else np.zeros(0, np.int64)
+    C = np.concatenate(C) if C else np.zeros(0, np.int64)
+    jv = SymVec.concat(V)
+    tape.jac_rows, tape.jac_cols = R.astype(np.int32), C.astype(np.int32)
+    permutation_needed = not all(affine)
+    tape.jac_is_list = not permutation_needed
+    if permutation_needed and R.size:
+        key = R * max(n, 1) + C
+        uniq, inv = np.unique(key, return_inverse=True)
+        if uniq.size != key.size:                       # quirk Q4: repeats receive the full sum
+            jv = jv.group_sum(inv, uniq.size).gather(inv)
+    tape.jac_const, jac_ins = _emit_output(b, jv, T.DST_JAC)
+
+    # ---- Hessian of the Lagrangian ----------------------------------------------
+    HR, HC, HV = [], [], []
+
+    def parse(hd):
+        for v1 in var_ids:
+            for v2 in var_ids:
+                if (v1, v2) in hd:
+                    r, c, v = hd[(v1, v2)]
+                    HR.append(np.asarray(r, np.int64) + off[v1])
+                    HC.append(np.asarray(c, np.int64) + off[v2])
+                    HV.append(v)
+
+    parse(b.hv(prob.objective, SymVec.slots([tape.sigma_slot])))
+    coff = 0
+    for con in prob.constraints:
+        parse(b.hv(con, SymVec.slot_range(tape.lam_slot + coff, con.size)))
+        coff += con.size
+    if HR:
+        hr, hc, hv = Builder._coo_sum_duplicates(np.concatenate(HR), np.concatenate(HC), SymVec.concat(HV))
+        low = np.where(hr >= hc)[0]
+        hr, hc, hv = hr[low], hc[low], hv.gather(low)
+    else:
+        hr = hc = np.zeros(0, np.int64)
+        hv = SymVec.zeros(0)
+    tape.hess_rows, tape.hess_cols = hr.astype(np.int32), hc.astype(np.int32)
+    tape.hess_const, hess_ins = _emit_output(b, hv, T.DST_HESS)
+
+    for name, ins in (("f", f_ins), ("grad", grad_ins), ("g", g_ins), ("jac", jac_ins), ("hess", hess_ins)):
+        tape.programs[name] = _closure(tape, [ins.id]) if ins is not None else []
+    tape.programs["all"] = sorted(set().union(*[set(p) for p in tape.programs.values()]))
+    return tape

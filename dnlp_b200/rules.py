@@ -1,0 +1,837 @@
+"""Symbolic twins of the reference's value / Jacobian / Hessian-vector rules.
+
+For every atom the reference evaluates three things numerically on each callback:
+``numeric`` (value), ``_jacobian`` (COO triplets) and ``_hess_vec`` (COO triplets of
+sum_i vec_i * Hessian_i).  Here the same rules run ONCE, at compile time, on
+``SymVec`` values: indices (rows, cols) are computed exactly as the reference
+computes them - same formulas, same SciPy calls where the reference routes
+through SciPy - so the emitted triplet *order* is the reference's, while the
+values stay symbolic and end up as tape instructions.
+
+Reference files (relative to /root/reference/cvxpy) are cited per rule.
+"""
+import numpy as np
+import scipy.sparse as sp
+
+from . import ir
+from . import tape as T
+from .symvec import NONE, SymVec
+
+
+def _flatF(v):
+    return np.asarray(v).flatten(order="F")
+
+
+def _dense(v):
+    return v.toarray() if sp.issparse(v) else np.asarray(v, dtype=np.float64)
+
+
+def _dims(node):
+    """MulExpression.get_dimensions, atoms/affine/binary_operators.py:299-307."""
+    if len(node.shape) == 0:
+        return (1, 1)
+    if len(node.shape) == 1:
+        return (node.shape[0], 1)
+    return node.shape
+
+
+def _same_var(a, b):
+    return a.is_var() and b.is_var() and a.attrs["id"] == b.attrs["id"]
+
+
+class Builder:
+    """Compile context: slot allocation, instruction emission, CSE caches."""
+
+    def __init__(self, prob):
+        self.prob = prob
+        self.tape = T.Tape(prob.n, prob.m)
+        self.var_off = {}
+        off = 0
+        for v in prob.variables:
+            self.var_off[v.attrs["id"]] = off
+            off += v.size
+        self.var_size = {v.attrs["id"]: v.size for v in prob.variables}
+        self._elem_cache = {}
+        self._value_cache = {}
+        self._mat_cache = {}
+        self._producers = []        # (start, end, instr id) of V ranges written by instructions
+
+    # ---- emission ----------------------------------------------------------
+    def _deps_of_slots(self, slots):
+        slots = np.asarray(slots, dtype=np.int64)
+        slots = slots[slots >= 0]
+        uses_lam = bool(np.any((slots >= self.tape.n) & (slots < self.tape.n + 1 + self.tape.m)))
+        deps = set()
+        if self._producers and slots.size:
+            starts = np.array([p[0] for p in self._producers], dtype=np.int64)
+            ends = np.array([p[1] for p in self._producers], dtype=np.int64)
+            ids = np.array([p[2] for p in self._producers], dtype=np.int64)
+            tmp = slots[slots >= self.tape.n + 1 + self.tape.m]
+            if tmp.size:
+                k = np.searchsorted(starts, tmp, side="right") - 1
+                ok = (k >= 0) & (tmp < ends[np.maximum(k, 0)])
+                deps = set(np.unique(ids[k[ok]]).tolist())
+        return deps, uses_lam
+
+    def _finish(self, ins, read_slots):
+        deps, uses_lam = self._deps_of_slots(read_slots)
+        for d in deps:
+            uses_lam = uses_lam or self.tape.instrs[d].uses_lam
+        ins.deps = tuple(sorted(deps))
+        ins.uses_lam = uses_lam
+        ins.level = 1 + max([self.tape.instrs[d].level for d in deps], default=-1)
+        self.tape.add(ins)
+        if ins.dst_space == T.DST_V:
+            self._producers.append((ins.dst_off, ins.dst_off + ins.count, ins.id))
+        return ins
+
+    def materialise(self, sv):
+        """Evaluate ``sv`` into fresh contiguous slots; returns the SymVec of those slots."""
+        if sv.contiguous_start() is not None:
+            return sv
+        key = (sv.K, sv.nterms, hash(sv.row.tobytes()), hash(sv.coef.tobytes()),
+               hash(sv.f1.tobytes()), hash(sv.f2.tobytes())) if sv.nterms < 4096 else None
+        if key is not None and key in self._mat_cache:
+            return self._mat_cache[key]
+        dst = self.tape.alloc(sv.K)
+        self.emit_poly(sv, T.DST_V, dst)
+        out = SymVec.slot_range(dst, sv.K)
+        if key is not None:
+            self._mat_cache[key] = out
+        return out
+
+    def emit_poly(self, sv, dst_space, dst_off, pos=None, count=None):
+        ins = T.Instr(T.K_POLY, dst_space=dst_space, dst_off=int(dst_off),
+                      count=sv.K if count is None else count,
+                      ptr=sv.ptr.copy(), coef=sv.coef, f1=sv.f1, f2=sv.f2, pos=pos)
+        return self._finish(ins, np.concatenate([sv.f1, sv.f2]))
+
+    def elem(self, fcode, a, b=None, param=0.0):
+        """dst = F(a, b); operands are broadcast when they have a single entry."""
+        count = max(a.K, b.K if b is not None else 1)
+
+        def operand(sv):
+            sv = self.materialise(sv)
+            return sv.contiguous_start(), (0 if (sv.K == 1 and count > 1) else 1)
+
+        a_off, a_st = operand(a)
+        b_off, b_st = operand(b) if b is not None else (0, 0)
+        key = (fcode, float(param), a_off, a_st, b_off, b_st, count)
+        if key in self._elem_cache:
+            return self._elem_cache[key]
+        dst = self.tape.alloc(count)
+        ins = T.Instr(T.K_ELEM, dst_off=dst, count=count, fcode=fcode, param=float(param),
+                      a_off=a_off, a_stride=a_st, b_off=b_off, b_stride=b_st)
+        reads = [np.arange(a_off, a_off + (count if a_st else 1))]
+        if b is not None:
+            reads.append(np.arange(b_off, b_off + (count if b_st else 1)))
+        self._finish(ins, np.concatenate(reads))
+        out = SymVec.slot_range(dst, count)
+        self._elem_cache[key] = out
+        return out
+
+    def mul(self, a, b):
+        """Entrywise product of two symbolic vectors (operands materialised as needed)."""
+        if a.K != b.K:
+            if a.K == 1:
+                a = a.gather(np.zeros(b.K, dtype=np.int64))
+            elif b.K == 1:
+                b = b.gather(np.zeros(a.K, dtype=np.int64))
+            else:
+                raise ValueError("size mismatch in product")
+        if a.can_multiply_directly(b):
+            return a.mul_simple(b)
+
+        def simple(sv):
+            return bool(np.all(sv.term_counts() <= 1)) and (sv.nterms == 0 or int(sv.arity().max()) <= 1)
+        if not simple(a):
+            a = self._materialise_entries(a)
+        if not a.can_multiply_directly(b) and not simple(b):
+            b = self._materialise_entries(b)
+        return a.mul_simple(b)
+
+    def _materialise_entries(self, sv):
+        """Materialise only the distinct non-trivial entries when the vector is a gather of few."""
+        return self.materialise(sv)
+
+    # ---- variables -----------------------------------------------------------
+    def var_slots(self, v):
+        return SymVec.slot_range(self.var_off[v.attrs["id"]], v.size)
+
+    # =========================================================================
+    # values  (Atom._value_impl / numeric, atoms/atom.py:431-449)
+    # =========================================================================
+    def value(self, node):
+        key = id(node)
+        if key not in self._value_cache:
+            self._value_cache[key] = (node, self._value(node))   # keep node alive for id()
+        return self._value_cache[key][1]
+
+    def _index_array(self, node):
+        return np.arange(node.size, dtype=np.int64).reshape(node.shape, order="F")
+
+    def _value(self, node):
+        op = node.op
+        if op == "var":
+            return self.var_slots(node)
+        if op == "const":
+            return SymVec.const(_flatF(_dense(node.attrs["value"])))
+        a = node.args
+        if op == "add":                                    # affine/add_expr.py:72-73
+            out = None
+            for arg in a:
+                v = self.value(arg)
+                if v.K != node.size:
+                    I = np.broadcast_to(self._index_array(arg), node.shape)
+                    v = v.gather(_flatF(I))
+                out = v if out is None else out.add(v)
+            return out
+        if op == "neg":                                    # affine/unary_operators.py:37
+            return self.value(a[0]).neg()
+        if op == "sum":                                    # affine/sum.py:93-101
+            arg = a[0]
+            v = self.value(arg)
+            if node.attrs["axis"] is None:
+                return v.sum_all()
+            out_keep = np.sum(np.empty(arg.shape), axis=node.attrs["axis"], keepdims=True).shape
+            G = int(np.prod(out_keep, dtype=np.int64))
+            I = np.arange(G, dtype=np.int64).reshape(out_keep, order="F")
+            grp = _flatF(np.broadcast_to(I, arg.shape))
+            return v.group_sum(grp, G)
+        if op == "index":                                  # affine/index.py:88-90
+            I = self._index_array(a[0])[ir.decode_key(node.attrs["orig_key"])]
+            return self.value(a[0]).gather(_flatF(I))
+        if op == "special_index":                          # affine/index.py:194-197
+            return self.value(a[0]).gather(_flatF(node.attrs["select"]))
+        if op == "reshape":                                # affine/reshape.py:102
+            I = np.reshape(self._index_array(a[0]), node.shape, order=node.attrs["order"])
+            return self.value(a[0]).gather(_flatF(I))
+        if op == "transpose":                              # affine/transpose.py:53
+            I = np.transpose(self._index_array(a[0]), node.attrs["axes"])
+            return self.value(a[0]).gather(_flatF(I))
+        if op == "promote":                                # affine/promote.py:68-70
+            return self.value(a[0]).gather(np.zeros(node.size, dtype=np.int64))
+        if op == "broadcast_to":                           # affine/broadcast_to.py:45-46
+            I = np.broadcast_to(self._index_array(a[0]), node.shape)
+            return self.value(a[0]).gather(_flatF(I))
+        if op == "multiply":                               # affine/binary_operators.py:431-438
+            x, y = a
+            if x.is_constant():
+                return self._bcast(self.value(y), y, node).scale(self._const_flat(x, node))
+            if y.is_constant():
+                return self._bcast(self.value(x), x, node).scale(self._const_flat(y, node))
+            return self.mul(self._bcast(self.value(x), x, node), self._bcast(self.value(y), y, node))
+        if op == "matmul":                                 # affine/binary_operators.py:134-140
+            return self._value_matmul(node)
+        if op in T.UNARY_TABLE:
+            return self.elem(T.UNARY_TABLE[op][0], self.value(a[0]))
+        if op == "power":                                  # elementwise/power.py:187-188 (exact p)
+            return self.elem(T.F_POW, self.value(a[0]), param=node.attrs["p"])
+        if op == "rel_entr":                               # elementwise/rel_entr.py:36-40
+            return self.elem(T.F_REL_ENTR, self.value(a[0]), self.value(a[1]))
+        if op == "quad_over_lin":                          # quad_over_lin.py:39-45
+            xv = self.value(a[0])
+            s = self.mul(xv, xv).sum_all()
+            return self.elem(T.F_DIV, s, self.value(a[1]))
+        if op == "quad_form":                              # quad_form.py:41-47
+            xv = self.value(a[0])
+            return self.mul(xv, self.quad_form_Qx(node)).sum_all()
+        raise NotImplementedError(op)
+
+    def _bcast(self, v, arg, node):
+        if v.K == node.size:
+            return v
+        I = np.broadcast_to(self._index_array(arg), node.shape)
+        return v.gather(_flatF(I))
+
+    def _const_flat(self, cnode, node):
+        c = _dense(cnode.attrs["value"])
+        if c.size != node.size:
+            c = np.broadcast_to(c, node.shape)
+        return _flatF(c)
+
+    def quad_form_Qx(self, node):
+        """Q @ x as materialised slots, shared by value and Jacobian of quad_form."""
+        key = ("Qx", id(node))
+        if key not in self._value_cache:
+            x, Q = node.args
+            Qv = Q.attrs["value"]
+            xv = self.value(x)
+            n = x.size
+            if sp.issparse(Qv):
+                c = sp.coo_array(Qv)
+                sv = xv.linear_map(c.coords[0], c.coords[1], c.data, n)
+                out = self.materialise(sv)
+            else:
+                xs = self.materialise(xv)
+                dst = self.tape.alloc(n)
+                ins = T.Instr(T.K_GEMV, dst_off=dst, count=n, ncols=n, x_off=xs.contiguous_start(),
+                              Q=np.ascontiguousarray(np.asarray(Qv, dtype=np.float64)).reshape(n, n),
+                              alpha=1.0)
+                self._finish(ins, np.arange(ins.x_off, ins.x_off + n))
+                out = SymVec.slot_range(dst, n)
+            self._value_cache[key] = (node, out)
+        return self._value_cache[key][1]
+
+    def _kron_map(self, left, right):
+        """COO (rows, cols, data) of kron(left, right) for constant operands."""
+        k = sp.coo_array(sp.kron(left, right, format="coo"))
+        return k.coords[0], k.coords[1], k.data
+
+    def _value_matmul(self, node):
+        X, Y = node.args
+        if X.ndim == 0 or Y.ndim == 0:                     # scalar: values[0] * values[1]
+            return self._value(ir.Node("multiply", [X, Y], node.shape))
+        # NumPy matmul semantics: a 1-D left operand is a row, a 1-D right operand a column;
+        # F-order flattening is unchanged by the added unit dimension.
+        xs = (1, X.shape[0]) if X.ndim == 1 else X.shape
+        ys = (Y.shape[0], 1) if Y.ndim == 1 else Y.shape
+        m, n = xs
+        p = ys[1]
+
+        def as2d(c, shape):
+            v = c.attrs["value"]
+            return v if sp.issparse(v) else sp.csr_array(np.asarray(v, dtype=np.float64).reshape(shape))
+        if X.is_constant():                                # vec(XY) = kron(I_p, X) vec(Y)
+            r, c, d = self._kron_map(sp.eye(p), as2d(X, xs))
+            return self.value(Y).linear_map(r, c, d, node.size)
+        if Y.is_constant():                                # vec(XY) = kron(Y.T, I_m) vec(X)
+            r, c, d = self._kron_map(as2d(Y, ys).T, sp.eye(m))
+            return self.value(X).linear_map(r, c, d, node.size)
+        i, l, j = np.meshgrid(np.arange(m), np.arange(n), np.arange(p), indexing="ij")
+        i, l, j = i.reshape(-1), l.reshape(-1), j.reshape(-1)
+        prod = self.mul(self.value(X).gather(i + l * m), self.value(Y).gather(l + j * n))
+        return prod.group_sum(i + j * m, node.size)
+
+    # =========================================================================
+    # Jacobians  (Atom.jacobian, atoms/atom.py:501-512)
+    # =========================================================================
+    def jac(self, node):
+        if node.op == "var":                               # expressions/variable.py:76-79
+            r = np.arange(node.size, dtype=np.int64)
+            return {node.attrs["id"]: (r, r, SymVec.const(np.ones(node.size)))}
+        if node.is_constant():                             # atoms/atom.py:504-505
+            return {}
+        if not self._verify_jac(node):                     # atoms/atom.py:509-510
+            raise ValueError("Argument error in jacobian for atom %s." % node.op)
+        out = getattr(self, "_jac_" + (node.op if node.op not in T.UNARY_TABLE else "unary"))(node)
+        return {k: (np.asarray(r, dtype=np.int64).reshape(-1), np.asarray(c, dtype=np.int64).reshape(-1), v)
+                for k, (r, c, v) in out.items()}
+
+    def _verify_jac(self, node):
+        op = node.op
+        if op in ir.ELEMENTWISE_UNARY or op == "quad_form":
+            return node.args[0].is_var()
+        if op in ("rel_entr", "multiply"):
+            return self._verify_hess(node)
+        if op == "quad_over_lin":
+            return node.args[0].is_var() and node.args[1].is_var()
+        if op == "matmul":
+            xs = {v.attrs["id"] for v in node.args[0].variables()}
+            return not any(v.attrs["id"] in xs for v in node.args[1].variables())
+        if op == "sum":
+            return node.attrs["axis"] in (None, 0, 1)
+        if op == "reshape":
+            return node.attrs["order"] == "F"
+        if op == "promote":
+            return node.args[0].size == 1
+        if op == "broadcast_to":
+            return len(node.shape) == 2
+        return True
+
+    def _verify_hess(self, node):
+        op = node.op
+        if op in ir.ELEMENTWISE_UNARY or op == "quad_form":
+            return node.args[0].is_var()
+        if op == "rel_entr":
+            x, y = node.args
+            if not (x.size == 1 or y.size == 1 or x.size == y.size):
+                return False
+            return x.is_var() and y.is_var() and not _same_var(x, y)
+        if op == "quad_over_lin":
+            return node.args[0].is_var() and node.args[1].is_var()
+        if op == "multiply":
+            x, y = node.args
+            if x.size != y.size or (x.is_constant() and y.is_constant()):
+                return False
+            both = x.is_var() and y.is_var()
+            ok = both or x.is_constant() or y.is_constant() or \
+                (x.op == "promote" and y.is_var()) or (y.op == "promote" and x.is_var())
+            return ok and not (both and _same_var(x, y))
+        if op == "matmul":
+            X, Y = node.args
+            if not X.is_var() and not X.is_constant() and not Y.is_constant():
+                return False
+            if not Y.is_var() and not Y.is_constant() and not X.is_constant():
+                return False
+            return not _same_var(X, Y)
+        if op == "reshape":
+            return node.attrs["order"] == "F"
+        if op == "broadcast_to":
+            return len(node.shape) == 2
+        return True
+
+    @staticmethod
+    def _broadcast_type(node):                             # affine/broadcast_to.py:84-109
+        m, n = node.shape
+        xs = tuple(node.args[0].shape)
+        xs = (1,) * (2 - len(xs)) + xs
+        kind = None
+        if xs[0] == 1 and xs[1] == n:
+            kind = "row"
+        elif xs[0] == m and xs[1] == 1:
+            kind = "col"
+        if all(s == 1 for s in xs):
+            kind = "scalar"
+        return kind
+
+    @staticmethod
+    def _coo_sum_duplicates(rows, cols, sv):
+        """``coo_matrix.sum_duplicates``: lexsort by (row, col), merge equal pairs."""
+        if sv.K == 0:
+            return rows, cols, sv
+        order = np.lexsort((cols, rows))
+        r, c = rows[order], cols[order]
+        new = np.ones(r.size, dtype=bool)
+        new[1:] = (r[1:] != r[:-1]) | (c[1:] != c[:-1])
+        grp = np.cumsum(new) - 1
+        return r[new], c[new], sv.gather(order).group_sum(grp, int(grp[-1]) + 1)
+
+    def _merge_dicts(self, parts, shape_of):
+        """Shared body of AddExpression._jacobian / _hess_vec (affine/add_expr.py:149-222)."""
+        out, need = {}, set()
+        for d in parts:
+            for k, (r, c, v) in d.items():
+                if k in out:
+                    R, C, V = out[k]
+                    out[k] = (np.concatenate([R, r]), np.concatenate([C, c]), SymVec.concat([V, v]))
+                    need.add(k)
+                else:
+                    out[k] = (np.atleast_1d(r).astype(np.int64), np.atleast_1d(c).astype(np.int64), v)
+        for k in need:
+            out[k] = self._coo_sum_duplicates(*out[k])
+        return out
+
+    def _jac_add(self, node):                              # affine/add_expr.py:190-222
+        return self._merge_dicts([self.jac(a) for a in node.args if not a.is_constant()], None)
+
+    def _jac_neg(self, node):                              # affine/unary_operators.py:129-136
+        return {k: (r, c, v.neg()) for k, (r, c, v) in self.jac(node.args[0]).items()}
+
+    def _jac_sum(self, node):                              # affine/sum.py:165-182
+        arg = node.args[0]
+        out = {}
+        for k, (r, c, v) in self.jac(arg).items():
+            if node.attrs["axis"] is None:
+                r = np.zeros(len(c), dtype=np.int64)
+            else:
+                m = arg.shape[0]
+                r = r // m if node.attrs["axis"] == 0 else r % m
+            out[k] = self._coo_sum_duplicates(r, c, v)
+        return out
+
+    def _jac_index(self, node):                            # affine/index.py:127-150
+        arg = node.args[0]
+        rng = [np.arange(s, (e if e is not None else -1), st) for s, e, st in node.attrs["key"]]
+        if len(rng) == 1:
+            idx = rng[0]
+        elif len(rng) == 2:
+            idx = np.add.outer(rng[0], rng[1] * arg.shape[0]).flatten(order="F")
+        else:
+            raise UnboundLocalError("cannot access local variable 'idx'")
+        pos = np.full(arg.size, -1, dtype=np.int64)
+        pos[idx] = np.arange(idx.size)
+        out = {}
+        for k, (r, c, v) in self.jac(arg).items():
+            keep = np.where(pos[r] >= 0)[0]
+            out[k] = (pos[r[keep]], c[keep], v.gather(keep))
+        return out
+
+    def _tagged_product(self, op_matrix, rows, cols, sv, shape):
+        """(op @ coo(vals)).tocoo() for a 0/1 selection operator: run the same SciPy calls on
+        integer tags so the emitted order is SciPy's own (affine/index.py:264-280)."""
+        rows, cols, sv = self._coo_sum_duplicates(rows, cols, sv)   # coo -> compressed sums duplicates
+        tags = np.arange(1, sv.K + 1, dtype=np.float64)
+        J = sp.coo_array((tags, (rows, cols)), shape=shape)
+        res = (op_matrix @ J).tocoo()
+        src = np.rint(res.data).astype(np.int64) - 1
+        return res.coords[0].astype(np.int64), res.coords[1].astype(np.int64), sv.gather(src)
+
+    def _jac_special_index(self, node):                    # affine/index.py:264-280
+        arg = node.args[0]
+        sel = _flatF(node.attrs["select"])
+        op = sp.eye_array(arg.size, format="csc")[sel]
+        out = {}
+        for k, (r, c, v) in self.jac(arg).items():
+            out[k] = self._tagged_product(op, r, c, v, (arg.size, self.var_size[k]))
+        return out
+
+    def _jac_reshape(self, node):                          # affine/reshape.py:160-161
+        return self.jac(node.args[0])
+
+    def _jac_transpose(self, node):                        # affine/transpose.py:126-133
+        mapping = np.arange(node.size).reshape(node.shape, order="F").T.reshape(-1, order="F")
+        return {k: (mapping[r], c, v) for k, (r, c, v) in self.jac(node.args[0]).items()}
+
+    def _jac_promote(self, node):                          # affine/promote.py:126-135
+        size = node.size
+        out = {}
+        for k, (_, c, v) in self.jac(node.args[0]).items():
+            rows = np.repeat(np.arange(size, dtype=np.int64), len(c))
+            out[k] = (rows, np.tile(c, size), v.gather(np.tile(np.arange(v.K), size)))
+        return out
+
+    def _jac_broadcast_to(self, node):                     # affine/broadcast_to.py:111-176
+        m, n = node.shape
+        kind = self._broadcast_type(node)
+        out = {}
+        for k, (r, c, v) in self.jac(node.args[0]).items():
+            e = np.arange(v.K)
+            if kind == "row":
+                out[k] = (np.repeat(r * m, m) + np.tile(np.arange(m), len(r)), np.repeat(c, m),
+                          v.gather(np.repeat(e, m)))
+            elif kind == "col":
+                out[k] = (np.repeat(r, n) + np.tile(np.arange(n) * m, len(r)), np.repeat(c, n),
+                          v.gather(np.repeat(e, n)))
+            elif kind == "scalar":
+                out[k] = (np.tile(np.arange(m * n), len(r)), np.repeat(c, m * n),
+                          v.gather(np.repeat(e, m * n)))
+            else:
+                raise NotImplementedError("Jacobian not implemented for broadcast_to.")
+        return out
+
+    def _jac_multiply(self, node):                         # affine/binary_operators.py:552-591
+        x, y = node.args
+        if x.is_constant():
+            xv = _flatF(np.atleast_1d(_dense(x.attrs["value"])))
+            return {k: (r, c, v.scale(xv[r])) for k, (r, c, v) in self.jac(y).items()}
+        if y.is_constant():
+            yv = _flatF(np.atleast_1d(_dense(y.attrs["value"])))
+            return {k: (r, c, v.scale(yv[r])) for k, (r, c, v) in self.jac(x).items()}
+        if not x.is_var() and x.is_affine():
+            xvar = x.args[0]
+            idxs = np.arange(y.size, dtype=np.int64)
+            return {xvar.attrs["id"]: (idxs, np.zeros(y.size, dtype=np.int64), self.value(y)),
+                    y.attrs["id"]: (idxs, idxs, self.value(x))}
+        if not y.is_var() and y.is_affine():
+            yvar = y.args[0]
+            idxs = np.arange(x.size, dtype=np.int64)
+            return {x.attrs["id"]: (idxs, idxs, self.value(y)),
+                    yvar.attrs["id"]: (idxs, np.zeros(x.size, dtype=np.int64), self.value(x))}
+        idxs = np.arange(x.size, dtype=np.int64)
+        return {x.attrs["id"]: (idxs, idxs, self.value(y)), y.attrs["id"]: (idxs, idxs, self.value(x))}
+
+    # -- matmul: kron structure through SciPy with tags (binary_operators.py:309-369) --
+    def _tag_matrix(self, operand, sv):
+        """Dense/sparse matrix whose nonzeros carry 1-based tags into ``sv``; entries the
+        reference would drop when building kron from ``operand.value`` are 0."""
+        shape = _dims(operand)
+        if operand.is_constant() and sp.issparse(operand.attrs["value"]):
+            c = sp.coo_array(operand.attrs["value"])
+            flat = c.coords[0] + c.coords[1] * shape[0]
+            return sp.coo_array((flat + 1.0, (c.coords[0], c.coords[1])), shape=shape)
+        keep = np.ones(sv.K, dtype=bool)
+        cm = sv.is_const_mask()
+        keep[cm] = sv.const_values()[cm] != 0.0
+        tags = np.where(keep, np.arange(1, sv.K + 1, dtype=np.float64), 0.0)
+        # keep the operand's own shape: SciPy treats a 1-D value as a row, as in the reference
+        return tags.reshape(operand.shape, order="F")
+
+    def _chain_through(self, kron_csr_tags, opval, inner_jac, inner_size):
+        """(d @ inner_jac.tocsc()).tocoo() with symbolic values.
+
+        Order: SciPy's own sparse product on the two patterns.  Values: every output
+        (i, j) is sum_k d[i, k] * J[k, j], expanded and grouped symbolically.
+        """
+        out = {}
+        A = kron_csr_tags.tocsr()
+        a_src = np.rint(A.data).astype(np.int64) - 1
+        a_rows = np.repeat(np.arange(A.shape[0], dtype=np.int64), np.diff(A.indptr))
+        a_cols = A.indices.astype(np.int64)
+        A1 = sp.csr_array((np.ones(A.nnz), A.indices, A.indptr), shape=A.shape)
+        for var, (r, c, v) in inner_jac.items():
+            ncols = self.var_size[var]
+            B1 = sp.coo_array((np.ones(len(r)), (r, c)), shape=(A.shape[1], ncols)).tocsc()
+            B1.data[:] = 1.0
+            P = (A1 @ B1).tocoo()
+            prow, pcol = P.coords[0].astype(np.int64), P.coords[1].astype(np.int64)
+            # symbolic values
+            br, bc, bv = self._coo_sum_duplicates(np.asarray(r, np.int64), np.asarray(c, np.int64), v)
+            order = np.argsort(br, kind="stable")
+            br, bc, bv = br[order], bc[order], bv.gather(order)
+            bptr = np.zeros(A.shape[1] + 1, dtype=np.int64)
+            np.cumsum(np.bincount(br, minlength=A.shape[1]), out=bptr[1:])
+            cnt = bptr[a_cols + 1] - bptr[a_cols]
+            ea = np.repeat(np.arange(A.nnz, dtype=np.int64), cnt)
+            optr = np.zeros(A.nnz + 1, dtype=np.int64)
+            np.cumsum(cnt, out=optr[1:])
+            eb = np.repeat(bptr[a_cols], cnt) + (np.arange(int(cnt.sum()), dtype=np.int64) - np.repeat(optr[:-1], cnt))
+            prod = self.mul(opval.gather(a_src[ea]), bv.gather(eb))
+            key = a_rows[ea] * ncols + bc[eb]
+            pkey = prow * ncols + pcol
+            sorter = np.argsort(pkey)
+            grp = sorter[np.searchsorted(pkey, key, sorter=sorter)]
+            vals = prod.group_sum(grp, pkey.size)
+            # SciPy's product drops results that are exactly zero; only compile-time constants can be
+            cm = vals.is_const_mask()
+            drop = cm & (vals.const_values() == 0.0)
+            if drop.any():
+                keep = np.where(~drop)[0]
+                prow, pcol, vals = prow[keep], pcol[keep], vals.gather(keep)
+            out[var] = (prow, pcol, vals)
+        return out
+
+    def _jac_matmul(self, node):
+        X, Y = node.args
+        m, _ = _dims(X)
+        _, p = _dims(Y)
+        dx_dict, dy_dict = {}, {}
+        if not X.is_constant():
+            yv = self.value(Y)
+            Tm = self._tag_matrix(Y, yv)
+            dx = sp.kron(Tm.T, sp.eye(m), format="csr")
+            if not X.is_var():
+                dx_dict = self._chain_through(dx, yv, self.jac(X), X.size)
+            else:
+                d = dx.tocoo()
+                dx_dict = {X.attrs["id"]: (d.row.astype(np.int64), d.col.astype(np.int64),
+                                            yv.gather(np.rint(d.data).astype(np.int64) - 1))}
+        if not Y.is_constant():
+            xv = self.value(X)
+            Tm = self._tag_matrix(X, xv)
+            dy = sp.kron(sp.eye(p), Tm, format="csr")
+            if not Y.is_var():
+                dy_dict = self._chain_through(dy, xv, self.jac(Y), Y.size)
+            else:
+                d = dy.tocoo()
+                dy_dict = {Y.attrs["id"]: (d.row.astype(np.int64), d.col.astype(np.int64),
+                                            xv.gather(np.rint(d.data).astype(np.int64) - 1))}
+        if X.is_constant() and not Y.is_constant():
+            return dy_dict
+        if not X.is_constant() and Y.is_constant():
+            return dx_dict
+        dx_dict.update(dy_dict)
+        return dx_dict
+
+    def _jac_unary(self, node):                            # e.g. elementwise/exp.py:112-121
+        x = node.args[0]
+        idxs = np.arange(x.size, dtype=np.int64)
+        return {x.attrs["id"]: (idxs, idxs, self.elem(T.UNARY_TABLE[node.op][1], self.var_slots(x)))}
+
+    def _jac_power(self, node):                            # elementwise/power.py:433-449
+        p = node.attrs["p_rational"] if node.attrs["p_rational"] is not None else node.attrs["p"]
+        if p == 0:
+            return {}
+        x = node.args[0]
+        idxs = np.arange(x.size, dtype=np.int64)
+        vals = self.elem(T.F_POW, self.var_slots(x), param=float(p) - 1).scale(float(p))
+        return {x.attrs["id"]: (idxs, idxs, vals)}
+
+    def _jac_rel_entr(self, node):                         # elementwise/rel_entr.py:129-148
+        x, y = node.args
+        xs, ys = self.var_slots(x), self.var_slots(y)
+        dx = self.elem(T.F_LOG_RATIO_P1, xs, ys)
+        dy = self.elem(T.F_DIV, xs, ys).neg()
+        z = np.array([0], dtype=np.int64)
+        if x.size == 1:
+            idxs = np.arange(y.size, dtype=np.int64)
+            return {x.attrs["id"]: (z, z, dx.sum_all()), y.attrs["id"]: (idxs, idxs, dy)}
+        if y.size == 1:
+            idxs = np.arange(x.size, dtype=np.int64)
+            return {x.attrs["id"]: (idxs, idxs, dx), y.attrs["id"]: (z, z, dy.sum_all())}
+        idxs = np.arange(x.size, dtype=np.int64)
+        return {x.attrs["id"]: (idxs, idxs, dx), y.attrs["id"]: (idxs, idxs, dy)}
+
+    def _sumsq(self, x):
+        xs = self.var_slots(x)
+        return self.materialise(xs.mul_simple(xs).sum_all())
+
+    def _jac_quad_over_lin(self, node):                    # quad_over_lin.py:178-185
+        x, y = node.args
+        xs, ys = self.var_slots(x), self.var_slots(y)
+        idxs = np.arange(x.size, dtype=np.int64)
+        dx = self.elem(T.F_DIV, xs, ys).scale(2.0)
+        dy = self.elem(T.F_DIV_SQ, self._sumsq(x), ys).neg()
+        z = np.array([0], dtype=np.int64)
+        return {x.attrs["id"]: (np.zeros(x.size, dtype=np.int64), idxs, dx), y.attrs["id"]: (z, z, dy)}
+
+    def _jac_quad_form(self, node):                        # quad_form.py:154-160
+        x = node.args[0]
+        return {x.attrs["id"]: (np.zeros(x.size, dtype=np.int64), np.arange(x.size, dtype=np.int64),
+                                self.quad_form_Qx(node).scale(2.0))}
+
+    # =========================================================================
+    # Hessian-vector products  (Atom.hess_vec, atoms/atom.py:515-561)
+    # =========================================================================
+    def hv(self, node, vec):
+        if node.op in ("var", "const"):                    # variable.py:73-74, constant.py:119-125
+            return {}
+        if vec.K != node.size:                             # atoms/atom.py:546-548
+            raise ValueError("Dimension mismatch in hess_vec. vec.size != phi(x).size")
+        if node.is_affine():                               # atoms/atom.py:551-552
+            return {}
+        if not self._verify_hess(node):                    # atoms/atom.py:556-559
+            raise ValueError("Argument error in hess_vec for atom %s." % node.op)
+        return self._hv_inner(node, vec)
+
+    def _hv_inner(self, node, vec):
+        if node.op == "var":
+            raise AttributeError("'Variable' object has no attribute '_hess_vec'")
+        return getattr(self, "_hv_" + (node.op if node.op not in T.UNARY_TABLE else "unary"))(node, vec)
+
+    def _hv_add(self, node, vec):                          # affine/add_expr.py:149-184
+        return self._merge_dicts([self.hv(a, vec) for a in node.args if not a.is_affine()], None)
+
+    def _hv_neg(self, node, vec):                          # affine/unary_operators.py:122-124
+        return self.hv(node.args[0], vec.neg())
+
+    def _hv_sum(self, node, vec):                          # affine/sum.py:146-156
+        arg = node.args[0]
+        if node.attrs["axis"] is None:
+            return self.hv(arg, vec.gather(np.zeros(arg.size, dtype=np.int64)))
+        m, n = arg.shape
+        e = np.arange(vec.K)
+        rep = np.repeat(e, m) if node.attrs["axis"] == 0 else np.tile(e, n)
+        return self.hv(arg, vec.gather(rep))
+
+    def _scatter_assign(self, size, pos, vec):
+        """``e = zeros(size); e[pos] = vec`` with NumPy's last-write-wins on repeats."""
+        pos = np.asarray(pos, dtype=np.int64).reshape(-1)
+        if vec.K != pos.size:
+            if vec.K == 1:
+                vec = vec.gather(np.zeros(pos.size, dtype=np.int64))
+            else:
+                raise ValueError("shape mismatch: value array could not be broadcast to indexing result")
+        last = np.full(size, -1, dtype=np.int64)
+        last[pos] = np.arange(pos.size)
+        src = np.where(last >= 0)[0]
+        return vec.gather(last[src]).scatter_into(size, src)
+
+    def _hv_index(self, node, vec):                        # affine/index.py:120-125 (flat scatter, Q6)
+        arg = node.args[0]
+        pos = np.arange(arg.size, dtype=np.int64)[ir.decode_key(node.attrs["orig_key"])]
+        return self.hv(arg, self._scatter_assign(arg.size, pos, vec))
+
+    def _hv_special_index(self, node, vec):                # affine/index.py:254-258
+        arg = node.args[0]
+        return self.hv(arg, self._scatter_assign(arg.size, _flatF(node.attrs["select"]), vec))
+
+    def _hv_reshape(self, node, vec):                      # affine/reshape.py:166-167
+        return self.hv(node.args[0], vec)
+
+    def _hv_transpose(self, node, vec):                    # affine/transpose.py:119-123
+        I = np.arange(node.size).reshape(node.shape, order="F").T.reshape(-1, order="F")
+        return self.hv(node.args[0], vec.gather(I))
+
+    def _hv_promote(self, node, vec):                      # affine/promote.py:120-121
+        return self._hv_inner(node.args[0], vec.sum_all())
+
+    def _hv_broadcast_to(self, node, vec):                 # affine/broadcast_to.py:181-192
+        m, n = node.shape
+        kind = self._broadcast_type(node)
+        e = np.arange(vec.K)
+        if kind == "row":
+            return self._hv_inner(node.args[0], vec.group_sum(e // m, n))
+        if kind == "col":
+            return self._hv_inner(node.args[0], vec.group_sum(e % m, m))
+        if kind == "scalar":
+            return self._hv_inner(node.args[0], vec.sum_all())
+        raise NotImplementedError("hess-vec not implemented for broadcast_to.")
+
+    def _hv_multiply(self, node, vec):                     # affine/binary_operators.py:511-546
+        x, y = node.args
+        if x.is_constant():
+            return self.hv(y, vec.scale(_flatF(_dense(x.attrs["value"]))))
+        if y.is_constant():
+            return self.hv(x, vec.scale(_flatF(_dense(y.attrs["value"]))))
+        xi = lambda v: v.attrs["id"]  # noqa: E731
+        if not x.is_var() and x.is_affine():
+            xvar = x.args[0]
+            z = np.zeros(xvar.size, dtype=np.int64)
+            c = np.arange(y.size, dtype=np.int64)
+            return {(xi(xvar), xi(y)): (z, c, vec), (xi(y), xi(xvar)): (c, z, vec)}
+        if not y.is_var() and y.is_affine():
+            yvar = y.args[0]
+            z = np.zeros(yvar.size, dtype=np.int64)
+            c = np.arange(x.size, dtype=np.int64)
+            return {(xi(x), xi(yvar)): (c, z, vec), (xi(yvar), xi(x)): (z, c, vec)}
+        r = np.arange(x.size, dtype=np.int64)
+        return {(xi(x), xi(y)): (r, r, vec), (xi(y), xi(x)): (r, r, vec)}
+
+    def _hv_matmul(self, node, vec):                       # affine/binary_operators.py:261-282
+        X, Y = node.args
+        m, n = _dims(X)
+        _, p = _dims(Y)
+        if (X.is_constant() or Y.is_constant()) and vec.K != m * p:
+            raise ValueError("cannot reshape array of size %d into shape (%d,%d)" % (vec.K, m, p))
+        if X.is_constant():      # B = X.T @ reshape(vec, (m, p));  vec(B) = kron(I_p, X.T) vec
+            Xd = X.attrs["value"]
+            Xs = Xd if sp.issparse(Xd) else sp.csr_array(np.asarray(Xd, dtype=np.float64).reshape(m, n))
+            r, c, d = self._kron_map(sp.eye(p), Xs.T)
+            return self.hv(Y, vec.linear_map(r, c, d, n * p))
+        if Y.is_constant():      # B = reshape(vec, (m, p)) @ Y.T;  vec(B) = kron(Y, I_m) vec
+            Yd = Y.attrs["value"]
+            Ys = Yd if sp.issparse(Yd) else sp.csr_array(np.asarray(Yd, dtype=np.float64).reshape(n, p))
+            r, c, d = self._kron_map(Ys, sp.eye(m))
+            return self.hv(X, vec.linear_map(r, c, d, m * n))
+        rows = np.tile(np.arange(m * n, dtype=np.int64), p)
+        cols = np.repeat(np.arange(n * p, dtype=np.int64), m)
+        vals = vec.gather((cols // n) * m + (rows % m))
+        xi, yi = X.attrs["id"], Y.attrs["id"]
+        return {(xi, yi): (rows, cols, vals), (yi, xi): (cols, rows, vals)}
+
+    def _hv_unary(self, node, vec):                        # e.g. elementwise/exp.py:102-107
+        x = node.args[0]
+        idxs = np.arange(x.size, dtype=np.int64)
+        d2 = self.elem(T.UNARY_TABLE[node.op][2], self.var_slots(x))
+        return {(x.attrs["id"], x.attrs["id"]): (idxs, idxs, self.mul(d2, vec))}
+
+    def _hv_power(self, node, vec):                        # elementwise/power.py:408-422
+        p = node.attrs["p_rational"] if node.attrs["p_rational"] is not None else node.attrs["p"]
+        if p == 0 or p == 1:
+            return {}
+        x = node.args[0]
+        idxs = np.arange(x.size, dtype=np.int64)
+        d2 = self.elem(T.F_POW, self.var_slots(x), param=float(p) - 2).scale(float(p) * float(p - 1))
+        return {(x.attrs["id"], x.attrs["id"]): (idxs, idxs, self.mul(d2, vec))}
+
+    def _hv_rel_entr(self, node, vec):                     # elementwise/rel_entr.py:150-180
+        x, y = node.args
+        xi, yi = x.attrs["id"], y.attrs["id"]
+        xs, ys = self.var_slots(x), self.var_slots(y)
+        dx2 = self.mul(vec, self.elem(T.F_RECIP, xs))
+        dy2 = self.mul(vec, self.elem(T.F_DIV_SQ, xs, ys))
+        dxdy = self.mul(vec, self.elem(T.F_RECIP, ys)).neg()
+        z1 = np.array([0], dtype=np.int64)
+        if x.size == 1:
+            idxs = np.arange(y.size, dtype=np.int64)
+            zy = np.zeros(y.size, dtype=np.int64)
+            return {(xi, xi): (z1, z1, dx2.sum_all()), (yi, yi): (idxs, idxs, dy2),
+                    (xi, yi): (zy, idxs, dxdy), (yi, xi): (idxs, zy, dxdy)}
+        if y.size == 1:
+            idxs = np.arange(x.size, dtype=np.int64)
+            zx = np.zeros(x.size, dtype=np.int64)
+            return {(xi, xi): (idxs, idxs, dx2), (yi, yi): (z1, z1, dy2.sum_all()),
+                    (xi, yi): (idxs, zx, dxdy), (yi, xi): (zx, idxs, dxdy)}
+        idxs = np.arange(x.size, dtype=np.int64)
+        return {(xi, xi): (idxs, idxs, dx2), (yi, yi): (idxs, idxs, dy2),
+                (xi, yi): (idxs, idxs, dxdy), (yi, xi): (idxs, idxs, dxdy)}
+
+    def _hv_quad_over_lin(self, node, vec):                # quad_over_lin.py:162-173
+        x, y = node.args
+        xi, yi = x.attrs["id"], y.attrs["id"]
+        xs, ys = self.var_slots(x), self.var_slots(y)
+        idxs = np.arange(x.size, dtype=np.int64)
+        zx = np.zeros(x.size, dtype=np.int64)
+        dx2 = self.mul(vec, self.elem(T.F_RECIP, ys)).scale(2.0).gather(zx)
+        dy2 = self.mul(vec, self.elem(T.F_DIV_CUBE, self._sumsq(x), ys)).scale(2.0)
+        dxdy = self.mul(vec, self.elem(T.F_DIV_SQ, xs, ys)).scale(-2.0)
+        z = np.array([0], dtype=np.int64)
+        return {(xi, xi): (idxs, idxs, dx2), (yi, yi): (z, z, dy2),
+                (xi, yi): (idxs, zx, dxdy), (yi, xi): (zx, idxs, dxdy)}
+
+    def _hv_quad_form(self, node, vec):                    # quad_form.py:143-149
+        x, Q = node.args
+        Qc = sp.coo_matrix(Q.attrs["value"])
+        vals = vec.gather(np.zeros(Qc.nnz, dtype=np.int64)).scale(2.0 * Qc.data)
+        return {(x.attrs["id"], x.attrs["id"]): (Qc.row.astype(np.int64), Qc.col.astype(np.int64), vals)}
