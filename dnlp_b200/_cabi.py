@@ -1,0 +1,207 @@
+"""ctypes binding of libdnlp_b200.so (the C-ABI declared in include/dnlp_b200.h).
+
+There is no CPU fallback: if the shared library is missing, cannot be loaded, or no CUDA
+device is visible, creating an oracle raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import tape as T
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libdnlp_b200.so")
+
+PROG_IDS = {"f": 0, "grad": 1, "g": 2, "jac": 3, "hess": 4, "all": 5}
+NPROG = 6
+
+c_i64p = C.POINTER(C.c_int64)
+c_i32p = C.POINTER(C.c_int32)
+c_f64p = C.POINTER(C.c_double)
+c_f32p = C.POINTER(C.c_float)
+
+
+class InstrDesc(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32), ("dst_space", C.c_int32), ("dst_off", C.c_int64), ("count", C.c_int64),
+        ("fcode", C.c_int32), ("a_stride", C.c_int32), ("b_stride", C.c_int32), ("accumulate", C.c_int32),
+        ("param", C.c_double), ("a_off", C.c_int64), ("b_off", C.c_int64),
+        ("ptr", c_i64p), ("coef", c_f64p), ("f1", c_i32p), ("f2", c_i32p), ("pos", c_i32p),
+        ("nterms", C.c_int64), ("row_len", C.c_int32), ("uses_lam", C.c_int32),
+        ("Q", c_f64p), ("ncols", C.c_int64), ("x_off", C.c_int64), ("alpha", C.c_double),
+        ("s_slot", C.c_int64),
+    ]
+
+
+class TapeDesc(C.Structure):
+    _fields_ = [
+        ("n", C.c_int64), ("m", C.c_int64), ("nslots", C.c_int64), ("nnz_jac", C.c_int64), ("nnz_hess", C.c_int64),
+        ("n_instr", C.c_int32), ("instrs", C.POINTER(InstrDesc)),
+        ("prog", c_i32p * NPROG), ("prog_len", C.c_int32 * NPROG),
+        ("f_const", C.c_double), ("grad_const", c_f64p), ("g_const", c_f64p),
+        ("jac_const", c_f64p), ("hess_const", c_f64p),
+    ]
+
+
+EXPORTS = [
+    "dnlp_device_count", "dnlp_version", "dnlp_create", "dnlp_destroy", "dnlp_last_error",
+    "dnlp_eval_f", "dnlp_eval_grad", "dnlp_eval_g", "dnlp_eval_jac", "dnlp_eval_hess", "dnlp_eval_all",
+    "dnlp_host_alloc", "dnlp_host_free", "dnlp_upload_point", "dnlp_run_device", "dnlp_profile_instrs",
+    "dnlp_read_output", "dnlp_kernel_launches", "dnlp_set_cache",
+]
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library (raises if it has not been built: no silent fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "dnlp_b200: %s is missing - build it with `python -m dnlp_b200.build` "
+            "(there is no CPU fallback for the oracle)" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    L.dnlp_device_count.restype = C.c_int
+    L.dnlp_version.restype = C.c_char_p
+    L.dnlp_create.argtypes = [C.POINTER(TapeDesc), C.c_int, C.POINTER(vp)]
+    L.dnlp_destroy.argtypes = [vp]
+    L.dnlp_destroy.restype = None
+    L.dnlp_last_error.argtypes = [vp]
+    L.dnlp_last_error.restype = C.c_char_p
+    L.dnlp_eval_f.argtypes = [vp, c_f64p, c_f64p]
+    L.dnlp_eval_grad.argtypes = [vp, c_f64p, c_f64p]
+    L.dnlp_eval_g.argtypes = [vp, c_f64p, c_f64p]
+    L.dnlp_eval_jac.argtypes = [vp, c_f64p, c_f64p]
+    L.dnlp_eval_hess.argtypes = [vp, c_f64p, c_f64p, C.c_double, c_f64p]
+    L.dnlp_eval_all.argtypes = [vp, c_f64p, c_f64p, C.c_double] + [c_f64p] * 5
+    L.dnlp_host_alloc.argtypes = [C.c_int64]
+    L.dnlp_host_alloc.restype = vp
+    L.dnlp_host_free.argtypes = [vp]
+    L.dnlp_host_free.restype = None
+    L.dnlp_upload_point.argtypes = [vp, c_f64p, c_f64p, C.c_double]
+    L.dnlp_run_device.argtypes = [vp, C.c_int32, C.c_int32, c_f32p]
+    L.dnlp_profile_instrs.argtypes = [vp, C.c_int32, C.c_int32, c_f32p]
+    L.dnlp_read_output.argtypes = [vp, C.c_int32, c_f64p]
+    L.dnlp_kernel_launches.argtypes = [vp]
+    L.dnlp_kernel_launches.restype = C.c_int64
+    L.dnlp_set_cache.argtypes = [vp, C.c_int32]
+    _lib = L
+    return L
+
+
+def device_count():
+    return int(lib().dnlp_device_count())
+
+
+def _p(arr, typ):
+    return None if arr is None else arr.ctypes.data_as(typ)
+
+
+def f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def pinned_empty(count):
+    """float64 NumPy array backed by cudaMallocHost memory (freed with the returned handle)."""
+    L = lib()
+    nbytes = max(int(count), 1) * 8
+    ptr = L.dnlp_host_alloc(nbytes)
+    if not ptr:
+        raise MemoryError("cudaMallocHost(%d) failed" % nbytes)
+    buf = (C.c_double * max(int(count), 1)).from_address(ptr)
+    arr = np.frombuffer(buf, dtype=np.float64, count=int(count))
+    return arr, _PinnedHandle(ptr)
+
+
+class _PinnedHandle:
+    def __init__(self, ptr):
+        self.ptr = ptr
+
+    def free(self):
+        if self.ptr:
+            lib().dnlp_host_free(self.ptr)
+            self.ptr = None
+
+
+class DeviceTape:
+    """Uploads a compiled ``Tape`` and owns the ``dnlp_oracle`` handle."""
+
+    def __init__(self, tape, device=0):
+        L = lib()
+        if L.dnlp_device_count() <= 0:
+            raise RuntimeError("dnlp_b200: no CUDA device visible (the oracle has no CPU fallback)")
+        self.tape = tape
+        self._keep = []
+        n_instr = len(tape.instrs)
+        arr = (InstrDesc * max(n_instr, 1))()
+        for i, ins in enumerate(tape.instrs):
+            d = arr[i]
+            d.kind, d.dst_space, d.dst_off, d.count = ins.kind, ins.dst_space, int(ins.dst_off), int(ins.count)
+            d.fcode, d.a_stride, d.b_stride = int(ins.fcode), int(ins.a_stride), int(ins.b_stride)
+            d.accumulate = int(bool(ins.accumulate))
+            d.param, d.a_off, d.b_off = float(ins.param), int(ins.a_off), int(ins.b_off)
+            d.uses_lam = int(bool(ins.uses_lam))
+            d.alpha, d.ncols, d.x_off, d.s_slot = float(ins.alpha), int(ins.ncols), int(ins.x_off), int(ins.s_slot)
+            if ins.kind == T.K_POLY:
+                lens = np.diff(ins.ptr)
+                uniform = lens.size > 0 and bool(np.all(lens == lens[0])) and lens[0] >= 1
+                coef = f64(ins.coef)
+                f1 = np.ascontiguousarray(ins.f1, dtype=np.int32)
+                has_f2 = bool(np.any(ins.f2 >= 0))
+                f2 = np.ascontiguousarray(ins.f2, dtype=np.int32) if has_f2 else None
+                ptr = None if uniform else np.ascontiguousarray(ins.ptr, dtype=np.int64)
+                self._keep += [coef, f1, f2, ptr]
+                d.ptr, d.coef, d.f1, d.f2 = _p(ptr, c_i64p), _p(coef, c_f64p), _p(f1, c_i32p), _p(f2, c_i32p)
+                d.nterms = int(coef.size)
+                d.row_len = int(lens[0]) if uniform else 0
+            elif ins.kind == T.K_GEMV:
+                Q = f64(ins.Q)
+                self._keep.append(Q)
+                d.Q = _p(Q, c_f64p)
+            elif ins.kind == T.K_SCALE:
+                coef = f64(ins.coef)
+                self._keep.append(coef)
+                d.coef = _p(coef, c_f64p)
+            if ins.pos is not None:
+                pos = np.ascontiguousarray(ins.pos, dtype=np.int32)
+                self._keep.append(pos)
+                d.pos = _p(pos, c_i32p)
+        td = TapeDesc()
+        td.n, td.m, td.nslots = tape.n, tape.m, tape.nslots
+        td.nnz_jac, td.nnz_hess = int(tape.jac_rows.size), int(tape.hess_rows.size)
+        td.n_instr, td.instrs = n_instr, arr
+        for name, pid in PROG_IDS.items():
+            p = np.ascontiguousarray(tape.programs.get(name, []), dtype=np.int32)
+            self._keep.append(p)
+            td.prog[pid] = _p(p, c_i32p) if p.size else None
+            td.prog_len[pid] = int(p.size)
+        consts = [f64(tape.grad_const), f64(tape.g_const), f64(tape.jac_const), f64(tape.hess_const)]
+        self._keep += consts
+        td.f_const = float(tape.f_const)
+        td.grad_const, td.g_const, td.jac_const, td.hess_const = [_p(c, c_f64p) if c.size else None for c in consts]
+        self._keep += [arr, td]
+        h = C.c_void_p()
+        if L.dnlp_create(C.byref(td), int(device), C.byref(h)) != 0:
+            raise RuntimeError("dnlp_create failed: %s" % L.dnlp_last_error(None).decode())
+        self.h = h
+        self._L = L
+        self._keep = [arr, td]   # host staging copies are no longer needed after upload
+
+    def check(self, rc):
+        if rc != 0:
+            raise RuntimeError("dnlp_b200: %s" % self._L.dnlp_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._L.dnlp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,459 @@
+// C-ABI implementation of the B200 NLP oracle (see include/dnlp_b200.h).
+//
+// Host side of the tape: owns HBM buffers (value buffer V, the tape's index/coefficient arrays,
+// the five output arrays), one CUDA stream, and the per-x instruction cache.  No torch types,
+// no exceptions across the ABI, no CPU evaluation path: every number returned was produced by
+// the kernels in dnlp_kernels.cuh.
+#include "../../include/dnlp_b200.h"
+#include "dnlp_kernels.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_create_error;
+
+#define CK(call)                                                                           \
+  do {                                                                                     \
+    cudaError_t e_ = (call);                                                               \
+    if (e_ != cudaSuccess) {                                                               \
+      char buf_[512];                                                                      \
+      snprintf(buf_, sizeof buf_, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,      \
+               cudaGetErrorString(e_));                                                    \
+      err = buf_;                                                                          \
+      return 1;                                                                            \
+    }                                                                                      \
+  } while (0)
+
+struct DevInstr {
+  dnlp_instr_desc d;       // pointers rewritten to device memory
+  double mean_len = 1.0;
+  bool has_f2 = false;
+};
+
+}  // namespace
+
+struct dnlp_oracle {
+  int device = 0;
+  int sm_count = 148;
+  int64_t n = 0, m = 0, nslots = 0, nnz_jac = 0, nnz_hess = 0;
+  cudaStream_t stream = nullptr;
+  double *V = nullptr;
+  double *out[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int64_t out_len[6] = {0, 0, 0, 0, 0, 0};
+  std::vector<DevInstr> instrs;
+  std::vector<int32_t> prog[DNLP_NPROG];
+  std::vector<void *> owned;           // device allocations to free
+  std::vector<uint8_t> valid;          // per instruction: result valid for the current x
+  std::vector<double> last_x;          // host copy of the last uploaded point (small n only)
+  bool have_last_x = false;
+  bool cache_enabled = true;
+  int64_t launches = 0;
+  std::string err;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+  template <typename T>
+  int upload(const T *host, int64_t count, T **dev) {
+    *dev = nullptr;
+    if (count <= 0 || host == nullptr) return 0;
+    void *p = nullptr;
+    CK(cudaMalloc(&p, (size_t)count * sizeof(T)));
+    owned.push_back(p);
+    CK(cudaMemcpy(p, host, (size_t)count * sizeof(T), cudaMemcpyHostToDevice));
+    *dev = static_cast<T *>(p);
+    return 0;
+  }
+
+  int grid_for(int64_t work_items, int threads_per_item, int block = 256) const {
+    // enough CTAs to cover the work once, capped at a few resident waves: sizes are multiples of
+    // the SM count so no partial wave is left on the two dies.
+    int64_t need = (work_items * threads_per_item + block - 1) / block;
+    int64_t cap = (int64_t)sm_count * 8;   // 8 x 256 threads = 2048 = full occupancy per SM
+    if (need >= cap) return (int)cap;
+    if (need < 1) need = 1;
+    if (need > sm_count) need = ((need + sm_count - 1) / sm_count) * sm_count;
+    return (int)need;
+  }
+
+  int launch(const DevInstr &I);
+  int run_program(int p, bool force);
+  int put_x(const double *x);
+  int put_lam(const double *lam, double sigma);
+  int fetch(int space, double *host);
+};
+
+// ------------------------------------------------------------------------------------------
+// kernel dispatch
+// ------------------------------------------------------------------------------------------
+namespace {
+
+using namespace dnlp;
+
+template <int F, bool B>
+void launch_elem_t(const dnlp_oracle *o, const dnlp_instr_desc &d, int grid) {
+  elem_kernel<F, B><<<grid, 256, 0, o->stream>>>(o->V, d.a_off, d.a_stride, d.b_off, d.b_stride,
+                                                d.dst_off, d.count, d.param);
+}
+
+bool launch_elem(const dnlp_oracle *o, const dnlp_instr_desc &d, int grid) {
+  switch (d.fcode) {
+#define U(F) case F: launch_elem_t<F, false>(o, d, grid); return true;
+#define Bn(F) case F: launch_elem_t<F, true>(o, d, grid); return true;
+    U(F_EXP) U(F_LOG) U(F_ENTR) U(F_NEG_LOG_M1) U(F_RECIP) U(F_NEG_RECIP) U(F_NEG_RECIP_SQ)
+    U(F_LOGISTIC) U(F_LOGISTIC_D1) U(F_LOGISTIC_D2) U(F_POW)
+    U(F_SIN) U(F_COS) U(F_NEG_SIN) U(F_NEG_COS) U(F_TAN) U(F_TAN_D1) U(F_TAN_D2)
+    U(F_SINH) U(F_COSH) U(F_TANH) U(F_TANH_D1) U(F_TANH_D2)
+    U(F_ASINH) U(F_ASINH_D1) U(F_ASINH_D2) U(F_ATANH) U(F_ATANH_D1) U(F_ATANH_D2)
+    U(F_XEXP) U(F_XEXP_D1) U(F_XEXP_D2)
+    Bn(F_REL_ENTR) Bn(F_LOG_RATIO_P1) Bn(F_DIV) Bn(F_DIV_SQ) Bn(F_DIV_CUBE)
+#undef U
+#undef Bn
+    default: return false;
+  }
+}
+
+template <int G>
+void launch_poly_g(const dnlp_oracle *o, const DevInstr &I, double *dst, int grid) {
+  const dnlp_instr_desc &d = I.d;
+  const bool uni = d.ptr == nullptr;
+#define LP(H, Un)                                                                                \
+  poly_kernel<G, H, Un><<<grid, 256, 0, o->stream>>>(o->V, dst, d.ptr, d.row_len, d.coef, d.f1,  \
+                                                     d.f2, d.pos, d.count, d.accumulate)
+  if (I.has_f2) { if (uni) LP(true, true); else LP(true, false); }
+  else { if (uni) LP(false, true); else LP(false, false); }
+#undef LP
+}
+
+}  // namespace
+
+int dnlp_oracle::launch(const DevInstr &I) {
+  const dnlp_instr_desc &d = I.d;
+  if (d.count <= 0) return 0;
+  double *dst = (d.dst_space == DNLP_DST_V) ? V + d.dst_off : out[d.dst_space] + d.dst_off;
+  switch (d.kind) {
+    case DNLP_ELEM: {
+      int grid = grid_for((d.count + 1) / 2, 1);
+      if (!launch_elem(this, d, grid)) { err = "unknown elementwise function code"; return 1; }
+      break;
+    }
+    case DNLP_POLY: {
+      if (d.ptr == nullptr && d.row_len == 1) {
+        int grid = grid_for(d.count, 1);
+        if (I.has_f2)
+          poly1_kernel<true><<<grid, 256, 0, stream>>>(V, dst, d.coef, d.f1, d.f2, d.pos, d.count, d.accumulate);
+        else
+          poly1_kernel<false><<<grid, 256, 0, stream>>>(V, dst, d.coef, d.f1, d.f2, d.pos, d.count, d.accumulate);
+        break;
+      }
+      // lanes per row from the mean row length (power of two, <= 32)
+      int G = 1;
+      while (G < 32 && (double)G * 1.5 < I.mean_len) G <<= 1;
+      int grid = grid_for(d.count, G);
+      switch (G) {
+        case 1: launch_poly_g<1>(this, I, dst, grid); break;
+        case 2: launch_poly_g<2>(this, I, dst, grid); break;
+        case 4: launch_poly_g<4>(this, I, dst, grid); break;
+        case 8: launch_poly_g<8>(this, I, dst, grid); break;
+        case 16: launch_poly_g<16>(this, I, dst, grid); break;
+        default: launch_poly_g<32>(this, I, dst, grid); break;
+      }
+      break;
+    }
+    case DNLP_GEMV: {
+      size_t smem = (size_t)d.ncols * sizeof(double);
+      int in_smem = smem <= 96 * 1024 ? 1 : 0;
+      if (!in_smem) smem = 0;
+      int64_t warps_needed = d.count;
+      int64_t blocks = (warps_needed + 7) / 8;
+      int64_t cap = (int64_t)sm_count * (in_smem && smem > 48 * 1024 ? 2 : 4);
+      int grid = (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
+      gemv_kernel<8><<<grid, 256, smem, stream>>>(d.Q, V, d.x_off, dst, d.count, d.ncols, d.alpha, in_smem);
+      break;
+    }
+    case DNLP_SCALE: {
+      int grid = grid_for((d.count + 1) / 2, 1);
+      scale_kernel<<<grid, 256, 0, stream>>>(V, d.s_slot, d.coef, dst, d.pos, d.count, d.accumulate);
+      break;
+    }
+    default:
+      err = "unknown instruction kind";
+      return 1;
+  }
+  ++launches;
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    err = std::string("kernel launch failed: ") + cudaGetErrorString(e);
+    return 1;
+  }
+  return 0;
+}
+
+int dnlp_oracle::run_program(int p, bool force) {
+  for (int32_t id : prog[p]) {
+    DevInstr &I = instrs[id];
+    const bool cacheable = cache_enabled && !force && !I.d.uses_lam && I.d.dst_space == DNLP_DST_V;
+    if (cacheable && valid[id]) continue;
+    if (launch(I)) return 1;
+    if (!I.d.uses_lam && I.d.dst_space == DNLP_DST_V) valid[id] = 1;
+  }
+  return 0;
+}
+
+int dnlp_oracle::put_x(const double *x) {
+  const size_t bytes = (size_t)n * sizeof(double);
+  const bool small = n <= (1 << 18);
+  if (cache_enabled && small && have_last_x && memcmp(last_x.data(), x, bytes) == 0) return 0;
+  if (n > 0) CK(cudaMemcpyAsync(V, x, bytes, cudaMemcpyHostToDevice, stream));
+  std::fill(valid.begin(), valid.end(), 0);
+  if (small) {
+    last_x.assign(x, x + n);
+    have_last_x = true;
+  } else {
+    have_last_x = false;
+  }
+  return 0;
+}
+
+int dnlp_oracle::put_lam(const double *lam, double sigma) {
+  // sigma and lambda are adjacent in V: [n] = sigma, [n+1, n+1+m) = lambda
+  CK(cudaMemcpyAsync(V + n, &sigma, sizeof(double), cudaMemcpyHostToDevice, stream));
+  if (m > 0) CK(cudaMemcpyAsync(V + n + 1, lam, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, stream));
+  return 0;
+}
+
+int dnlp_oracle::fetch(int space, double *host) {
+  if (host == nullptr || out_len[space] == 0) return 0;
+  CK(cudaMemcpyAsync(host, out[space], (size_t)out_len[space] * sizeof(double), cudaMemcpyDeviceToHost, stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// extern "C"
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int dnlp_device_count(void) {
+  int c = 0;
+  if (cudaGetDeviceCount(&c) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return c;
+}
+
+const char *dnlp_version(void) { return "dnlp_b200 0.1 (sm_100a)"; }
+
+const char *dnlp_last_error(dnlp_oracle *o) { return o ? o->err.c_str() : g_create_error.c_str(); }
+
+void dnlp_destroy(dnlp_oracle *o) {
+  if (!o) return;
+  cudaSetDevice(o->device);
+  if (o->stream) cudaStreamSynchronize(o->stream);
+  for (void *p : o->owned) cudaFree(p);
+  if (o->ev0) cudaEventDestroy(o->ev0);
+  if (o->ev1) cudaEventDestroy(o->ev1);
+  if (o->stream) cudaStreamDestroy(o->stream);
+  delete o;
+}
+
+static int create_impl(dnlp_oracle *o, const dnlp_tape_desc *t) {
+  std::string &err = o->err;
+  CK(cudaSetDevice(o->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, o->device));
+  o->sm_count = prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&o->stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&o->ev0));
+  CK(cudaEventCreate(&o->ev1));
+  o->n = t->n; o->m = t->m; o->nslots = t->nslots; o->nnz_jac = t->nnz_jac; o->nnz_hess = t->nnz_hess;
+
+  void *p = nullptr;
+  CK(cudaMalloc(&p, (size_t)(t->nslots + 2) * sizeof(double)));
+  o->owned.push_back(p);
+  o->V = static_cast<double *>(p);
+  CK(cudaMemset(o->V, 0, (size_t)(t->nslots + 2) * sizeof(double)));
+
+  const int64_t lens[6] = {0, 1, t->n, t->m, t->nnz_jac, t->nnz_hess};
+  const double *consts[6] = {nullptr, &t->f_const, t->grad_const, t->g_const, t->jac_const, t->hess_const};
+  for (int s = 1; s < 6; ++s) {
+    o->out_len[s] = lens[s];
+    CK(cudaMalloc(&p, (size_t)(lens[s] + 2) * sizeof(double)));
+    o->owned.push_back(p);
+    o->out[s] = static_cast<double *>(p);
+    if (lens[s] > 0) {
+      if (consts[s])
+        CK(cudaMemcpy(o->out[s], consts[s], (size_t)lens[s] * sizeof(double), cudaMemcpyHostToDevice));
+      else
+        CK(cudaMemset(o->out[s], 0, (size_t)lens[s] * sizeof(double)));
+    }
+  }
+
+  o->instrs.resize(t->n_instr);
+  o->valid.assign(t->n_instr, 0);
+  for (int i = 0; i < t->n_instr; ++i) {
+    const dnlp_instr_desc &h = t->instrs[i];
+    DevInstr &D = o->instrs[i];
+    D.d = h;
+    D.d.ptr = nullptr; D.d.coef = nullptr; D.d.f1 = nullptr; D.d.f2 = nullptr; D.d.pos = nullptr; D.d.Q = nullptr;
+    if (h.kind == DNLP_POLY) {
+      if (h.ptr) { if (o->upload(h.ptr, h.count + 1, const_cast<int64_t **>(&D.d.ptr))) return 1; }
+      if (o->upload(h.coef, h.nterms, const_cast<double **>(&D.d.coef))) return 1;
+      if (o->upload(h.f1, h.nterms, const_cast<int32_t **>(&D.d.f1))) return 1;
+      if (h.f2) { if (o->upload(h.f2, h.nterms, const_cast<int32_t **>(&D.d.f2))) return 1; }
+      D.has_f2 = h.f2 != nullptr;
+      D.mean_len = h.count > 0 ? (double)h.nterms / (double)h.count : 1.0;
+    } else if (h.kind == DNLP_GEMV) {
+      if (o->upload(h.Q, h.count * h.ncols, const_cast<double **>(&D.d.Q))) return 1;
+    } else if (h.kind == DNLP_SCALE) {
+      if (o->upload(h.coef, h.count, const_cast<double **>(&D.d.coef))) return 1;
+    }
+    if ((h.kind == DNLP_POLY || h.kind == DNLP_SCALE) && h.pos) {
+      if (o->upload(h.pos, h.count, const_cast<int32_t **>(&D.d.pos))) return 1;
+    }
+  }
+  for (int q = 0; q < DNLP_NPROG; ++q) {
+    o->prog[q].assign(t->prog[q], t->prog[q] + t->prog_len[q]);
+    for (int32_t id : o->prog[q])
+      if (id < 0 || id >= t->n_instr) { err = "program references an unknown instruction"; return 1; }
+  }
+  // opt in to > 48 KB dynamic shared memory for the GEMV x tile
+  CK(cudaFuncSetAttribute(dnlp::gemv_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+  CK(cudaStreamSynchronize(o->stream));
+  return 0;
+}
+
+int dnlp_create(const dnlp_tape_desc *t, int device, dnlp_oracle **out) {
+  *out = nullptr;
+  dnlp_oracle *o = new dnlp_oracle();
+  o->device = device;
+  if (create_impl(o, t)) {
+    g_create_error = o->err;
+    dnlp_destroy(o);
+    return 1;
+  }
+  *out = o;
+  return 0;
+}
+
+#define ENTER(o)                                   \
+  std::string &err = (o)->err;                     \
+  CK(cudaSetDevice((o)->device))
+
+int dnlp_eval_f(dnlp_oracle *o, const double *x, double *f) {
+  ENTER(o);
+  if (o->put_x(x) || o->run_program(DNLP_PROG_F, false) || o->fetch(DNLP_DST_F, f)) return 1;
+  CK(cudaStreamSynchronize(o->stream));
+  return 0;
+}
+
+int dnlp_eval_grad(dnlp_oracle *o, const double *x, double *grad) {
+  ENTER(o);
+  if (o->put_x(x) || o->run_program(DNLP_PROG_GRAD, false) || o->fetch(DNLP_DST_GRAD, grad)) return 1;
+  CK(cudaStreamSynchronize(o->stream));
+  return 0;
+}
+
+int dnlp_eval_g(dnlp_oracle *o, const double *x, double *g) {
+  ENTER(o);
+  if (o->put_x(x) || o->run_program(DNLP_PROG_G, false) || o->fetch(DNLP_DST_G, g)) return 1;
+  CK(cudaStreamSynchronize(o->stream));
+  return 0;
+}
+
+int dnlp_eval_jac(dnlp_oracle *o, const double *x, double *vals) {
+  ENTER(o);
+  if (o->put_x(x) || o->run_program(DNLP_PROG_JAC, false) || o->fetch(DNLP_DST_JAC, vals)) return 1;
+  CK(cudaStreamSynchronize(o->stream));
+  return 0;
+}
+
+int dnlp_eval_hess(dnlp_oracle *o, const double *x, const double *lam, double sigma, double *vals) {
+  ENTER(o);
+  if (o->put_x(x) || o->put_lam(lam, sigma) || o->run_program(DNLP_PROG_HESS, false) ||
+      o->fetch(DNLP_DST_HESS, vals)) return 1;
+  CK(cudaStreamSynchronize(o->stream));
+  return 0;
+}
+
+int dnlp_eval_all(dnlp_oracle *o, const double *x, const double *lam, double sigma,
+                  double *f, double *grad, double *g, double *jac, double *hess) {
+  ENTER(o);
+  if (o->put_x(x) || o->put_lam(lam, sigma) || o->run_program(DNLP_PROG_ALL, false)) return 1;
+  if (o->fetch(DNLP_DST_F, f) || o->fetch(DNLP_DST_GRAD, grad) || o->fetch(DNLP_DST_G, g) ||
+      o->fetch(DNLP_DST_JAC, jac) || o->fetch(DNLP_DST_HESS, hess)) return 1;
+  CK(cudaStreamSynchronize(o->stream));
+  return 0;
+}
+
+void *dnlp_host_alloc(int64_t bytes) {
+  void *p = nullptr;
+  if (cudaMallocHost(&p, (size_t)bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+
+void dnlp_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+int dnlp_upload_point(dnlp_oracle *o, const double *x, const double *lam, double sigma) {
+  ENTER(o);
+  o->have_last_x = false;
+  if (o->put_x(x)) return 1;
+  if (lam != nullptr || o->m == 0) { if (o->put_lam(lam, sigma)) return 1; }
+  CK(cudaStreamSynchronize(o->stream));
+  return 0;
+}
+
+int dnlp_run_device(dnlp_oracle *o, int32_t prog_mask, int32_t iters, float *elapsed_ms) {
+  ENTER(o);
+  CK(cudaEventRecord(o->ev0, o->stream));
+  for (int it = 0; it < iters; ++it) {
+    std::fill(o->valid.begin(), o->valid.end(), 0);   // a new point every step: nothing is reused
+    for (int p = 0; p < DNLP_NPROG; ++p)
+      if (prog_mask & (1 << p))
+        if (o->run_program(p, false)) return 1;
+  }
+  CK(cudaEventRecord(o->ev1, o->stream));
+  CK(cudaEventSynchronize(o->ev1));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, o->ev0, o->ev1));
+  if (elapsed_ms) *elapsed_ms = ms;
+  return 0;
+}
+
+int dnlp_profile_instrs(dnlp_oracle *o, int32_t p, int32_t iters, float *ms_per_instr) {
+  ENTER(o);
+  if (p < 0 || p >= DNLP_NPROG) { err = "bad program id"; return 1; }
+  const size_t ni = o->instrs.size();
+  for (size_t i = 0; i < ni; ++i) ms_per_instr[i] = 0.f;
+  for (int it = 0; it < iters; ++it) {
+    for (int32_t id : o->prog[p]) {
+      CK(cudaEventRecord(o->ev0, o->stream));
+      if (o->launch(o->instrs[id])) return 1;
+      CK(cudaEventRecord(o->ev1, o->stream));
+      CK(cudaEventSynchronize(o->ev1));
+      float ms = 0.f;
+      CK(cudaEventElapsedTime(&ms, o->ev0, o->ev1));
+      ms_per_instr[id] += ms / (float)iters;
+    }
+  }
+  return 0;
+}
+
+int dnlp_read_output(dnlp_oracle *o, int32_t space, double *out) {
+  ENTER(o);
+  if (space < 1 || space > 5) { err = "bad output id"; return 1; }
+  if (o->fetch(space, out)) return 1;
+  CK(cudaStreamSynchronize(o->stream));
+  return 0;
+}
+
+int64_t dnlp_kernel_launches(dnlp_oracle *o) { return o->launches; }
+
+int dnlp_set_cache(dnlp_oracle *o, int32_t enabled) {
+  o->cache_enabled = enabled != 0;
+  o->have_last_x = false;
+  std::fill(o->valid.begin(), o->valid.end(), 0);
+  return 0;
+}
+
+}  // extern "C"

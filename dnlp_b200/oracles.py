@@ -1,0 +1,141 @@
+"""``GpuOracles``: the object handed to cyipopt / Knitro in place of the reference's ``Oracles``.
+
+Same surface as cvxpy/reductions/solvers/nlp_solvers/nlp_solver.py:181-427:
+``objective, gradient, constraints, jacobian, jacobianstructure, hessian,
+hessianstructure, intermediate`` and the ``iterations`` attribute read after the
+solve (ipopt_nlpif.py:173).  Every value comes from the CUDA tape through the C-ABI.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _cabi
+from .compiler import compile_problem
+
+_f64p = _cabi.c_f64p
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_f64p)
+
+
+class GpuOracles:
+    def __init__(self, problem_ir, device=0, pinned_outputs=True):
+        """``problem_ir``: a ``dnlp_b200.ir.ProblemIR`` (see frontend_cvxpy.data_to_ir)."""
+        self.problem = problem_ir
+        self.tape = compile_problem(problem_ir)
+        self.dev = _cabi.DeviceTape(self.tape, device)
+        self.n, self.m = self.tape.n, self.tape.m
+        self.num_constraints = self.m
+        self.initial_point = problem_ir.x0
+        self.iterations = 0
+        self.nnz_jac = int(self.tape.jac_rows.size)
+        self.nnz_hess = int(self.tape.hess_rows.size)
+        self._handles = []
+        alloc = self._pinned if pinned_outputs else (lambda k: np.empty(k))
+        # reference: one gradient buffer reused across calls (nlp_solver.py:184,235)
+        self.grad_obj = alloc(self.n)
+        self._f = alloc(1)
+        self._g = alloc(self.m)
+        self._jac = alloc(self.nnz_jac)
+        self._hess = alloc(self.nnz_hess)
+        self._x = alloc(self.n)
+        self._lam = alloc(max(self.m, 1))
+
+    def _pinned(self, count):
+        arr, h = _cabi.pinned_empty(count)
+        self._handles.append(h)
+        return arr
+
+    def close(self):
+        self.dev.close()
+        for h in self._handles:
+            h.free()
+        self._handles = []
+
+    def _stage_x(self, x):
+        x = np.asarray(x, dtype=np.float64).reshape(-1)
+        if x.size != self.n:
+            raise ValueError("x has %d entries, expected %d" % (x.size, self.n))
+        np.copyto(self._x, x)
+        return _ptr(self._x)
+
+    # ---- the seven callbacks --------------------------------------------------
+    def objective(self, x):
+        self.dev.check(self.dev._L.dnlp_eval_f(self.dev.h, self._stage_x(x), _ptr(self._f)))
+        return np.float64(self._f[0])
+
+    def gradient(self, x):
+        self.dev.check(self.dev._L.dnlp_eval_grad(self.dev.h, self._stage_x(x), _ptr(self.grad_obj)))
+        return self.grad_obj
+
+    def constraints(self, x):
+        self.dev.check(self.dev._L.dnlp_eval_g(self.dev.h, self._stage_x(x), _ptr(self._g)))
+        return self._g
+
+    def jacobian(self, x):
+        self.dev.check(self.dev._L.dnlp_eval_jac(self.dev.h, self._stage_x(x), _ptr(self._jac)))
+        return self._jac
+
+    def jacobianstructure(self):
+        return self.tape.jac_rows, self.tape.jac_cols
+
+    def hessian(self, x, duals, obj_factor):
+        lam = np.asarray(duals, dtype=np.float64).reshape(-1)
+        if lam.size != self.m:
+            raise ValueError("duals has %d entries, expected %d" % (lam.size, self.m))
+        self._lam[:self.m] = lam
+        self.dev.check(self.dev._L.dnlp_eval_hess(self.dev.h, self._stage_x(x), _ptr(self._lam),
+                                                 float(obj_factor), _ptr(self._hess)))
+        return self._hess
+
+    def hessianstructure(self):
+        return self.tape.hess_rows, self.tape.hess_cols
+
+    def intermediate(self, alg_mod, iter_count, obj_value, inf_pr, inf_du, mu,
+                     d_norm, regularization_size, alpha_du, alpha_pr, ls_trials):
+        self.iterations = iter_count
+
+    # ---- fused evaluation of the whole set at one point ------------------------
+    def eval_all(self, x, duals, obj_factor, want=("f", "grad", "g", "jac", "hess")):
+        lam = np.asarray(duals, dtype=np.float64).reshape(-1)
+        self._lam[:self.m] = lam
+        bufs = {"f": self._f, "grad": self.grad_obj, "g": self._g, "jac": self._jac, "hess": self._hess}
+        args = [_ptr(bufs[k]) if k in want else None for k in ("f", "grad", "g", "jac", "hess")]
+        self.dev.check(self.dev._L.dnlp_eval_all(self.dev.h, self._stage_x(x), _ptr(self._lam),
+                                                float(obj_factor), *args))
+        return {k: (np.float64(self._f[0]) if k == "f" else bufs[k]) for k in want}
+
+    # ---- device-resident measurement hooks (bench.py) ---------------------------
+    def upload_point(self, x, duals=None, obj_factor=1.0):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        lam = None if duals is None else np.ascontiguousarray(duals, dtype=np.float64)
+        self.dev.check(self.dev._L.dnlp_upload_point(self.dev.h, _ptr(x), None if lam is None else _ptr(lam),
+                                                    float(obj_factor)))
+
+    def run_device(self, programs=("f", "grad", "g", "jac", "hess"), iters=1):
+        mask = 0
+        for p in programs:
+            mask |= 1 << _cabi.PROG_IDS[p]
+        ms = C.c_float(0)
+        self.dev.check(self.dev._L.dnlp_run_device(self.dev.h, mask, int(iters), C.byref(ms)))
+        return float(ms.value)
+
+    def profile_instrs(self, program="all", iters=3):
+        out = np.zeros(max(len(self.tape.instrs), 1), dtype=np.float32)
+        self.dev.check(self.dev._L.dnlp_profile_instrs(self.dev.h, _cabi.PROG_IDS[program], int(iters),
+                                                      out.ctypes.data_as(_cabi.c_f32p)))
+        return out[:len(self.tape.instrs)]
+
+    def read_output(self, name):
+        space = {"f": 1, "grad": 2, "g": 3, "jac": 4, "hess": 5}[name]
+        n = {"f": 1, "grad": self.n, "g": self.m, "jac": self.nnz_jac, "hess": self.nnz_hess}[name]
+        out = np.empty(n)
+        self.dev.check(self.dev._L.dnlp_read_output(self.dev.h, space, _ptr(out)))
+        return out
+
+    def kernel_launches(self):
+        return int(self.dev._L.dnlp_kernel_launches(self.dev.h))
+
+    def set_cache(self, enabled):
+        self.dev._L.dnlp_set_cache(self.dev.h, int(bool(enabled)))

@@ -1,0 +1,134 @@
+/*
+ * dnlp_b200 - C ABI of the B200-native NLP oracle.
+ *
+ * Drop-in boundary: these entry points replace, one for one, the seven callbacks
+ * of the reference's `Oracles` object that cyipopt / Knitro drive
+ * (/root/reference/cvxpy/reductions/solvers/nlp_solvers/nlp_solver.py:181-427;
+ *  consumers: ipopt_nlpif.py:143-170, knitro_nlpif.py:211-309).
+ *
+ *   Oracles.__init__           nlp_solver.py:182-203   -> dnlp_create
+ *   Oracles.objective          nlp_solver.py:212-216   -> dnlp_eval_f
+ *   Oracles.gradient           nlp_solver.py:218-235   -> dnlp_eval_grad
+ *   Oracles.constraints        nlp_solver.py:237-244   -> dnlp_eval_g
+ *   Oracles.jacobian           nlp_solver.py:278-307   -> dnlp_eval_jac
+ *   Oracles.hessian            nlp_solver.py:394-421   -> dnlp_eval_hess
+ *   Oracles.jacobianstructure  nlp_solver.py:309-335   -> host arrays produced once by the DAG
+ *   Oracles.hessianstructure   nlp_solver.py:374-392      compiler (dnlp_b200/compiler.py); the
+ *                                                         library only stores nnz counts
+ *
+ * Plain pointers and sizes only; no exceptions cross the ABI.  Every function
+ * returning int returns 0 on success, non-zero otherwise (dnlp_last_error gives text).
+ * All arithmetic is fp64, all slot / position indices int32, row pointers int64.
+ *
+ * Ownership: the oracle owns its device buffers, stream and events.  `x`, `lam` and
+ * output pointers are caller-owned host memory (pageable or pinned) that is read /
+ * written only during the call; every call is complete (stream-synchronised) on return.
+ * Threading: one oracle is used from one thread at a time (callbacks arrive serially).
+ */
+#ifndef DNLP_B200_H
+#define DNLP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dnlp_oracle dnlp_oracle;
+
+/* instruction kinds */
+enum { DNLP_ELEM = 1, DNLP_POLY = 2, DNLP_GEMV = 3, DNLP_SCALE = 4 };
+/* destinations: the value buffer V or one of the five outputs */
+enum { DNLP_DST_V = 0, DNLP_DST_F = 1, DNLP_DST_GRAD = 2, DNLP_DST_G = 3, DNLP_DST_JAC = 4, DNLP_DST_HESS = 5 };
+/* programs */
+enum { DNLP_PROG_F = 0, DNLP_PROG_GRAD = 1, DNLP_PROG_G = 2, DNLP_PROG_JAC = 3, DNLP_PROG_HESS = 4,
+       DNLP_PROG_ALL = 5, DNLP_NPROG = 6 };
+
+/* One tape instruction (host pointers; dnlp_create copies everything to HBM). */
+typedef struct {
+  int32_t kind;
+  int32_t dst_space;
+  int64_t dst_off;
+  int64_t count;
+  /* ELEM: dst[k] = F(V[a_off + k*a_stride], V[b_off + k*b_stride]; param) */
+  int32_t fcode;
+  int32_t a_stride;
+  int32_t b_stride;
+  int32_t accumulate;     /* POLY/SCALE: dst += instead of dst = */
+  double param;
+  int64_t a_off;
+  int64_t b_off;
+  /* POLY: dst[pos?[k]] = sum_{t in ptr[k]..ptr[k+1]} coef[t] * V[f1[t]] * V[f2[t]]   (index -1 = 1.0) */
+  const int64_t *ptr;     /* count+1 entries, or NULL when every row has row_len terms */
+  const double *coef;     /* nterms */
+  const int32_t *f1;      /* nterms */
+  const int32_t *f2;      /* nterms, or NULL when no term has a second factor */
+  const int32_t *pos;     /* count entries or NULL (identity) */
+  int64_t nterms;
+  int32_t row_len;        /* uniform row length when ptr == NULL */
+  int32_t uses_lam;       /* depends on (sigma, lambda): never cached across calls */
+  /* GEMV: dst[i] = alpha * sum_j Q[i*ncols + j] * V[x_off + j] */
+  const double *Q;
+  int64_t ncols;
+  int64_t x_off;
+  double alpha;
+  /* SCALE: dst[pos?[k]] = V[s_slot] * coef[k] */
+  int64_t s_slot;
+} dnlp_instr_desc;
+
+typedef struct {
+  int64_t n;              /* variables */
+  int64_t m;              /* constraints */
+  int64_t nslots;         /* length of V: n + 1 + m + temporaries */
+  int64_t nnz_jac;
+  int64_t nnz_hess;
+  int32_t n_instr;
+  const dnlp_instr_desc *instrs;
+  const int32_t *prog[DNLP_NPROG];   /* instruction ids in execution order */
+  int32_t prog_len[DNLP_NPROG];
+  /* compile-time constant part of every output (entries owned by an instruction are overwritten) */
+  double f_const;
+  const double *grad_const;   /* n */
+  const double *g_const;      /* m */
+  const double *jac_const;    /* nnz_jac */
+  const double *hess_const;   /* nnz_hess */
+} dnlp_tape_desc;
+
+int dnlp_device_count(void);
+const char *dnlp_version(void);
+
+int dnlp_create(const dnlp_tape_desc *tape, int device, dnlp_oracle **out);
+void dnlp_destroy(dnlp_oracle *o);
+const char *dnlp_last_error(dnlp_oracle *o);   /* o may be NULL: error of the last failed create */
+
+/* ---- the callbacks (host buffers in, host buffers out) ---- */
+int dnlp_eval_f(dnlp_oracle *o, const double *x, double *f);
+int dnlp_eval_grad(dnlp_oracle *o, const double *x, double *grad /* n */);
+int dnlp_eval_g(dnlp_oracle *o, const double *x, double *g /* m */);
+int dnlp_eval_jac(dnlp_oracle *o, const double *x, double *vals /* nnz_jac */);
+int dnlp_eval_hess(dnlp_oracle *o, const double *x, const double *lam /* m */, double sigma,
+                   double *vals /* nnz_hess */);
+/* all five at one (x, lam, sigma): one upload, shared forward sweep, outputs may be NULL to skip the copy */
+int dnlp_eval_all(dnlp_oracle *o, const double *x, const double *lam, double sigma,
+                  double *f, double *grad, double *g, double *jac, double *hess);
+
+/* ---- pinned host memory for callers that want true async copies ---- */
+void *dnlp_host_alloc(int64_t bytes);
+void dnlp_host_free(void *p);
+
+/* ---- device-resident execution and measurement (bench.py / tests) ----
+ * dnlp_upload_point puts (x, lam, sigma) into HBM; dnlp_run_device then executes the programs in
+ * `prog_mask` (bit i = program i) `iters` times back to back with every cache invalidated before each
+ * iteration and returns the CUDA-event time of the whole loop in ms.
+ * dnlp_profile_instrs times every instruction of one program with its own event pair. */
+int dnlp_upload_point(dnlp_oracle *o, const double *x, const double *lam, double sigma);
+int dnlp_run_device(dnlp_oracle *o, int32_t prog_mask, int32_t iters, float *elapsed_ms);
+int dnlp_profile_instrs(dnlp_oracle *o, int32_t prog, int32_t iters, float *ms_per_instr /* n_instr */);
+int dnlp_read_output(dnlp_oracle *o, int32_t dst_space, double *out);   /* D2H of one output array */
+int64_t dnlp_kernel_launches(dnlp_oracle *o);                           /* launches since create */
+int dnlp_set_cache(dnlp_oracle *o, int32_t enabled);                    /* x-keyed forward cache on/off */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DNLP_B200_H */
