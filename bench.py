@@ -1,0 +1,284 @@
+#!/usr/bin/env python
+"""Benchmark of the NLP oracle hot path: oracle evals/s for the set (f, grad f, g, J, Hess L).
+
+    python bench.py --gpus N --steps K --warmup W [--workload c2|c3|c5|c1] [--impl reference]
+
+One "step" = one evaluation of all five quantities at a fresh point.
+
+  value     device-side throughput: (x, lambda, sigma) already resident in HBM, every per-x cache
+            invalidated before each step, timed with CUDA events on the oracle's own stream.
+  e2e       the same set through the public drop-in object (`GpuOracles`: the five cyipopt
+            callbacks, pinned HOST buffers in and out, H2D/D2H inside the timed region).
+  roofline  the dominant kernel's algorithmic bytes / its CUDA-event duration, against the measured
+            HBM copy bandwidth in MEASURED_PEAKS.json.
+  cpu_baseline  the CPU oracle port (oracle/dnlp_oracle.py: NumPy/SciPy restatement of the
+            reference's algorithm) on a bounded sample of the same workload, on this box's host cores.
+
+N > 1 (torchrun): the default workload does not shard a single evaluation; every rank evaluates its
+own start point of the same problem (multi-start replicas, no collective) and the aggregate is
+reported as weak scaling.  `--impl reference` times the CPU implementation (rank 0 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+PROGS = ("f", "grad", "g", "jac", "hess")
+
+
+# ------------------------------------------------------------------ workloads
+def build_workload(name, scale=1.0):
+    """Returns (ProblemIR, description dict).  `scale` < 1 shrinks the instance (CPU sample)."""
+    from dnlp_b200 import workloads as W
+    if name == "c1":
+        return W.eigen_qcqp(3), {"workload": "c1: README toy eigen-QCQP n=3"}
+    if name == "c2":
+        n = max(8, int(round(8192 * scale)))
+        return W.eigen_qcqp(n), {"workload": "c2: eigen-QCQP maximize quad_form(x,A) s.t. sum_squares(x)==1, "
+                                 "dense A n=%d, single start" % n, "n": n}
+    if name == "c3":
+        m, n = max(64, int(2_000_000 * scale)), max(16, int(4096 * (scale ** 0.5)))
+        At, x0 = W.logistic_data(m, n, 16)
+        return W.logistic_regression(At, x0), {"workload": "c3: sparse logistic-type regression m=%d n=%d, "
+                                               "16 nnz/row (lifted smooth form)" % (m, n), "m": m, "n": n}
+    if name == "c5":
+        N = max(64, int(10_000_000 * scale) // 8 * 8)
+        m = max(8, N // 2)
+        A, x0 = W.microbench_data(N, m, 10)
+        return W.microbench(A, x0), {"workload": "c5: %d-node elementwise DAG + %d-nnz CSR constraint Jacobian"
+                                     % (N, A.nnz), "N": N, "m": m, "nnz": int(A.nnz)}
+    raise SystemExit("unknown workload %r" % name)
+
+
+def eval_point(prob, rank, rng=None):
+    rng = rng or np.random.default_rng(1000 + rank)
+    x = np.asarray(prob.x0, dtype=np.float64) * (1.0 + 0.01 * rng.standard_normal(prob.n))
+    lam = rng.standard_normal(prob.m)
+    return x, lam, 1.0
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self._stop = index, [], threading.Event()
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                if out.returncode == 0 and out.stdout.strip():
+                    self.rows.append([c.strip() for c in out.stdout.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for i, nm in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------ CPU baseline (oracle port)
+def cpu_port_evals_per_s(name, budget_s=20.0):
+    """Time the CPU oracle port on a bounded sample of the workload; returns (evals/s scaled to the
+    full workload, description)."""
+    from oracle.dnlp_oracle import RefOracles
+    sample_scale = {"c1": 1.0, "c2": 0.125, "c3": 0.01, "c5": 0.01}[name]
+    prob, desc = build_workload(name, sample_scale)
+    o = RefOracles(prob)
+    o.jacobianstructure(), o.hessianstructure()
+    x, lam, sigma = eval_point(prob, 0)
+    reps, t_total = 0, 0.0
+    with np.errstate(all="ignore"):
+        while reps < 3 or (t_total < budget_s and reps < 50):
+            t0 = time.perf_counter()
+            o.objective(x), o.gradient(x), o.constraints(x), o.jacobian(x), o.hessian(x, lam, sigma)
+            t_total += time.perf_counter() - t0
+            reps += 1
+            if t_total > budget_s:
+                break
+    per_eval = t_total / reps
+    # cost is linear in the number of triplets; scale by the nnz ratio
+    work_sample = o.jac_rows.size + 2 * o.hess_rows.size + prob.n + prob.m
+    full = {"c1": 1.0, "c2": (8192 * 8193 // 2 * 2 + 3 * 8192) / max(work_sample, 1),
+            "c3": 1.0 / 0.01, "c5": 1.0 / 0.01}[name]
+    if name == "c2":
+        n_s = desc["n"]
+        full = (8192.0 / n_s) ** 2
+    return 1.0 / (per_eval * full), {
+        "sample": "%s; %d full evals in %.1f s (%.4f s/eval at sample size), scaled x%.1f by triplet count "
+                  "to the full workload" % (desc["workload"], reps, t_total, per_eval, full),
+        "seconds_per_eval_at_sample": per_eval, "scale_factor": full}
+
+
+# ------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default=os.environ.get("DNLP_BENCH_WORKLOAD", "c2"))
+    ap.add_argument("--scale", type=float, default=float(os.environ.get("DNLP_BENCH_SCALE", "1.0")))
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+
+    metric = "oracle evals/s (f, grad f, g, J, Hess L)"
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        v, d = cpu_port_evals_per_s(args.workload, budget_s=max(5.0, min(60.0, 2.0 * args.steps)))
+        line = {"impl": "reference", "metric": metric, "value": v, "unit": "evals/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / v, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": args.workload},
+                "cpu_baseline": {"value": v, "unit": "evals/s", "cores": 1, "kind": "port", "sample": d["sample"]},
+                "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+
+    from dnlp_b200.oracles import GpuOracles
+    prob, desc = build_workload(args.workload, args.scale)
+    t0 = time.time()
+    o = GpuOracles(prob, device=local_rank)
+    compile_s = time.time() - t0
+    x, lam, sigma = eval_point(prob, rank)
+
+    def barrier():
+        if dist is not None:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident throughput -------------------------------------------------------------
+    o.upload_point(x, lam, sigma)
+    o.run_device(PROGS, args.warmup)
+    launches0 = o.kernel_launches()
+    barrier()
+    with ClockSampler(local_rank) as clk:
+        ms = o.run_device(PROGS, args.steps)
+        launches = o.kernel_launches() - launches0
+        barrier()
+        # ---- end to end through the public callbacks, host buffers --------------------------------
+        rng = np.random.default_rng(7 + rank)
+        xs = [x * (1.0 + 1e-3 * rng.standard_normal(prob.n)) for _ in range(min(args.steps, 4))]
+        for i in range(2):
+            xi = xs[i % len(xs)]
+            o.objective(xi), o.gradient(xi), o.constraints(xi), o.jacobian(xi), o.hessian(xi, lam, sigma)
+        barrier()
+        e2e_steps = args.steps
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            xi = xs[i % len(xs)]
+            o.objective(xi), o.gradient(xi), o.constraints(xi), o.jacobian(xi), o.hessian(xi, lam, sigma)
+        e2e_s = time.perf_counter() - t0
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            o.eval_all(xs[i % len(xs)], lam, sigma)
+        fused_s = time.perf_counter() - t0
+    clocks = clk.summary()
+
+    if dist is not None:
+        import torch
+        t = torch.tensor([ms, e2e_s * 1e3, fused_s * 1e3], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms, fused_ms = [float(v) for v in t.tolist()]
+    else:
+        e2e_ms, fused_ms = e2e_s * 1e3, fused_s * 1e3
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel (CUDA events around every instruction) --------------
+        per = o.profile_instrs("all", iters=3)
+        top = int(np.argmax(per))
+        ins = o.tape.instrs[top]
+        kind = {1: "elem", 2: "poly", 3: "gemv", 4: "scale"}[ins.kind]
+        alg_bytes = ins.nbytes_algorithmic()
+        achieved = alg_bytes / (per[top] * 1e-3) / 1e9 if per[top] > 0 else 0.0
+        total_alg = sum(o.tape.instrs[i].nbytes_algorithmic() for i in o.tape.programs["all"])
+        small_n = prob.n <= (1 << 18)
+        h2d = (prob.n * 8 if small_n else 5 * prob.n * 8) + (prob.m + 1) * 8
+        d2h = 8 * (1 + prob.n + prob.m + o.nnz_jac + o.nnz_hess)
+        line = {
+            "metric": metric, "value": world * args.steps / (ms * 1e-3), "unit": "evals/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": dict(desc, parallelism="single start" if world == 1 else
+                           "multi-start replicas: one start point per GPU, no collective",
+                           l2="inputs larger than L2 (126 MB)" if total_alg > 2 * 126e6 else
+                           "working set fits L2; no flush", nnz_jac=o.nnz_jac, nnz_hess=o.nnz_hess,
+                           compile_s=round(compile_s, 2), algorithmic_bytes_per_eval=int(total_alg)),
+            "hbm_gbs_whole_eval": total_alg / (ms / args.steps * 1e-3) / 1e9,
+            "clocks": clocks,
+            "e2e": {"value": world * e2e_steps / (e2e_ms * 1e-3), "unit": "evals/s",
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "api": "GpuOracles.objective/gradient/constraints/jacobian/hessian (5 callbacks)",
+                    "fused_eval_all_value": world * e2e_steps / (fused_ms * 1e-3)},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "%s_kernel (instr %d, %d rows)" % (kind, top, ins.count),
+                         "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "traffic": None, "algorithmic_bytes": int(alg_bytes), "ms": float(per[top]),
+                         "peak_source": peak_src,
+                         "share_of_step": float(per[top] / max(per.sum(), 1e-12))},
+        }
+        if not args.no_cpu_baseline:
+            v, d = cpu_port_evals_per_s(args.workload)
+            line["cpu_baseline"] = {"value": v, "unit": "evals/s", "cores": 1, "kind": "port",
+                                    "sample": d["sample"]}
+        print(json.dumps(line))
+    o.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

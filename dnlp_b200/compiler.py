@@ -36,20 +36,22 @@ def _closure(tape, root_ids):
     return sorted(need)
 
 
+SIMPLIFY_LIMIT = 4_000_000     # like-term merging is an optimisation; skipped for huge vectors
+
+
 def _emit_output(b, sv, space):
-    """Split an output vector into its compile-time constant part and a POLY instruction
-    for the entries that depend on x / lambda.  Returns (const_values, instr or None)."""
-    sv = sv.simplify()
+    """Split an output vector into its compile-time constant part and the instruction(s) that
+    fill the entries depending on x / lambda.  Returns (const_values, [root instructions])."""
+    if sv.nterms <= SIMPLIFY_LIMIT:
+        sv = sv.simplify()
     cmask = sv.is_const_mask()
     const = np.where(cmask, sv.const_values(), 0.0)
     dyn = np.where(~cmask)[0]
     if dyn.size == 0:
-        return const, None
+        return const, []
     if dyn.size == sv.K:
-        ins = b.emit_poly(sv, space, 0, pos=None)
-    else:
-        ins = b.emit_poly(sv.gather(dyn), space, 0, pos=dyn.astype(np.int64))
-    return const, ins
+        return const, b.emit_output(sv, space, pos=None)
+    return const, b.emit_output(sv.gather(dyn), space, pos=dyn.astype(np.int64))
 
 
 def compile_problem(prob):
@@ -143,6 +145,6 @@ def compile_problem(prob):
     tape.hess_const, hess_ins = _emit_output(b, hv, T.DST_HESS)
 
     for name, ins in (("f", f_ins), ("grad", grad_ins), ("g", g_ins), ("jac", jac_ins), ("hess", hess_ins)):
-        tape.programs[name] = _closure(tape, [ins.id]) if ins is not None else []
+        tape.programs[name] = _closure(tape, [i.id for i in ins])
     tape.programs["all"] = sorted(set().union(*[set(p) for p in tape.programs.values()]))
     return tape

@@ -63,9 +63,10 @@ class Builder:
         uses_lam = bool(np.any((slots >= self.tape.n) & (slots < self.tape.n + 1 + self.tape.m)))
         deps = set()
         if self._producers and slots.size:
-            starts = np.array([p[0] for p in self._producers], dtype=np.int64)
-            ends = np.array([p[1] for p in self._producers], dtype=np.int64)
-            ids = np.array([p[2] for p in self._producers], dtype=np.int64)
+            prod = sorted(self._producers)          # allocation order != emission order
+            starts = np.array([p[0] for p in prod], dtype=np.int64)
+            ends = np.array([p[1] for p in prod], dtype=np.int64)
+            ids = np.array([p[2] for p in prod], dtype=np.int64)
             tmp = slots[slots >= self.tape.n + 1 + self.tape.m]
             if tmp.size:
                 k = np.searchsorted(starts, tmp, side="right") - 1
@@ -100,11 +101,73 @@ class Builder:
             self._mat_cache[key] = out
         return out
 
-    def emit_poly(self, sv, dst_space, dst_off, pos=None, count=None):
+    LAYER_MIN = 1 << 16  # outputs at least this long get the streaming first-layer treatment
+    LONG_ROW = 4096      # rows longer than this are reduced in two stages (chunks of CHUNK terms)
+    CHUNK = 1024
+
+    def _split_long_rows(self, sv):
+        """Two-stage reduction: a row with millions of terms (f = sum_i phi(t_i)) would be summed by
+        a single warp; instead its terms are cut into CHUNK-sized partial rows evaluated into
+        temporaries, and the row becomes the sum of those partials (applied recursively)."""
+        lens = sv.term_counts()
+        if sv.nterms == 0 or int(lens.max()) <= self.LONG_ROW:
+            return sv
+        long_rows = lens > self.LONG_ROW
+        t_long = long_rows[sv.row]
+        within = np.arange(sv.nterms, dtype=np.int64) - sv.ptr[sv.row]
+        nparts = np.where(long_rows, (lens + self.CHUNK - 1) // self.CHUNK, 0)
+        part_off = np.zeros(sv.K + 1, dtype=np.int64)
+        np.cumsum(nparts, out=part_off[1:])
+        P = int(part_off[-1])
+        prow = part_off[sv.row[t_long]] + within[t_long] // self.CHUNK
+        partial = SymVec(P, prow, sv.coef[t_long], sv.f1[t_long], sv.f2[t_long])
+        slots = self.materialise(partial).bare_slots()
+        owner = np.repeat(np.arange(sv.K, dtype=np.int64), nparts)
+        keep = ~t_long
+        row = np.concatenate([sv.row[keep], owner])
+        order = np.argsort(row, kind="stable")
+        none = np.full(P, NONE, dtype=np.int64)
+        out = SymVec(sv.K, row[order],
+                     np.concatenate([sv.coef[keep], np.ones(P)])[order],
+                     np.concatenate([sv.f1[keep], slots])[order],
+                     np.concatenate([sv.f2[keep], none])[order])
+        return self._split_long_rows(out)
+
+    def emit_poly(self, sv, dst_space, dst_off, pos=None, count=None, accumulate=False):
+        sv = self._split_long_rows(sv)
         ins = T.Instr(T.K_POLY, dst_space=dst_space, dst_off=int(dst_off),
                       count=sv.K if count is None else count,
-                      ptr=sv.ptr.copy(), coef=sv.coef, f1=sv.f1, f2=sv.f2, pos=pos)
+                      ptr=sv.ptr.copy(), coef=sv.coef, f1=sv.f1, f2=sv.f2, pos=pos,
+                      accumulate=accumulate)
         return self._finish(ins, np.concatenate([sv.f1, sv.f2]))
+
+    def emit_output(self, sv, space, pos=None):
+        """Write an output vector.  Large vectors whose rows are (almost all) a single term are
+        split into a streaming first layer - a SCALE when that term is one shared slot times a
+        constant (dense quad_form Hessian: 2*sigma*Q), else a one-term-per-row POLY (Jacobian fill)
+        - plus a small scatter-accumulate POLY for the few rows with more terms."""
+        K = sv.K
+        lens = sv.term_counts()
+        multi = lens > 1
+        if K >= self.LAYER_MIN and int(lens.min()) >= 1 and int(multi.sum()) <= K // 8:
+            first = sv.ptr[:-1]
+            c0, a0, b0 = sv.coef[first], sv.f1[first], sv.f2[first]
+            roots = []
+            if np.all(b0 == NONE) and a0[0] != NONE and np.all(a0 == a0[0]):
+                ins = T.Instr(T.K_SCALE, dst_space=space, dst_off=0, count=K, coef=c0,
+                              s_slot=int(a0[0]), pos=pos)
+                roots.append(self._finish(ins, a0[:1]))
+            else:
+                roots.append(self.emit_poly(SymVec(K, np.arange(K), c0, a0, b0), space, 0, pos=pos))
+            if multi.any():
+                rest = np.ones(sv.nterms, dtype=bool)
+                rest[first] = False
+                rows = np.where(multi)[0]
+                rv = SymVec(K, sv.row[rest], sv.coef[rest], sv.f1[rest], sv.f2[rest]).gather(rows)
+                roots.append(self.emit_poly(rv, space, 0, pos=rows if pos is None else pos[rows],
+                                            accumulate=True))
+            return roots
+        return [self.emit_poly(sv, space, 0, pos=pos)]
 
     def elem(self, fcode, a, b=None, param=0.0):
         """dst = F(a, b); operands are broadcast when they have a single entry."""

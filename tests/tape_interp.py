@@ -89,10 +89,11 @@ class TapeInterp:
                 V[ins.dst_off:ins.dst_off + ins.count] = res
             else:
                 dst = outs[ins.dst_space]
-                if ins.pos is None:
-                    dst[:ins.count] = res
+                pos = np.arange(ins.count) if ins.pos is None else ins.pos
+                if ins.accumulate:
+                    dst[pos] += res
                 else:
-                    dst[ins.pos] = res
+                    dst[pos] = res
 
     def eval(self, name, x, lam=None, sigma=1.0):
         t = self.t

@@ -68,3 +68,24 @@ def test_gpu_matches_oracle_on_fresh_points(name, gpu_mod):
                 assert_close(o.hessian(x, lam, sigma), ref.hessian(x, lam, sigma), "hess")
     finally:
         o.close()
+
+
+@pytest.mark.parametrize("name", ["c2_eigen_qcqp_small", "c3_logistic_small", "c4_qcqp_small",
+                                  "c5_microbench_small", "portfolio_socp", "matmul_var_var"])
+def test_gpu_optimised_emission_paths(name, gpu_mod, monkeypatch):
+    """Large-problem kernels (two-stage reductions, SCALE, one-term POLY, scatter-accumulate) forced on."""
+    from dnlp_b200.rules import Builder
+    monkeypatch.setattr(Builder, "LAYER_MIN", 2)
+    monkeypatch.setattr(Builder, "LONG_ROW", 3)
+    monkeypatch.setattr(Builder, "CHUNK", 2)
+    g = Golden(name)
+    o = gpu_mod(g.problem)
+    try:
+        for i, p in enumerate(g.points):
+            assert_close(o.objective(p["x"]), p["f"], "f[%d]" % i)
+            assert_close(o.gradient(p["x"]), p["grad"], "grad[%d]" % i)
+            assert_close(o.constraints(p["x"]), p["g"], "g[%d]" % i)
+            assert_close(o.jacobian(p["x"]), p["jac"], "jac[%d]" % i)
+            assert_close(o.hessian(p["x"], p["lam"], float(p["sigma"])), p["hess"], "hess[%d]" % i)
+    finally:
+        o.close()
