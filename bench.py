@@ -190,6 +190,9 @@ def main():
     t0 = time.time()
     o = GpuOracles(prob, device=local_rank)
     compile_s = time.time() - t0
+    if rank == 0:
+        sys.stderr.write("[bench] %s: compiled in %.1f s, n=%d m=%d nnzJ=%d nnzH=%d, %d instructions\n"
+                         % (desc["workload"], compile_s, prob.n, prob.m, o.nnz_jac, o.nnz_hess, len(o.tape.instrs)))
     x, lam, sigma = eval_point(prob, rank)
 
     def barrier():
@@ -206,6 +209,8 @@ def main():
     with ClockSampler(local_rank) as clk:
         ms = o.run_device(PROGS, args.steps)
         launches = o.kernel_launches() - launches0
+        if rank == 0:
+            sys.stderr.write("[bench] device: %.4f ms/eval\n" % (ms / args.steps))
         barrier()
         # ---- end to end through the public callbacks, host buffers --------------------------------
         rng = np.random.default_rng(7 + rank)
@@ -273,7 +278,7 @@ def main():
             v, d = cpu_port_evals_per_s(args.workload)
             line["cpu_baseline"] = {"value": v, "unit": "evals/s", "cores": 1, "kind": "port",
                                     "sample": d["sample"]}
-        print(json.dumps(line))
+        print(json.dumps(line, default=float))
     o.close()
     if dist is not None:
         dist.barrier()

@@ -71,7 +71,8 @@ class Builder:
             if tmp.size:
                 k = np.searchsorted(starts, tmp, side="right") - 1
                 ok = (k >= 0) & (tmp < ends[np.maximum(k, 0)])
-                deps = set(np.unique(ids[k[ok]]).tolist())
+                hit = np.bincount(k[ok], minlength=len(prod)) > 0
+                deps = set(ids[hit].tolist())
         return deps, uses_lam
 
     def _finish(self, ins, read_slots):
@@ -101,6 +102,7 @@ class Builder:
             self._mat_cache[key] = out
         return out
 
+    VALUE_CACHE_MAX_TERMS = 1 << 21
     LAYER_MIN = 1 << 16  # outputs at least this long get the streaming first-layer treatment
     LONG_ROW = 4096      # rows longer than this are reduced in two stages (chunks of CHUNK terms)
     CHUNK = 1024
@@ -139,7 +141,13 @@ class Builder:
                       count=sv.K if count is None else count,
                       ptr=sv.ptr.copy(), coef=sv.coef, f1=sv.f1, f2=sv.f2, pos=pos,
                       accumulate=accumulate)
-        return self._finish(ins, np.concatenate([sv.f1, sv.f2]))
+        ins = self._finish(ins, sv.f1)
+        if np.any(sv.f2 != NONE):
+            d2, l2 = self._deps_of_slots(sv.f2)
+            ins.deps = tuple(sorted(set(ins.deps) | d2))
+            ins.uses_lam = ins.uses_lam or l2 or any(self.tape.instrs[d].uses_lam for d in d2)
+            ins.level = 1 + max([self.tape.instrs[d].level for d in ins.deps], default=-1)
+        return ins
 
     def emit_output(self, sv, space, pos=None):
         """Write an output vector.  Large vectors whose rows are (almost all) a single term are
@@ -226,9 +234,12 @@ class Builder:
     # =========================================================================
     def value(self, node):
         key = id(node)
-        if key not in self._value_cache:
-            self._value_cache[key] = (node, self._value(node))   # keep node alive for id()
-        return self._value_cache[key][1]
+        if key in self._value_cache:
+            return self._value_cache[key][1]
+        v = self._value(node)
+        if v.nterms <= self.VALUE_CACHE_MAX_TERMS:       # CSE for small values; big ones are not kept alive
+            self._value_cache[key] = (node, v)           # keep node alive for id()
+        return v
 
     def _index_array(self, node):
         return np.arange(node.size, dtype=np.int64).reshape(node.shape, order="F")
@@ -585,20 +596,21 @@ class Builder:
         return {x.attrs["id"]: (idxs, idxs, self.value(y)), y.attrs["id"]: (idxs, idxs, self.value(x))}
 
     # -- matmul: kron structure through SciPy with tags (binary_operators.py:309-369) --
-    def _tag_matrix(self, operand, sv):
-        """Dense/sparse matrix whose nonzeros carry 1-based tags into ``sv``; entries the
-        reference would drop when building kron from ``operand.value`` are 0."""
-        shape = _dims(operand)
+    def _tag_matrix(self, operand):
+        """(T, vals): a matrix whose nonzeros carry 1-based tags into the symbolic vector ``vals``.
+        Entries the reference would drop when building kron from ``operand.value`` are absent/0.
+        A sparse constant is never densified: its stored entries are the tagged ones."""
         if operand.is_constant() and sp.issparse(operand.attrs["value"]):
             c = sp.coo_array(operand.attrs["value"])
-            flat = c.coords[0] + c.coords[1] * shape[0]
-            return sp.coo_array((flat + 1.0, (c.coords[0], c.coords[1])), shape=shape)
+            tags = np.arange(1, c.nnz + 1, dtype=np.float64)
+            return sp.coo_array((tags, (c.coords[0], c.coords[1])), shape=c.shape), SymVec.const(c.data)
+        sv = self.value(operand)
         keep = np.ones(sv.K, dtype=bool)
         cm = sv.is_const_mask()
         keep[cm] = sv.const_values()[cm] != 0.0
         tags = np.where(keep, np.arange(1, sv.K + 1, dtype=np.float64), 0.0)
         # keep the operand's own shape: SciPy treats a 1-D value as a row, as in the reference
-        return tags.reshape(operand.shape, order="F")
+        return tags.reshape(operand.shape, order="F"), sv
 
     def _chain_through(self, kron_csr_tags, opval, inner_jac, inner_size):
         """(d @ inner_jac.tocsc()).tocoo() with symbolic values.
@@ -650,8 +662,7 @@ class Builder:
         _, p = _dims(Y)
         dx_dict, dy_dict = {}, {}
         if not X.is_constant():
-            yv = self.value(Y)
-            Tm = self._tag_matrix(Y, yv)
+            Tm, yv = self._tag_matrix(Y)
             dx = sp.kron(Tm.T, sp.eye(m), format="csr")
             if not X.is_var():
                 dx_dict = self._chain_through(dx, yv, self.jac(X), X.size)
@@ -660,8 +671,7 @@ class Builder:
                 dx_dict = {X.attrs["id"]: (d.row.astype(np.int64), d.col.astype(np.int64),
                                             yv.gather(np.rint(d.data).astype(np.int64) - 1))}
         if not Y.is_constant():
-            xv = self.value(X)
-            Tm = self._tag_matrix(X, xv)
+            Tm, xv = self._tag_matrix(X)
             dy = sp.kron(sp.eye(p), Tm, format="csr")
             if not Y.is_var():
                 dy_dict = self._chain_through(dy, xv, self.jac(Y), Y.size)

@@ -26,15 +26,29 @@ def _i64(a):
     return np.asarray(a, dtype=np.int64)
 
 
+def _i32(a):
+    """Slot / entry indices are stored as int32 (value buffers stay below 2^31 slots) to halve the
+    compiler's memory footprint on 50 M-term vectors; index *arithmetic* is done in int64."""
+    return np.asarray(a, dtype=np.int32)
+
+
+def _sorted_by_row(K, row, coef, f1, f2):
+    """SymVec with terms stably ordered by entry; skips the sort when already ordered."""
+    if row.size > 1 and np.any(row[1:] < row[:-1]):
+        order = np.argsort(row, kind="stable")
+        return SymVec(K, row[order], coef[order], f1[order], f2[order])
+    return SymVec(K, row, coef, f1, f2)
+
+
 class SymVec:
     __slots__ = ("K", "row", "coef", "f1", "f2", "_ptr")
 
     def __init__(self, K, row, coef, f1, f2):
         self.K = int(K)
-        self.row = _i64(row)
+        self.row = _i32(row)
         self.coef = np.asarray(coef, dtype=np.float64)
-        self.f1 = _i64(f1)
-        self.f2 = _i64(f2)
+        self.f1 = _i32(f1)
+        self.f2 = _i32(f2)
         self._ptr = None
 
     # ---- constructors -----------------------------------------------------
@@ -77,6 +91,14 @@ class SymVec:
     def term_counts(self):
         return np.diff(self.ptr)
 
+    def is_unit(self):
+        """Exactly one term per entry, stored in entry order (slots, constants, simple products)."""
+        if self.nterms != self.K:
+            return False
+        if self.K == 0:
+            return True
+        return bool(self.row[0] == 0 and self.row[-1] == self.K - 1 and np.all(np.diff(self.row) == 1))
+
     def is_const_mask(self):
         """Per entry: True when no term depends on a slot (value known at compile time)."""
         dep = np.zeros(self.K, dtype=bool)
@@ -86,11 +108,10 @@ class SymVec:
 
     def const_values(self):
         """Numeric value of the constant part of every entry (terms without factors)."""
-        out = np.zeros(self.K)
         m = (self.f1 == NONE) & (self.f2 == NONE)
-        if m.any():
-            np.add.at(out, self.row[m], self.coef[m])
-        return out
+        if not m.any():
+            return np.zeros(self.K)
+        return np.bincount(self.row[m], weights=self.coef[m], minlength=self.K)
 
     def bare_slots(self):
         """If every entry is exactly ``1.0 * V[s]`` return the slot array, else None."""
@@ -129,6 +150,8 @@ class SymVec:
     def gather(self, idx):
         """New entry j = old entry idx[j] (selection, permutation or duplication)."""
         idx = _i64(idx).reshape(-1)
+        if self.is_unit():
+            return SymVec(idx.size, np.arange(idx.size, dtype=np.int32), self.coef[idx], self.f1[idx], self.f2[idx])
         p = self.ptr
         cnt = p[idx + 1] - p[idx]
         total = int(cnt.sum())
@@ -147,16 +170,14 @@ class SymVec:
         pos = _i64(pos).reshape(-1)
         assert pos.size == self.K
         new_row = pos[self.row]
-        order = np.argsort(new_row, kind="stable")
-        return SymVec(K, new_row[order], self.coef[order], self.f1[order], self.f2[order])
+        return _sorted_by_row(K, new_row, self.coef, self.f1, self.f2)
 
     def group_sum(self, group, G):
         """New entry g = sum of old entries k with group[k] == g."""
         group = _i64(group).reshape(-1)
         assert group.size == self.K
         new_row = group[self.row]
-        order = np.argsort(new_row, kind="stable")
-        return SymVec(G, new_row[order], self.coef[order], self.f1[order], self.f2[order])
+        return _sorted_by_row(G, new_row, self.coef, self.f1, self.f2)
 
     def sum_all(self):
         return self.group_sum(np.zeros(self.K, dtype=np.int64), 1)
@@ -168,19 +189,17 @@ class SymVec:
             return SymVec.zeros(0)
         offs = np.cumsum([0] + [p.K for p in parts])
         return SymVec(offs[-1],
-                      np.concatenate([p.row + o for p, o in zip(parts, offs[:-1])]),
+                      np.concatenate([p.row.astype(np.int64) + o for p, o in zip(parts, offs[:-1])]),
                       np.concatenate([p.coef for p in parts]),
                       np.concatenate([p.f1 for p in parts]),
                       np.concatenate([p.f2 for p in parts]))
 
     def add(self, other):
         assert self.K == other.K
-        row = np.concatenate([self.row, other.row])
-        order = np.argsort(row, kind="stable")
-        return SymVec(self.K, row[order],
-                      np.concatenate([self.coef, other.coef])[order],
-                      np.concatenate([self.f1, other.f1])[order],
-                      np.concatenate([self.f2, other.f2])[order])
+        return _sorted_by_row(self.K, np.concatenate([self.row, other.row]),
+                              np.concatenate([self.coef, other.coef]),
+                              np.concatenate([self.f1, other.f1]),
+                              np.concatenate([self.f2, other.f2]))
 
     def linear_map(self, out_rows, in_idx, weights, n_out):
         """sum_j M[i, j] * self[j] for a constant sparse M given as COO (out_rows, in_idx, weights)."""

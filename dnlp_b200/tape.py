@@ -96,9 +96,17 @@ class Instr:
             return 8 * (n_in + self.count)
         if self.kind == K_POLY:
             nt = int(self.coef.size)
-            idx = 4 * nt * (1 + int(np.any(self.f2 >= 0)))
-            gathers = 8 * min(nt, int(np.unique(self.f1).size)) if nt else 0
-            return 8 * nt + idx + 4 * (self.count + 1) + gathers + 8 * self.count
+            has_f2 = bool(np.any(self.f2 >= 0))
+            idx = 4 * nt * (1 + int(has_f2))
+            # gathered slots are read once from HBM (the gathered vectors are L2-resident):
+            # bounded by the span of slots referenced
+            span = int(self.f1.max()) - int(self.f1[self.f1 >= 0].min()) + 1 if nt and np.any(self.f1 >= 0) else 0
+            gathers = 8 * min(nt, span) * (1 + int(has_f2))
+            lens = np.diff(self.ptr)
+            uniform = lens.size > 0 and bool(np.all(lens == lens[0]))
+            ptr_bytes = 0 if uniform else 8 * (self.count + 1)
+            pos_bytes = 4 * self.count if self.pos is not None else 0
+            return 8 * nt + idx + ptr_bytes + pos_bytes + gathers + 8 * self.count * (2 if self.accumulate else 1)
         if self.kind == K_GEMV:
             return 8 * self.count * self.ncols + 8 * self.ncols + 8 * self.count
         if self.kind == K_SCALE:
