@@ -191,8 +191,11 @@ def main():
     o = GpuOracles(prob, device=local_rank)
     compile_s = time.time() - t0
     if rank == 0:
-        sys.stderr.write("[bench] %s: compiled in %.1f s, n=%d m=%d nnzJ=%d nnzH=%d, %d instructions\n"
-                         % (desc["workload"], compile_s, prob.n, prob.m, o.nnz_jac, o.nnz_hess, len(o.tape.instrs)))
+        import resource
+        sys.stderr.write("[bench] %s: compiled in %.1f s, n=%d m=%d nnzJ=%d nnzH=%d, %d instructions, "
+                         "host maxrss %.1f GB\n"
+                         % (desc["workload"], compile_s, prob.n, prob.m, o.nnz_jac, o.nnz_hess, len(o.tape.instrs),
+                            resource.getrusage(resource.RUSAGE_SELF).ru_maxrss / 1e6))
     x, lam, sigma = eval_point(prob, rank)
 
     def barrier():
