@@ -246,6 +246,14 @@ def main():
     if rank == 0:
         # ---- roofline of the dominant kernel (CUDA events around every instruction) --------------
         per = o.profile_instrs("all", iters=3)
+        if os.environ.get("DNLP_BENCH_PROFILE"):
+            names = {1: "elem", 2: "poly", 3: "gemv", 4: "scale"}
+            for i in o.tape.programs["all"]:
+                ii = o.tape.instrs[i]
+                nb = ii.nbytes_algorithmic()
+                sys.stderr.write("[instr %3d] %-5s dst=%d rows=%-9d terms=%-9d %8.4f ms %8.1f GB/s\n" % (
+                    i, names[ii.kind], ii.dst_space, ii.count, 0 if ii.coef is None else ii.coef.size,
+                    per[i], nb / max(per[i], 1e-9) / 1e6))
         top = int(np.argmax(per))
         ins = o.tape.instrs[top]
         kind = {1: "elem", 2: "poly", 3: "gemv", 4: "scale"}[ins.kind]

@@ -44,6 +44,8 @@ def _emit_output(b, sv, space):
     fill the entries depending on x / lambda.  Returns (const_values, [root instructions])."""
     if sv.nterms <= SIMPLIFY_LIMIT:
         sv = sv.simplify()
+    else:
+        sv = sv.drop_zero_constants()
     cmask = sv.is_const_mask()
     const = np.where(cmask, sv.const_values(), 0.0)
     dyn = np.where(~cmask)[0]

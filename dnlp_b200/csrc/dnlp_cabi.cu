@@ -35,6 +35,14 @@ struct DevInstr {
   bool has_f2 = false;
 };
 
+// All x-only elementwise instructions of one program, fused into a single launch.
+struct ElemBatch {
+  dnlp::ElemDesc *descs = nullptr;   // device
+  int ndesc = 0;
+  int64_t total_tiles = 0;
+  std::vector<int32_t> members;      // instruction ids covered
+};
+
 }  // namespace
 
 struct dnlp_oracle {
@@ -47,6 +55,7 @@ struct dnlp_oracle {
   int64_t out_len[6] = {0, 0, 0, 0, 0, 0};
   std::vector<DevInstr> instrs;
   std::vector<int32_t> prog[DNLP_NPROG];
+  ElemBatch batch[DNLP_NPROG];
   std::vector<void *> owned;           // device allocations to free
   std::vector<uint8_t> valid;          // per instruction: result valid for the current x
   std::vector<double> last_x;          // host copy of the last uploaded point (small n only)
@@ -55,6 +64,8 @@ struct dnlp_oracle {
   int64_t launches = 0;
   std::string err;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double *scratch = nullptr;           // partials of the single-row reduction kernel
+  unsigned int *ticket = nullptr;
 
   template <typename T>
   int upload(const T *host, int64_t count, T **dev) {
@@ -80,6 +91,7 @@ struct dnlp_oracle {
   }
 
   int launch(const DevInstr &I);
+  int build_batches();
   int run_program(int p, bool force);
   int put_x(const double *x);
   int put_lam(const double *lam, double sigma);
@@ -120,9 +132,9 @@ template <int G>
 void launch_poly_g(const dnlp_oracle *o, const DevInstr &I, double *dst, int grid) {
   const dnlp_instr_desc &d = I.d;
   const bool uni = d.ptr == nullptr;
-#define LP(H, Un)                                                                                \
-  poly_kernel<G, H, Un><<<grid, 256, 0, o->stream>>>(o->V, dst, d.ptr, d.row_len, d.coef, d.f1,  \
-                                                     d.f2, d.pos, d.count, d.accumulate)
+#define LP(H, Un)                                                                                   \
+  poly_rows_kernel<G, 2, H, Un><<<grid, 256, 0, o->stream>>>(o->V, dst, d.ptr, d.row_len, d.coef,   \
+                                                             d.f1, d.f2, d.pos, d.count, d.accumulate)
   if (I.has_f2) { if (uni) LP(true, true); else LP(true, false); }
   else { if (uni) LP(false, true); else LP(false, false); }
 #undef LP
@@ -141,18 +153,32 @@ int dnlp_oracle::launch(const DevInstr &I) {
       break;
     }
     case DNLP_POLY: {
-      if (d.ptr == nullptr && d.row_len == 1) {
-        int grid = grid_for(d.count, 1);
+      if (d.count == 1 && d.nterms >= 2048 && !d.pos) {
+        // one long row: grid-wide deterministic reduction in a single launch
+        int64_t blocks = (d.nterms + 256 * 16 - 1) / (256 * 16);
+        int64_t cap = (int64_t)sm_count * 4;
+        int grid = (int)(blocks < cap ? blocks : cap);
         if (I.has_f2)
-          poly1_kernel<true><<<grid, 256, 0, stream>>>(V, dst, d.coef, d.f1, d.f2, d.pos, d.count, d.accumulate);
+          poly_reduce_kernel<true><<<grid, 256, 0, stream>>>(V, dst, d.coef, d.f1, d.f2, d.nterms, d.accumulate, scratch, ticket);
         else
-          poly1_kernel<false><<<grid, 256, 0, stream>>>(V, dst, d.coef, d.f1, d.f2, d.pos, d.count, d.accumulate);
+          poly_reduce_kernel<false><<<grid, 256, 0, stream>>>(V, dst, d.coef, d.f1, d.f2, d.nterms, d.accumulate, scratch, ticket);
         break;
       }
-      // lanes per row from the mean row length (power of two, <= 32)
+      if (d.ptr == nullptr && d.row_len == 1) {
+        // one term per row (Jacobian fill, diagonal Hessian): 4 independent chains per thread
+        int grid = grid_for((d.count + 3) / 4, 1);
+        if (grid > sm_count * 4) grid = sm_count * 4;
+        if (I.has_f2)
+          poly1_stream_kernel<4, true><<<grid, 256, 0, stream>>>(V, dst, d.coef, d.f1, d.f2, d.pos, d.count, d.accumulate);
+        else
+          poly1_stream_kernel<4, false><<<grid, 256, 0, stream>>>(V, dst, d.coef, d.f1, d.f2, d.pos, d.count, d.accumulate);
+        break;
+      }
+      // lanes per row: smallest power of two >= half the mean row length (measured on B200:
+      // L=5 -> 4, L=10 -> 8, L=16 -> 8; profiles/r01_kbench.txt), two rows in flight per group
       int G = 1;
-      while (G < 32 && (double)G * 1.5 < I.mean_len) G <<= 1;
-      int grid = grid_for(d.count, G);
+      while (G < 32 && (double)G * 2.0 < I.mean_len) G <<= 1;
+      int grid = grid_for((d.count + 1) / 2, G);
       switch (G) {
         case 1: launch_poly_g<1>(this, I, dst, grid); break;
         case 2: launch_poly_g<2>(this, I, dst, grid); break;
@@ -165,18 +191,27 @@ int dnlp_oracle::launch(const DevInstr &I) {
     }
     case DNLP_GEMV: {
       size_t smem = (size_t)d.ncols * sizeof(double);
-      int in_smem = smem <= 96 * 1024 ? 1 : 0;
-      if (!in_smem) smem = 0;
-      int64_t warps_needed = d.count;
-      int64_t blocks = (warps_needed + 7) / 8;
-      int64_t cap = (int64_t)sm_count * (in_smem && smem > 48 * 1024 ? 2 : 4);
-      int grid = (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
-      gemv_kernel<8><<<grid, 256, smem, stream>>>(d.Q, V, d.x_off, dst, d.count, d.ncols, d.alpha, in_smem);
+      if ((d.ncols & 1) == 0 && smem <= 96 * 1024) {
+        // whole CTA per row, 16 warps x 4 x 128-bit loads in flight, 2 CTAs per SM
+        int64_t cap = (int64_t)sm_count * 2;
+        int grid = (int)(d.count < cap ? d.count : cap);
+        gemv_cta_kernel<4, 16><<<grid, 512, smem, stream>>>(d.Q, V, d.x_off, dst, d.count, d.ncols, d.alpha);
+      } else {
+        int in_smem = smem <= 96 * 1024 ? 1 : 0;
+        if (!in_smem) smem = 0;
+        int64_t blocks = (d.count + 7) / 8;
+        int64_t cap = (int64_t)sm_count * (in_smem && smem > 48 * 1024 ? 2 : 4);
+        int grid = (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
+        gemv_kernel<8><<<grid, 256, smem, stream>>>(d.Q, V, d.x_off, dst, d.count, d.ncols, d.alpha, in_smem);
+      }
       break;
     }
     case DNLP_SCALE: {
       int grid = grid_for((d.count + 1) / 2, 1);
-      scale_kernel<<<grid, 256, 0, stream>>>(V, d.s_slot, d.coef, dst, d.pos, d.count, d.accumulate);
+      if (!d.pos && !d.accumulate && ((reinterpret_cast<uintptr_t>(d.coef) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0)
+        scale_stream_kernel<4><<<sm_count * 16, 256, 0, stream>>>(V, d.s_slot, d.coef, dst, d.count);
+      else
+        scale_kernel<<<grid, 256, 0, stream>>>(V, d.s_slot, d.coef, dst, d.pos, d.count, d.accumulate);
       break;
     }
     default:
@@ -192,11 +227,60 @@ int dnlp_oracle::launch(const DevInstr &I) {
   return 0;
 }
 
+int dnlp_oracle::build_batches() {
+  for (int p = 0; p < DNLP_NPROG; ++p) {
+    ElemBatch &B = batch[p];
+    std::vector<dnlp::ElemDesc> descs;
+    for (int32_t id : prog[p]) {
+      const dnlp_instr_desc &d = instrs[id].d;
+      if (d.kind != DNLP_ELEM || d.level != 0 || d.uses_lam || d.dst_space != DNLP_DST_V || d.count <= 0) continue;
+      bool merged = false;
+      for (auto &e : descs) {        // share the source loads: phi, phi', phi'' of one segment
+        if (e.nout < 3 && e.a_off == d.a_off && e.b_off == d.b_off && e.count == d.count &&
+            e.a_stride == d.a_stride && e.b_stride == d.b_stride) {
+          e.fcode[e.nout] = d.fcode; e.param[e.nout] = d.param; e.dst_off[e.nout] = d.dst_off; ++e.nout;
+          merged = true;
+          break;
+        }
+      }
+      if (!merged) {
+        dnlp::ElemDesc e{};
+        e.a_off = d.a_off; e.b_off = d.b_off; e.count = d.count; e.a_stride = d.a_stride; e.b_stride = d.b_stride;
+        e.nout = 1; e.fcode[0] = d.fcode; e.param[0] = d.param; e.dst_off[0] = d.dst_off;
+        descs.push_back(e);
+      }
+      B.members.push_back(id);
+    }
+    if (B.members.size() < 2) { B.members.clear(); continue; }   // a single instruction gains nothing
+    int64_t tiles = 0;
+    for (auto &e : descs) { e.tile0 = tiles; tiles += (e.count + dnlp::ELEM_TILE - 1) / dnlp::ELEM_TILE; }
+    B.ndesc = (int)descs.size();
+    B.total_tiles = tiles;
+    if (upload(descs.data(), (int64_t)descs.size(), &B.descs)) return 1;
+  }
+  return 0;
+}
+
 int dnlp_oracle::run_program(int p, bool force) {
+  ElemBatch &B = batch[p];
+  if (!B.members.empty()) {
+    bool all_invalid = true;
+    if (cache_enabled && !force)
+      for (int32_t id : B.members) if (valid[id]) { all_invalid = false; break; }
+    if (all_invalid) {
+      int64_t cap = (int64_t)sm_count * 8;
+      int grid = (int)(B.total_tiles < cap ? B.total_tiles : cap);
+      dnlp::elem_batch_kernel<<<grid, 256, 0, stream>>>(V, B.descs, B.ndesc, B.total_tiles);
+      ++launches;
+      cudaError_t e = cudaPeekAtLastError();
+      if (e != cudaSuccess) { err = std::string("kernel launch failed: ") + cudaGetErrorString(e); return 1; }
+      for (int32_t id : B.members) valid[id] = 1;
+    }
+  }
   for (int32_t id : prog[p]) {
     DevInstr &I = instrs[id];
-    const bool cacheable = cache_enabled && !force && !I.d.uses_lam && I.d.dst_space == DNLP_DST_V;
-    if (cacheable && valid[id]) continue;
+    const bool cacheable = !I.d.uses_lam && I.d.dst_space == DNLP_DST_V;
+    if (cacheable && valid[id] && !force) continue;
     if (launch(I)) return 1;
     if (!I.d.uses_lam && I.d.dst_space == DNLP_DST_V) valid[id] = 1;
   }
@@ -274,6 +358,14 @@ static int create_impl(dnlp_oracle *o, const dnlp_tape_desc *t) {
   o->V = static_cast<double *>(p);
   CK(cudaMemset(o->V, 0, (size_t)(t->nslots + 2) * sizeof(double)));
 
+  CK(cudaMalloc(&p, 4096 * sizeof(double)));
+  o->owned.push_back(p);
+  o->scratch = static_cast<double *>(p);
+  CK(cudaMalloc(&p, 64));
+  o->owned.push_back(p);
+  o->ticket = static_cast<unsigned int *>(p);
+  CK(cudaMemset(o->ticket, 0, 64));
+
   const int64_t lens[6] = {0, 1, t->n, t->m, t->nnz_jac, t->nnz_hess};
   const double *consts[6] = {nullptr, &t->f_const, t->grad_const, t->g_const, t->jac_const, t->hess_const};
   for (int s = 1; s < 6; ++s) {
@@ -317,8 +409,10 @@ static int create_impl(dnlp_oracle *o, const dnlp_tape_desc *t) {
     for (int32_t id : o->prog[q])
       if (id < 0 || id >= t->n_instr) { err = "program references an unknown instruction"; return 1; }
   }
+  if (o->build_batches()) return 1;
   // opt in to > 48 KB dynamic shared memory for the GEMV x tile
   CK(cudaFuncSetAttribute(dnlp::gemv_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+  CK(cudaFuncSetAttribute(dnlp::gemv_cta_kernel<4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
   CK(cudaStreamSynchronize(o->stream));
   return 0;
 }
@@ -425,6 +519,9 @@ int dnlp_profile_instrs(dnlp_oracle *o, int32_t p, int32_t iters, float *ms_per_
   if (p < 0 || p >= DNLP_NPROG) { err = "bad program id"; return 1; }
   const size_t ni = o->instrs.size();
   for (size_t i = 0; i < ni; ++i) ms_per_instr[i] = 0.f;
+  for (int32_t id : o->prog[p])                      // untimed pass: lazy module load, caches
+    if (o->launch(o->instrs[id])) return 1;
+  CK(cudaStreamSynchronize(o->stream));
   for (int it = 0; it < iters; ++it) {
     for (int32_t id : o->prog[p]) {
       CK(cudaEventRecord(o->ev0, o->stream));

@@ -104,6 +104,7 @@ class Builder:
 
     VALUE_CACHE_MAX_TERMS = 1 << 21
     LAYER_MIN = 1 << 16  # outputs at least this long get the streaming first-layer treatment
+    SPLIT_SINGLE_ROW = False
     LONG_ROW = 4096      # rows longer than this are reduced in two stages (chunks of CHUNK terms)
     CHUNK = 1024
 
@@ -114,6 +115,8 @@ class Builder:
         lens = sv.term_counts()
         if sv.nterms == 0 or int(lens.max()) <= self.LONG_ROW:
             return sv
+        if sv.K == 1 and not self.SPLIT_SINGLE_ROW:
+            return sv            # a lone long row is reduced grid-wide by poly_reduce_kernel
         long_rows = lens > self.LONG_ROW
         t_long = long_rows[sv.row]
         within = np.arange(sv.nterms, dtype=np.int64) - sv.ptr[sv.row]

@@ -67,6 +67,8 @@ typedef struct {
   int64_t nterms;
   int32_t row_len;        /* uniform row length when ptr == NULL */
   int32_t uses_lam;       /* depends on (sigma, lambda): never cached across calls */
+  int32_t level;          /* 0 = reads only x / lambda (no instruction feeds it) */
+  int32_t reserved;
   /* GEMV: dst[i] = alpha * sum_j Q[i*ncols + j] * V[x_off + j] */
   const double *Q;
   int64_t ncols;

@@ -89,3 +89,51 @@ def test_gpu_optimised_emission_paths(name, gpu_mod, monkeypatch):
             assert_close(o.hessian(p["x"], p["lam"], float(p["sigma"])), p["hess"], "hess[%d]" % i)
     finally:
         o.close()
+
+
+def _cmp_with_oracle(prob, gpu_mod, npoints=2, seed=0):
+    ref = RefOracles(prob)
+    jr, jc = ref.jacobianstructure()
+    hr, hc = ref.hessianstructure()
+    o = gpu_mod(prob)
+    try:
+        np.testing.assert_array_equal(o.jacobianstructure()[0], jr)
+        np.testing.assert_array_equal(o.jacobianstructure()[1], jc)
+        np.testing.assert_array_equal(o.hessianstructure()[0], hr)
+        np.testing.assert_array_equal(o.hessianstructure()[1], hc)
+        rng = np.random.default_rng(seed)
+        with np.errstate(all="ignore"):
+            for _ in range(npoints):
+                x = prob.x0 * (1 + 0.01 * rng.standard_normal(prob.n))
+                lam = rng.standard_normal(prob.m)
+                sigma = float(rng.uniform(0.5, 1.5))
+                assert_close(o.objective(x), ref.objective(x), "f")
+                assert_close(o.gradient(x), ref.gradient(x), "grad")
+                assert_close(o.constraints(x), ref.constraints(x), "g", atol=1e-9)
+                assert_close(o.jacobian(x), ref.jacobian(x), "jac")
+                assert_close(o.hessian(x, lam, sigma), ref.hessian(x, lam, sigma), "hess")
+                res = o.eval_all(x, lam, sigma)
+                assert_close(res["hess"], ref.hessian(x, lam, sigma), "eval_all/hess")
+                assert_close(res["g"], ref.constraints(x), "eval_all/g", atol=1e-9)
+    finally:
+        o.close()
+
+
+@pytest.mark.parametrize("n", [1500, 1501])
+def test_gpu_medium_eigen_qcqp(n, gpu_mod):
+    """Sizes that reach the production kernels: CTA-per-row GEMV (even n) / warp-per-row GEMV
+    (odd n), SCALE + scatter-accumulate Hessian, grid-wide single-row reduction."""
+    from dnlp_b200 import workloads as W
+    _cmp_with_oracle(W.eigen_qcqp(n), gpu_mod)
+
+
+def test_gpu_medium_logistic(gpu_mod):
+    from dnlp_b200 import workloads as W
+    At, x0 = W.logistic_data(30000, 64, 16)
+    _cmp_with_oracle(W.logistic_regression(At, x0), gpu_mod)
+
+
+def test_gpu_medium_microbench(gpu_mod):
+    from dnlp_b200 import workloads as W
+    A, x0 = W.microbench_data(80000, 40000, 10)
+    _cmp_with_oracle(W.microbench(A, x0), gpu_mod)
