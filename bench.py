@@ -262,7 +262,8 @@ def main():
         total_alg = sum(o.tape.instrs[i].nbytes_algorithmic() for i in o.tape.programs["all"])
         small_n = prob.n <= (1 << 18)
         h2d = (prob.n * 8 if small_n else 5 * prob.n * 8) + (prob.m + 1) * 8
-        d2h = 8 * (1 + prob.n + prob.m + o.nnz_jac + o.nnz_hess)
+        full = {"grad": prob.n, "g": prob.m, "jac": o.nnz_jac, "hess": o.nnz_hess}
+        d2h = 8 * (1 + sum(o._dyn[k][0].size if k in o._dyn else v for k, v in full.items()))
         line = {
             "metric": metric, "value": world * args.steps / (ms * 1e-3), "unit": "evals/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,

@@ -49,6 +49,7 @@ def _emit_output(b, sv, space):
     cmask = sv.is_const_mask()
     const = np.where(cmask, sv.const_values(), 0.0)
     dyn = np.where(~cmask)[0]
+    b.tape.dynamic[space] = dyn.astype(np.int32)
     if dyn.size == 0:
         return const, []
     if dyn.size == sv.K:

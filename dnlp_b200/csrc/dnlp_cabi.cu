@@ -64,6 +64,9 @@ struct dnlp_oracle {
   int64_t launches = 0;
   std::string err;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int32_t *dyn_pos[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  double *dyn_buf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int64_t dyn_len[6] = {0, 0, 0, 0, 0, 0};
   double *scratch = nullptr;           // partials of the single-row reduction kernel
   unsigned int *ticket = nullptr;
 
@@ -476,6 +479,39 @@ int dnlp_eval_all(dnlp_oracle *o, const double *x, const double *lam, double sig
   if (o->put_x(x) || o->put_lam(lam, sigma) || o->run_program(DNLP_PROG_ALL, false)) return 1;
   if (o->fetch(DNLP_DST_F, f) || o->fetch(DNLP_DST_GRAD, grad) || o->fetch(DNLP_DST_G, g) ||
       o->fetch(DNLP_DST_JAC, jac) || o->fetch(DNLP_DST_HESS, hess)) return 1;
+  CK(cudaStreamSynchronize(o->stream));
+  return 0;
+}
+
+int dnlp_set_dynamic(dnlp_oracle *o, int32_t space, const int32_t *pos, int64_t count) {
+  ENTER(o);
+  if (space < DNLP_DST_GRAD || space > DNLP_DST_HESS) { err = "bad output id"; return 1; }
+  for (int64_t i = 0; i < count; ++i)
+    if (pos[i] < 0 || pos[i] >= o->out_len[space]) { err = "dynamic position out of range"; return 1; }
+  if (o->upload(pos, count, &o->dyn_pos[space])) return 1;
+  void *p = nullptr;
+  CK(cudaMalloc(&p, (size_t)(count + 2) * sizeof(double)));
+  o->owned.push_back(p);
+  o->dyn_buf[space] = static_cast<double *>(p);
+  o->dyn_len[space] = count;
+  return 0;
+}
+
+int dnlp_eval_dyn(dnlp_oracle *o, int32_t prog, const double *x, const double *lam, double sigma,
+                  double *compact) {
+  ENTER(o);
+  if (prog < DNLP_PROG_GRAD || prog > DNLP_PROG_HESS) { err = "bad program id"; return 1; }
+  const int space = prog + 1;          // program i writes output i + 1
+  if (o->put_x(x)) return 1;
+  if (prog == DNLP_PROG_HESS && o->put_lam(lam, sigma)) return 1;
+  if (o->run_program(prog, false)) return 1;
+  const int64_t cnt = o->dyn_len[space];
+  if (cnt > 0) {
+    int grid = o->grid_for(cnt, 1);
+    dnlp::gather_kernel<<<grid, 256, 0, o->stream>>>(o->out[space], o->dyn_pos[space], o->dyn_buf[space], cnt);
+    ++o->launches;
+    CK(cudaMemcpyAsync(compact, o->dyn_buf[space], (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, o->stream));
+  }
   CK(cudaStreamSynchronize(o->stream));
   return 0;
 }

@@ -658,4 +658,12 @@ poly_reduce_kernel(const double *__restrict__ V, double *__restrict__ dst, const
   }
 }
 
+// ---- compaction of the x/lambda-dependent entries of an output before the D2H copy ----------
+__global__ void __launch_bounds__(256)
+gather_kernel(const double *__restrict__ src, const int32_t *__restrict__ pos, double *__restrict__ dst,
+              int64_t count) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += (int64_t)gridDim.x * blockDim.x)
+    dst[k] = src[pos[k]];
+}
+
 }  // namespace dnlp

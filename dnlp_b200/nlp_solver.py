@@ -1,0 +1,56 @@
+"""Integration with the reference's NLP solver interface.
+
+``prob.solve(nlp=True, solver=cp.IPOPT, ...)`` reaches the oracle through
+``NLPsolver._prepare_data_and_inv_data`` (cvxpy/reductions/solvers/nlp_solvers/nlp_solver.py:61-79),
+which instantiates the module-level name ``Oracles`` and hands the object to
+``cyipopt.Problem`` (ipopt_nlpif.py:143-151) or to the Knitro callbacks
+(knitro_nlpif.py:211-309).  ``install()`` rebinds that one name to ``gpu_oracles``; nothing
+else in the reference changes, and the user-facing API stays ``prob.solve(nlp=True)``.
+
+    import cvxpy as cp, dnlp_b200.nlp_solver as gpu
+    gpu.install()                      # or: with gpu.gpu_oracle(): prob.solve(nlp=True)
+    prob.solve(nlp=True, solver=cp.IPOPT)
+
+The reference is imported lazily so the rest of the package works without it.
+"""
+import contextlib
+import importlib
+
+from .frontend_cvxpy import problem_to_ir
+from .oracles import GpuOracles
+
+_REF_MODULE = "cvxpy.reductions.solvers.nlp_solvers.nlp_solver"
+_saved = {}
+DEVICE = 0
+
+
+def gpu_oracles(problem, initial_point, num_constraints):
+    """Same signature as ``Oracles.__init__`` (nlp_solver.py:182)."""
+    pir = problem_to_ir(problem, x0=initial_point)
+    if pir.m != num_constraints:
+        raise ValueError("constraint count mismatch: IR has %d rows, caller says %d" % (pir.m, num_constraints))
+    return GpuOracles(pir, device=DEVICE)
+
+
+def install(device=0):
+    global DEVICE
+    DEVICE = device
+    mod = importlib.import_module(_REF_MODULE)
+    if "Oracles" not in _saved:
+        _saved["Oracles"] = mod.Oracles
+    mod.Oracles = gpu_oracles
+    return mod
+
+
+def uninstall():
+    if "Oracles" in _saved:
+        importlib.import_module(_REF_MODULE).Oracles = _saved.pop("Oracles")
+
+
+@contextlib.contextmanager
+def gpu_oracle(device=0):
+    install(device)
+    try:
+        yield
+    finally:
+        uninstall()

@@ -20,6 +20,9 @@ def _ptr(a):
 
 
 class GpuOracles:
+    ELIDE_MIN = 4096               # outputs shorter than this are always copied whole
+    ELIDE_MAX_FRACTION = 0.5       # elide constants when at most this share of entries is dynamic
+
     def __init__(self, problem_ir, device=0, pinned_outputs=True):
         """``problem_ir``: a ``dnlp_b200.ir.ProblemIR`` (see frontend_cvxpy.data_to_ir)."""
         self.problem = problem_ir
@@ -41,6 +44,21 @@ class GpuOracles:
         self._hess = alloc(self.nnz_hess)
         self._x = alloc(self.n)
         self._lam = alloc(max(self.m, 1))
+        # Constant-entry elision: when only a small part of an output depends on x / lambda
+        # (affine Jacobian rows, reference quirk Q5), only that part crosses PCIe per call; the
+        # constants are written into the (reused) output array once, here.
+        self._dyn = {}
+        for name, space, buf, const in (("jac", 4, self._jac, self.tape.jac_const),
+                                        ("hess", 5, self._hess, self.tape.hess_const),
+                                        ("g", 3, self._g, self.tape.g_const),
+                                        ("grad", 2, self.grad_obj, self.tape.grad_const)):
+            pos = self.tape.dynamic.get(space)
+            if pos is not None and buf.size >= self.ELIDE_MIN and pos.size <= self.ELIDE_MAX_FRACTION * buf.size:
+                buf[:] = const
+                pos = np.ascontiguousarray(pos, dtype=np.int32)
+                self.dev.check(self.dev._L.dnlp_set_dynamic(self.dev.h, space, pos.ctypes.data_as(_cabi.c_i32p),
+                                                           int(pos.size)))
+                self._dyn[name] = (pos, alloc(pos.size))
 
     def _pinned(self, count):
         arr, h = _cabi.pinned_empty(count)
@@ -52,6 +70,12 @@ class GpuOracles:
         for h in self._handles:
             h.free()
         self._handles = []
+
+    def _eval_dyn(self, name, prog, x, lam=None, sigma=1.0):
+        pos, compact = self._dyn[name]
+        self.dev.check(self.dev._L.dnlp_eval_dyn(self.dev.h, prog, self._stage_x(x),
+                                                None if lam is None else _ptr(lam), float(sigma), _ptr(compact)))
+        return pos, compact
 
     def _stage_x(self, x):
         x = np.asarray(x, dtype=np.float64).reshape(-1)
@@ -66,14 +90,26 @@ class GpuOracles:
         return np.float64(self._f[0])
 
     def gradient(self, x):
+        if "grad" in self._dyn:
+            pos, compact = self._eval_dyn("grad", 1, x)
+            self.grad_obj[pos] = compact
+            return self.grad_obj
         self.dev.check(self.dev._L.dnlp_eval_grad(self.dev.h, self._stage_x(x), _ptr(self.grad_obj)))
         return self.grad_obj
 
     def constraints(self, x):
+        if "g" in self._dyn:
+            pos, compact = self._eval_dyn("g", 2, x)
+            self._g[pos] = compact
+            return self._g
         self.dev.check(self.dev._L.dnlp_eval_g(self.dev.h, self._stage_x(x), _ptr(self._g)))
         return self._g
 
     def jacobian(self, x):
+        if "jac" in self._dyn:
+            pos, compact = self._eval_dyn("jac", 3, x)
+            self._jac[pos] = compact
+            return self._jac
         self.dev.check(self.dev._L.dnlp_eval_jac(self.dev.h, self._stage_x(x), _ptr(self._jac)))
         return self._jac
 
@@ -85,6 +121,10 @@ class GpuOracles:
         if lam.size != self.m:
             raise ValueError("duals has %d entries, expected %d" % (lam.size, self.m))
         self._lam[:self.m] = lam
+        if "hess" in self._dyn:
+            pos, compact = self._eval_dyn("hess", 4, x, self._lam, obj_factor)
+            self._hess[pos] = compact
+            return self._hess
         self.dev.check(self.dev._L.dnlp_eval_hess(self.dev.h, self._stage_x(x), _ptr(self._lam),
                                                  float(obj_factor), _ptr(self._hess)))
         return self._hess

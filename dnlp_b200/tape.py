@@ -130,6 +130,7 @@ class Tape:
         self.g_const = None
         self.f_const = 0.0
         self.jac_is_list = False    # reference returns a Python list when all constraints are affine
+        self.dynamic = {}           # output space -> int32 positions of the x/lambda-dependent entries
 
     @property
     def sigma_slot(self):

@@ -114,6 +114,15 @@ int dnlp_eval_hess(dnlp_oracle *o, const double *x, const double *lam /* m */, d
 int dnlp_eval_all(dnlp_oracle *o, const double *x, const double *lam, double sigma,
                   double *f, double *grad, double *g, double *jac, double *hess);
 
+/* ---- constant-entry elision (reference quirk Q5: affine Jacobian rows never change) ----
+ * dnlp_set_dynamic registers, for one output (DNLP_DST_GRAD..DNLP_DST_HESS), the positions of the
+ * entries that depend on x / lambda.  dnlp_eval_dyn then runs program `prog` and copies ONLY those
+ * entries, compacted in `pos` order, to `compact`; the caller keeps the constant entries (it got
+ * them once from the compiler) and scatters the compact values into its array. */
+int dnlp_set_dynamic(dnlp_oracle *o, int32_t dst_space, const int32_t *pos, int64_t count);
+int dnlp_eval_dyn(dnlp_oracle *o, int32_t prog, const double *x, const double *lam, double sigma,
+                  double *compact);
+
 /* ---- pinned host memory for callers that want true async copies ---- */
 void *dnlp_host_alloc(int64_t bytes);
 void dnlp_host_free(void *p);

@@ -137,3 +137,21 @@ def test_gpu_medium_microbench(gpu_mod):
     from dnlp_b200 import workloads as W
     A, x0 = W.microbench_data(80000, 40000, 10)
     _cmp_with_oracle(W.microbench(A, x0), gpu_mod)
+
+
+@pytest.mark.parametrize("name", ["c3_logistic_small", "clnlbeam", "portfolio_socp", "hs071", "c2_eigen_qcqp_small"])
+def test_gpu_constant_entry_elision(name, gpu_mod, monkeypatch):
+    """Compact D2H of only the x/lambda-dependent entries (affine rows cached, reference quirk Q5)."""
+    monkeypatch.setattr(gpu_mod, "ELIDE_MIN", 1)
+    monkeypatch.setattr(gpu_mod, "ELIDE_MAX_FRACTION", 1.0)
+    g = Golden(name)
+    o = gpu_mod(g.problem)
+    try:
+        assert o._dyn, "elision not active"
+        for i, p in enumerate(g.points):
+            assert_close(o.gradient(p["x"]), p["grad"], "grad[%d]" % i)
+            assert_close(o.constraints(p["x"]), p["g"], "g[%d]" % i)
+            assert_close(o.jacobian(p["x"]), p["jac"], "jac[%d]" % i)
+            assert_close(o.hessian(p["x"], p["lam"], float(p["sigma"])), p["hess"], "hess[%d]" % i)
+    finally:
+        o.close()

@@ -1,0 +1,81 @@
+"""Drop-in boundary against the LIVE reference (runs only where /root/reference exists).
+
+`install()` rebinds the one name the reference's solver interface instantiates; the reduction
+chain then yields a GpuOracles object whose structures equal the reference Oracles' bit for bit.
+The device upload is stubbed here (no GPU in the build container); the CUDA path itself is
+covered by tests/test_gpu_parity.py."""
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+
+REF = "/root/reference"
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "cvxpy")), reason="reference not present")
+
+
+@pytest.fixture(scope="module")
+def cp():
+    v = types.ModuleType("cvxpy.version")
+    v.short_version = v.version = "1.8.0"
+    v.full_version, v.git_revision, v.commit_count, v.release = "1.8.0.dev0", "Unknown", "0", False
+    sys.modules["cvxpy.version"] = v
+    sys.path.insert(0, REF)
+    sys.dont_write_bytecode = True
+    import cvxpy
+    yield cvxpy
+    sys.path.remove(REF)
+
+
+def _chain(cp, prob):
+    from cvxpy.reductions.cvx_attr2constr import CvxAttr2Constr
+    from cvxpy.reductions.dnlp2smooth.dnlp2smooth import Dnlp2Smooth
+    from cvxpy.reductions.flip_objective import FlipObjective
+    from cvxpy.reductions.solvers.nlp_solvers.ipopt_nlpif import IPOPT
+    from cvxpy.reductions.solvers.solving_chain import SolvingChain
+    red = ([FlipObjective()] if type(prob.objective) == cp.Maximize else []) + \
+        [CvxAttr2Constr(reduce_bounds=False), Dnlp2Smooth(), IPOPT()]
+    return SolvingChain(reductions=red).apply(problem=prob)[0]
+
+
+def test_install_swaps_the_oracle_and_structures_match(cp, monkeypatch):
+    import dnlp_b200.nlp_solver as gpu
+    from dnlp_b200 import _cabi
+    from dnlp_b200.oracles import GpuOracles
+
+    class FakeDevice:                       # no GPU here: keep the compile, skip the upload
+        def __init__(self, tape, device=0):
+            self.tape = tape
+
+        def close(self):
+            pass
+    monkeypatch.setattr(_cabi, "DeviceTape", FakeDevice)
+    monkeypatch.setattr(_cabi, "pinned_empty", lambda k: (np.empty(k), types.SimpleNamespace(free=lambda: None)))
+
+    def build():
+        np.random.seed(0)
+        x = cp.Variable(4, bounds=[0, 6])
+        x.value = np.array([1.0, 5.0, 5.0, 1.0])
+        return cp.Problem(cp.Minimize(x[0] * x[3] * (x[0] + x[1] + x[2]) + x[2]),
+                          [x[0] * x[1] * x[2] * x[3] >= 25, cp.sum(cp.square(x)) == 40])
+
+    ref = _chain(cp, build())["oracles"]
+    with gpu.gpu_oracle():
+        data = _chain(cp, build())
+    ours = data["oracles"]
+    assert isinstance(ours, GpuOracles)
+    assert type(ref).__name__ == "Oracles"
+    for a, b in zip(ours.jacobianstructure(), ref.jacobianstructure()):
+        assert a.dtype == np.int32
+        np.testing.assert_array_equal(a, b)
+    for a, b in zip(ours.hessianstructure(), ref.hessianstructure()):
+        np.testing.assert_array_equal(a, b)
+    # the bound methods the solver interfaces read from `data` exist with the reference's names
+    for name in ("objective", "gradient", "constraints", "jacobian", "jacobianstructure",
+                 "hessian", "hessianstructure"):
+        assert callable(data[name])
+    assert hasattr(ours, "intermediate") and ours.iterations == 0
+    # after the context manager the reference's own class is back
+    import cvxpy.reductions.solvers.nlp_solvers.nlp_solver as mod
+    assert mod.Oracles is type(ref)
