@@ -207,6 +207,106 @@ def bench_sharded(args, rank, local_rank, world, dist, metric):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------ C4: batched multi-start QCQP
+def bench_multistart(args, rank, local_rank, world, dist, metric, hbm_peak, peak_src):
+    """4096 random starts of a nonconvex QCQP (n=512, 8 quadratic constraints); the batch is split
+    evenly over the ranks (no collective).  One step = every start's (f, grad, g, J, Hess L)."""
+    from dnlp_b200 import workloads as W
+    from dnlp_b200.multistart import BatchedOracles
+    n, k = max(16, int(512 * args.scale)), 8
+    Btot = max(world, int(4096 * args.scale))
+    P, q, rng = W.qcqp_data(n, k)
+    prob = W.qcqp(P, q)
+    X = rng.uniform(-1, 1, (Btot, n))                       # the same rng stream as SURVEY 8(d) C4
+    b0, b1 = (Btot * rank) // world, (Btot * (rank + 1)) // world
+    B = b1 - b0
+    lrng = np.random.default_rng(17)
+    LAM = lrng.standard_normal((Btot, k))[b0:b1]
+    SIG = np.ones(B)
+    o = BatchedOracles(prob, B, device=local_rank)
+
+    def barrier():
+        if dist is not None:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+    o.upload(X[b0:b1], LAM, SIG)
+    o.run_device(PROGS, args.warmup)
+    l0 = o.kernel_launches()
+    barrier()
+    with ClockSampler(local_rank) as clk:
+        ms = o.run_device(PROGS, args.steps)
+        launches = o.kernel_launches() - l0
+        barrier()
+        o.eval(X[b0:b1], LAM, SIG)
+        barrier()
+        e_steps = max(1, min(args.steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            o.eval(X[b0:b1], LAM, SIG)
+        e2e_ms = (time.perf_counter() - t0) * 1e3
+    if dist is not None:
+        import torch
+        t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = [float(v) for v in t.tolist()]
+    if rank == 0:
+        per = o.profile_instrs("all", iters=2)
+        top = int(np.argmax(per))
+        ins = o.tape.instrs[top]
+        if ins.kind == 3:      # GEMM on the FP64 tensor cores
+            flops = 2.0 * ins.count * ins.ncols * B
+            roof = {"bound": "tensor", "kernel": "bgemm_dmma_kernel (instr %d: [%dx%d]x[%dx%d])" % (top, ins.count, ins.ncols, ins.ncols, B),
+                    "achieved": flops / (per[top] * 1e-3) / 1e12, "peak": 40.0, "unit": "TFLOP/s",
+                    "frac": flops / (per[top] * 1e-3) / 1e12 / 40.0, "traffic": None,
+                    "peak_source": "nominal B200 FP64 tensor (no measured figure in MEASURED_PEAKS.json)"}
+        else:
+            nb = ins.nbytes_algorithmic() if ins.kind != 2 else (8 * ins.count * B * (2 if ins.accumulate else 1)
+                                                                 + 12 * int(ins.coef.size))
+            roof = {"bound": "hbm", "kernel": "batched instr %d kind %d (%d rows x %d starts)" % (top, ins.kind, ins.count, B),
+                    "achieved": nb / (per[top] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": nb / (per[top] * 1e-3) / 1e9 / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes": int(nb)}
+        roof["ms"] = float(per[top])
+        roof["share_of_step"] = float(per[top] / max(per.sum(), 1e-12))
+        gemm_ms = float(sum(per[i] for i in o.tape.programs["all"] if o.tape.instrs[i].kind == 3))
+        gemm_fl = float(sum(2.0 * o.tape.instrs[i].count * o.tape.instrs[i].ncols * B
+                            for i in o.tape.programs["all"] if o.tape.instrs[i].kind == 3))
+        line = {"metric": metric, "value": Btot * args.steps / (ms * 1e-3), "unit": "evals/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": "c4: multi-start batch of %d random starts of a nonconvex QCQP n=%d, %d quadratic "
+                           "constraints; one eval = one start's full set" % (Btot, n, k),
+                           "parallelism": "starts split over %d GPU(s), no collective" % world,
+                           "l2": "outputs larger than L2", "starts_per_gpu": B},
+                "dmma": {"gemm_tflops": gemm_fl / max(gemm_ms * 1e-3, 1e-12) / 1e12, "gemm_ms": gemm_ms,
+                         "peak_nominal_tflops": 40.0},
+                "clocks": clk.summary(),
+                "e2e": {"value": Btot * e_steps / (e2e_ms * 1e-3), "unit": "evals/s",
+                        "api": "BatchedOracles.eval (host arrays in/out)",
+                        "h2d_bytes_per_step": int(8 * B * (n + k + 1)),
+                        "d2h_bytes_per_step": int(8 * B * (1 + n + k + o.nnz_jac + o.nnz_hess))},
+                "gpu_launches": int(launches), "roofline": roof}
+        if not args.no_cpu_baseline:
+            from oracle.dnlp_oracle import RefOracles
+            r = RefOracles(prob)
+            r.jacobianstructure(), r.hessianstructure()
+            t0, cnt = time.perf_counter(), 0
+            while time.perf_counter() - t0 < 10.0:
+                xb = X[cnt % Btot]
+                r.objective(xb), r.gradient(xb), r.constraints(xb), r.jacobian(xb), r.hessian(xb, LAM[0], 1.0)
+                cnt += 1
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": cnt / dt, "unit": "evals/s", "cores": 1, "kind": "port",
+                                    "sample": "%d starts of the same QCQP evaluated one by one in %.1f s" % (cnt, dt)}
+        print(json.dumps(line, default=float))
+    o.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------ main
 def main():
     ap = argparse.ArgumentParser()
@@ -256,6 +356,8 @@ def main():
 
     if args.workload == "c3s":
         return bench_sharded(args, rank, local_rank, world, dist, metric)
+    if args.workload == "c4":
+        return bench_multistart(args, rank, local_rank, world, dist, metric, hbm_peak, peak_src)
 
     from dnlp_b200.oracles import GpuOracles
     prob, desc = build_workload(args.workload, args.scale)

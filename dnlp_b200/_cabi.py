@@ -50,6 +50,8 @@ EXPORTS = [
     "dnlp_eval_f", "dnlp_eval_grad", "dnlp_eval_g", "dnlp_eval_jac", "dnlp_eval_hess", "dnlp_eval_all",
     "dnlp_host_alloc", "dnlp_host_free", "dnlp_upload_point", "dnlp_run_device", "dnlp_profile_instrs",
     "dnlp_read_output", "dnlp_kernel_launches", "dnlp_set_cache", "dnlp_set_dynamic", "dnlp_eval_dyn",
+    "dnlp_batch_create", "dnlp_batch_destroy", "dnlp_batch_last_error", "dnlp_batch_eval", "dnlp_batch_upload",
+    "dnlp_batch_run_device", "dnlp_batch_profile_instrs", "dnlp_batch_kernel_launches",
 ]
 
 _lib = None
@@ -92,6 +94,17 @@ def lib():
     L.dnlp_set_cache.argtypes = [vp, C.c_int32]
     L.dnlp_set_dynamic.argtypes = [vp, C.c_int32, c_i32p, C.c_int64]
     L.dnlp_eval_dyn.argtypes = [vp, C.c_int32, c_f64p, c_f64p, C.c_double, c_f64p]
+    L.dnlp_batch_create.argtypes = [C.POINTER(TapeDesc), C.c_int, C.c_int32, C.POINTER(vp)]
+    L.dnlp_batch_destroy.argtypes = [vp]
+    L.dnlp_batch_destroy.restype = None
+    L.dnlp_batch_last_error.argtypes = [vp]
+    L.dnlp_batch_last_error.restype = C.c_char_p
+    L.dnlp_batch_eval.argtypes = [vp] + [c_f64p] * 8
+    L.dnlp_batch_upload.argtypes = [vp, c_f64p, c_f64p, c_f64p]
+    L.dnlp_batch_run_device.argtypes = [vp, C.c_int32, C.c_int32, c_f32p]
+    L.dnlp_batch_profile_instrs.argtypes = [vp, C.c_int32, C.c_int32, c_f32p]
+    L.dnlp_batch_kernel_launches.argtypes = [vp]
+    L.dnlp_batch_kernel_launches.restype = C.c_int64
     _lib = L
     return L
 
@@ -130,70 +143,80 @@ class _PinnedHandle:
             self.ptr = None
 
 
+def make_tape_desc(tape):
+    """Tape -> (TapeDesc, keepalive list).  Host arrays referenced by the descriptor must stay alive
+    until dnlp_create / dnlp_batch_create has copied them to the device."""
+    keep = []
+    n_instr = len(tape.instrs)
+    arr = (InstrDesc * max(n_instr, 1))()
+    for i, ins in enumerate(tape.instrs):
+        d = arr[i]
+        d.kind, d.dst_space, d.dst_off, d.count = ins.kind, ins.dst_space, int(ins.dst_off), int(ins.count)
+        d.fcode, d.a_stride, d.b_stride = int(ins.fcode), int(ins.a_stride), int(ins.b_stride)
+        d.accumulate = int(bool(ins.accumulate))
+        d.param, d.a_off, d.b_off = float(ins.param), int(ins.a_off), int(ins.b_off)
+        d.uses_lam = int(bool(ins.uses_lam))
+        d.level = int(ins.level)
+        d.alpha, d.ncols, d.x_off, d.s_slot = float(ins.alpha), int(ins.ncols), int(ins.x_off), int(ins.s_slot)
+        if ins.kind == T.K_POLY:
+            lens = np.diff(ins.ptr)
+            uniform = lens.size > 0 and bool(np.all(lens == lens[0])) and lens[0] >= 1
+            coef = f64(ins.coef)
+            f1 = np.ascontiguousarray(ins.f1, dtype=np.int32)
+            has_f2 = bool(np.any(ins.f2 >= 0))
+            f2 = np.ascontiguousarray(ins.f2, dtype=np.int32) if has_f2 else None
+            ptr = None if uniform else np.ascontiguousarray(ins.ptr, dtype=np.int64)
+            keep += [coef, f1, f2, ptr]
+            d.ptr, d.coef, d.f1, d.f2 = _p(ptr, c_i64p), _p(coef, c_f64p), _p(f1, c_i32p), _p(f2, c_i32p)
+            d.nterms = int(coef.size)
+            d.row_len = int(lens[0]) if uniform else 0
+        elif ins.kind == T.K_GEMV:
+            Q = f64(ins.Q)
+            keep.append(Q)
+            d.Q = _p(Q, c_f64p)
+        elif ins.kind == T.K_SCALE:
+            coef = f64(ins.coef)
+            keep.append(coef)
+            d.coef = _p(coef, c_f64p)
+        if ins.pos is not None:
+            pos = np.ascontiguousarray(ins.pos, dtype=np.int32)
+            keep.append(pos)
+            d.pos = _p(pos, c_i32p)
+    td = TapeDesc()
+    td.n, td.m, td.nslots = tape.n, tape.m, tape.nslots
+    td.nnz_jac, td.nnz_hess = int(tape.jac_rows.size), int(tape.hess_rows.size)
+    td.n_instr, td.instrs = n_instr, arr
+    for name, pid in PROG_IDS.items():
+        p = np.ascontiguousarray(tape.programs.get(name, []), dtype=np.int32)
+        keep.append(p)
+        td.prog[pid] = _p(p, c_i32p) if p.size else None
+        td.prog_len[pid] = int(p.size)
+    consts = [f64(tape.grad_const), f64(tape.g_const), f64(tape.jac_const), f64(tape.hess_const)]
+    keep += consts
+    td.f_const = float(tape.f_const)
+    td.grad_const, td.g_const, td.jac_const, td.hess_const = [_p(c, c_f64p) if c.size else None for c in consts]
+    keep += [arr, td]
+    return td, keep
+
+
+def _require_device(L):
+    if L.dnlp_device_count() <= 0:
+        raise RuntimeError("dnlp_b200: no CUDA device visible (the oracle has no CPU fallback)")
+
+
 class DeviceTape:
     """Uploads a compiled ``Tape`` and owns the ``dnlp_oracle`` handle."""
 
     def __init__(self, tape, device=0):
         L = lib()
-        if L.dnlp_device_count() <= 0:
-            raise RuntimeError("dnlp_b200: no CUDA device visible (the oracle has no CPU fallback)")
+        _require_device(L)
         self.tape = tape
-        self._keep = []
-        n_instr = len(tape.instrs)
-        arr = (InstrDesc * max(n_instr, 1))()
-        for i, ins in enumerate(tape.instrs):
-            d = arr[i]
-            d.kind, d.dst_space, d.dst_off, d.count = ins.kind, ins.dst_space, int(ins.dst_off), int(ins.count)
-            d.fcode, d.a_stride, d.b_stride = int(ins.fcode), int(ins.a_stride), int(ins.b_stride)
-            d.accumulate = int(bool(ins.accumulate))
-            d.param, d.a_off, d.b_off = float(ins.param), int(ins.a_off), int(ins.b_off)
-            d.uses_lam = int(bool(ins.uses_lam))
-            d.level = int(ins.level)
-            d.alpha, d.ncols, d.x_off, d.s_slot = float(ins.alpha), int(ins.ncols), int(ins.x_off), int(ins.s_slot)
-            if ins.kind == T.K_POLY:
-                lens = np.diff(ins.ptr)
-                uniform = lens.size > 0 and bool(np.all(lens == lens[0])) and lens[0] >= 1
-                coef = f64(ins.coef)
-                f1 = np.ascontiguousarray(ins.f1, dtype=np.int32)
-                has_f2 = bool(np.any(ins.f2 >= 0))
-                f2 = np.ascontiguousarray(ins.f2, dtype=np.int32) if has_f2 else None
-                ptr = None if uniform else np.ascontiguousarray(ins.ptr, dtype=np.int64)
-                self._keep += [coef, f1, f2, ptr]
-                d.ptr, d.coef, d.f1, d.f2 = _p(ptr, c_i64p), _p(coef, c_f64p), _p(f1, c_i32p), _p(f2, c_i32p)
-                d.nterms = int(coef.size)
-                d.row_len = int(lens[0]) if uniform else 0
-            elif ins.kind == T.K_GEMV:
-                Q = f64(ins.Q)
-                self._keep.append(Q)
-                d.Q = _p(Q, c_f64p)
-            elif ins.kind == T.K_SCALE:
-                coef = f64(ins.coef)
-                self._keep.append(coef)
-                d.coef = _p(coef, c_f64p)
-            if ins.pos is not None:
-                pos = np.ascontiguousarray(ins.pos, dtype=np.int32)
-                self._keep.append(pos)
-                d.pos = _p(pos, c_i32p)
-        td = TapeDesc()
-        td.n, td.m, td.nslots = tape.n, tape.m, tape.nslots
-        td.nnz_jac, td.nnz_hess = int(tape.jac_rows.size), int(tape.hess_rows.size)
-        td.n_instr, td.instrs = n_instr, arr
-        for name, pid in PROG_IDS.items():
-            p = np.ascontiguousarray(tape.programs.get(name, []), dtype=np.int32)
-            self._keep.append(p)
-            td.prog[pid] = _p(p, c_i32p) if p.size else None
-            td.prog_len[pid] = int(p.size)
-        consts = [f64(tape.grad_const), f64(tape.g_const), f64(tape.jac_const), f64(tape.hess_const)]
-        self._keep += consts
-        td.f_const = float(tape.f_const)
-        td.grad_const, td.g_const, td.jac_const, td.hess_const = [_p(c, c_f64p) if c.size else None for c in consts]
-        self._keep += [arr, td]
+        td, keep = make_tape_desc(tape)
         h = C.c_void_p()
         if L.dnlp_create(C.byref(td), int(device), C.byref(h)) != 0:
             raise RuntimeError("dnlp_create failed: %s" % L.dnlp_last_error(None).decode())
         self.h = h
         self._L = L
-        self._keep = [arr, td]   # host staging copies are no longer needed after upload
 
     def check(self, rc):
         if rc != 0:
@@ -202,6 +225,36 @@ class DeviceTape:
     def close(self):
         if getattr(self, "h", None):
             self._L.dnlp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceBatch:
+    """Batched (multi-start) counterpart of ``DeviceTape``: owns a ``dnlp_batch`` handle."""
+
+    def __init__(self, tape, batch, device=0):
+        L = lib()
+        _require_device(L)
+        self.tape, self.batch = tape, int(batch)
+        td, keep = make_tape_desc(tape)
+        h = C.c_void_p()
+        if L.dnlp_batch_create(C.byref(td), int(device), int(batch), C.byref(h)) != 0:
+            raise RuntimeError("dnlp_batch_create failed: %s" % L.dnlp_batch_last_error(None).decode())
+        self.h = h
+        self._L = L
+
+    def check(self, rc):
+        if rc != 0:
+            raise RuntimeError("dnlp_b200: %s" % self._L.dnlp_batch_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._L.dnlp_batch_destroy(self.h)
             self.h = None
 
     def __del__(self):

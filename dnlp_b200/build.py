@@ -6,8 +6,9 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 LIB = os.path.join(PKG, "libdnlp_b200.so")
-SOURCES = [os.path.join(PKG, "csrc", "dnlp_cabi.cu")]
-HEADERS = [os.path.join(PKG, "csrc", "dnlp_kernels.cuh"), os.path.join(ROOT, "include", "dnlp_b200.h")]
+SOURCES = [os.path.join(PKG, "csrc", "dnlp_cabi.cu"), os.path.join(PKG, "csrc", "dnlp_batch.cu")]
+HEADERS = [os.path.join(PKG, "csrc", "dnlp_kernels.cuh"), os.path.join(PKG, "csrc", "dnlp_batch_kernels.cuh"),
+           os.path.join(ROOT, "include", "dnlp_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

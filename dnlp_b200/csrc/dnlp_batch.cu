@@ -1,0 +1,335 @@
+// Batched (multi-start) engine behind the C-ABI: the same tape evaluated at B points in lock step.
+// See include/dnlp_b200.h (dnlp_batch_*) and dnlp_batch_kernels.cuh.
+#include "../../include/dnlp_b200.h"
+#include "dnlp_batch_kernels.cuh"
+
+#include <cstdio>
+#include <string>
+#include <vector>
+
+namespace {
+thread_local std::string g_batch_create_error;
+
+#define CKB(call)                                                                          \
+  do {                                                                                     \
+    cudaError_t e_ = (call);                                                               \
+    if (e_ != cudaSuccess) {                                                               \
+      char buf_[512];                                                                      \
+      snprintf(buf_, sizeof buf_, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,      \
+               cudaGetErrorString(e_));                                                    \
+      err = buf_;                                                                          \
+      return 1;                                                                            \
+    }                                                                                      \
+  } while (0)
+
+struct BInstr {
+  dnlp_instr_desc d;
+  bool has_f2 = false;
+};
+}  // namespace
+
+struct dnlp_batch {
+  int device = 0, sm_count = 148, B = 0;
+  int64_t n = 0, m = 0, nslots = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double *V = nullptr;                   // nslots x B, batch fastest
+  double *out[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};      // len x B, batch fastest
+  double *out_const[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int64_t out_len[6] = {0, 0, 0, 0, 0, 0};
+  double *stage = nullptr;               // staging for layout changes (max(len) x B)
+  int64_t stage_len = 0;
+  std::vector<BInstr> instrs;
+  std::vector<int32_t> prog[DNLP_NPROG];
+  std::vector<void *> owned;
+  int64_t launches = 0;
+  std::string err;
+
+  template <typename T>
+  int upload(const T *host, int64_t count, T **dev) {
+    *dev = nullptr;
+    if (count <= 0 || host == nullptr) return 0;
+    void *p = nullptr;
+    CKB(cudaMalloc(&p, (size_t)count * sizeof(T)));
+    owned.push_back(p);
+    CKB(cudaMemcpy(p, host, (size_t)count * sizeof(T), cudaMemcpyHostToDevice));
+    *dev = static_cast<T *>(p);
+    return 0;
+  }
+  int grid_for(int64_t items) const {
+    int64_t need = (items + 255) / 256, cap = (int64_t)sm_count * 8;
+    return (int)(need < 1 ? 1 : (need > cap ? cap : need));
+  }
+  int launch(const BInstr &I);
+  int run_program(int p);
+  int reset_outputs();
+  int put(const double *host, double *dev_batch_major, int64_t len);
+  int get(int space, double *host);
+};
+
+namespace {
+using namespace dnlp;
+
+template <int F, bool Bn>
+void launch_belem_t(const dnlp_batch *o, const dnlp_instr_desc &d, int grid) {
+  belem_kernel<F, Bn><<<grid, 256, 0, o->stream>>>(o->V, d.a_off, d.a_stride, d.b_off, d.b_stride, d.dst_off,
+                                                  d.count, d.param, o->B);
+}
+bool launch_belem(const dnlp_batch *o, const dnlp_instr_desc &d, int grid) {
+  switch (d.fcode) {
+#define U(F) case F: launch_belem_t<F, false>(o, d, grid); return true;
+#define Bn(F) case F: launch_belem_t<F, true>(o, d, grid); return true;
+    U(F_EXP) U(F_LOG) U(F_ENTR) U(F_NEG_LOG_M1) U(F_RECIP) U(F_NEG_RECIP) U(F_NEG_RECIP_SQ)
+    U(F_LOGISTIC) U(F_LOGISTIC_D1) U(F_LOGISTIC_D2) U(F_POW)
+    U(F_SIN) U(F_COS) U(F_NEG_SIN) U(F_NEG_COS) U(F_TAN) U(F_TAN_D1) U(F_TAN_D2)
+    U(F_SINH) U(F_COSH) U(F_TANH) U(F_TANH_D1) U(F_TANH_D2)
+    U(F_ASINH) U(F_ASINH_D1) U(F_ASINH_D2) U(F_ATANH) U(F_ATANH_D1) U(F_ATANH_D2)
+    U(F_XEXP) U(F_XEXP_D1) U(F_XEXP_D2)
+    Bn(F_REL_ENTR) Bn(F_LOG_RATIO_P1) Bn(F_DIV) Bn(F_DIV_SQ) Bn(F_DIV_CUBE)
+#undef U
+#undef Bn
+    default: return false;
+  }
+}
+}  // namespace
+
+int dnlp_batch::launch(const BInstr &I) {
+  const dnlp_instr_desc &d = I.d;
+  if (d.count <= 0) return 0;
+  double *dst = (d.dst_space == DNLP_DST_V) ? V + d.dst_off * B : out[d.dst_space] + d.dst_off * B;
+  switch (d.kind) {
+    case DNLP_ELEM:
+      if (!launch_belem(this, d, grid_for(d.count * B))) { err = "unknown elementwise function code"; return 1; }
+      break;
+    case DNLP_POLY: {
+      const int threads = B >= 256 ? 256 : ((B + 31) / 32) * 32;
+      const int bchunks = (B + threads - 1) / threads;
+      int64_t blocks = d.count * bchunks, cap = (int64_t)sm_count * 16;
+      int grid = (int)(blocks < cap ? blocks : cap);
+      if (I.has_f2)
+        bpoly_kernel<true><<<grid, threads, 0, stream>>>(V, dst, d.ptr, d.row_len, d.coef, d.f1, d.f2, d.pos, d.count, d.accumulate, B);
+      else
+        bpoly_kernel<false><<<grid, threads, 0, stream>>>(V, dst, d.ptr, d.row_len, d.coef, d.f1, d.f2, d.pos, d.count, d.accumulate, B);
+      break;
+    }
+    case DNLP_GEMV: {
+      const int tiles = (int)(((d.count + GM - 1) / GM) * ((B + GN - 1) / GN));
+      const int cap = sm_count * 4;
+      bgemm_dmma_kernel<<<tiles < cap ? tiles : cap, 128, 0, stream>>>(d.Q, V + d.x_off * B, dst, (int)d.count, B,
+                                                                      (int)d.ncols, d.alpha);
+      break;
+    }
+    case DNLP_SCALE:
+      bscale_kernel<<<grid_for(d.count * B), 256, 0, stream>>>(V, d.s_slot, d.coef, dst, d.pos, d.count, d.accumulate, B);
+      break;
+    default:
+      err = "unknown instruction kind";
+      return 1;
+  }
+  ++launches;
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) { err = std::string("kernel launch failed: ") + cudaGetErrorString(e); return 1; }
+  return 0;
+}
+
+int dnlp_batch::run_program(int p) {
+  for (int32_t id : prog[p]) if (launch(instrs[id])) return 1;
+  return 0;
+}
+
+int dnlp_batch::put(const double *host, double *dev, int64_t len) {
+  if (len <= 0) return 0;
+  CKB(cudaMemcpyAsync(stage, host, (size_t)len * B * sizeof(double), cudaMemcpyHostToDevice, stream));
+  const int64_t tiles = ((len + 31) / 32) * ((B + 31) / 32);
+  to_batch_major_kernel<<<(int)(tiles < sm_count * 8 ? tiles : sm_count * 8), 256, 0, stream>>>(stage, dev, len, B);
+  ++launches;
+  return 0;
+}
+
+int dnlp_batch::get(int space, double *host) {
+  const int64_t len = out_len[space];
+  if (host == nullptr || len <= 0) return 0;
+  const int64_t tiles = ((len + 31) / 32) * ((B + 31) / 32);
+  from_batch_major_kernel<<<(int)(tiles < sm_count * 8 ? tiles : sm_count * 8), 256, 0, stream>>>(out[space], stage, len, B);
+  ++launches;
+  CKB(cudaMemcpyAsync(host, stage, (size_t)len * B * sizeof(double), cudaMemcpyDeviceToHost, stream));
+  return 0;
+}
+
+extern "C" {
+
+void dnlp_batch_destroy(dnlp_batch *o) {
+  if (!o) return;
+  cudaSetDevice(o->device);
+  if (o->stream) cudaStreamSynchronize(o->stream);
+  for (void *p : o->owned) cudaFree(p);
+  if (o->ev0) cudaEventDestroy(o->ev0);
+  if (o->ev1) cudaEventDestroy(o->ev1);
+  if (o->stream) cudaStreamDestroy(o->stream);
+  delete o;
+}
+
+static int batch_create_impl(dnlp_batch *o, const dnlp_tape_desc *t) {
+  std::string &err = o->err;
+  CKB(cudaSetDevice(o->device));
+  cudaDeviceProp prop;
+  CKB(cudaGetDeviceProperties(&prop, o->device));
+  o->sm_count = prop.multiProcessorCount;
+  CKB(cudaStreamCreateWithFlags(&o->stream, cudaStreamNonBlocking));
+  CKB(cudaEventCreate(&o->ev0));
+  CKB(cudaEventCreate(&o->ev1));
+  o->n = t->n; o->m = t->m; o->nslots = t->nslots;
+  const int B = o->B;
+  void *p = nullptr;
+  CKB(cudaMalloc(&p, (size_t)(t->nslots + 2) * B * sizeof(double)));
+  o->owned.push_back(p);
+  o->V = static_cast<double *>(p);
+  CKB(cudaMemset(o->V, 0, (size_t)(t->nslots + 2) * B * sizeof(double)));
+  const int64_t lens[6] = {0, 1, t->n, t->m, t->nnz_jac, t->nnz_hess};
+  const double *consts[6] = {nullptr, &t->f_const, t->grad_const, t->g_const, t->jac_const, t->hess_const};
+  int64_t maxlen = t->n > t->m ? t->n : t->m;
+  for (int s = 1; s < 6; ++s) {
+    o->out_len[s] = lens[s];
+    if (lens[s] > maxlen) maxlen = lens[s];
+    CKB(cudaMalloc(&p, (size_t)(lens[s] + 2) * B * sizeof(double)));
+    o->owned.push_back(p);
+    o->out[s] = static_cast<double *>(p);
+    if (lens[s] > 0 && consts[s]) { if (o->upload(consts[s], lens[s], &o->out_const[s])) return 1; }
+  }
+  o->stage_len = maxlen + 2;
+  CKB(cudaMalloc(&p, (size_t)o->stage_len * B * sizeof(double)));
+  o->owned.push_back(p);
+  o->stage = static_cast<double *>(p);
+
+  o->instrs.resize(t->n_instr);
+  for (int i = 0; i < t->n_instr; ++i) {
+    const dnlp_instr_desc &h = t->instrs[i];
+    BInstr &D = o->instrs[i];
+    D.d = h;
+    D.d.ptr = nullptr; D.d.coef = nullptr; D.d.f1 = nullptr; D.d.f2 = nullptr; D.d.pos = nullptr; D.d.Q = nullptr;
+    if (h.kind == DNLP_POLY) {
+      if (h.ptr) { if (o->upload(h.ptr, h.count + 1, const_cast<int64_t **>(&D.d.ptr))) return 1; }
+      if (o->upload(h.coef, h.nterms, const_cast<double **>(&D.d.coef))) return 1;
+      if (o->upload(h.f1, h.nterms, const_cast<int32_t **>(&D.d.f1))) return 1;
+      if (h.f2) { if (o->upload(h.f2, h.nterms, const_cast<int32_t **>(&D.d.f2))) return 1; }
+      D.has_f2 = h.f2 != nullptr;
+    } else if (h.kind == DNLP_GEMV) {
+      if (o->upload(h.Q, h.count * h.ncols, const_cast<double **>(&D.d.Q))) return 1;
+    } else if (h.kind == DNLP_SCALE) {
+      if (o->upload(h.coef, h.count, const_cast<double **>(&D.d.coef))) return 1;
+    }
+    if ((h.kind == DNLP_POLY || h.kind == DNLP_SCALE) && h.pos) {
+      if (o->upload(h.pos, h.count, const_cast<int32_t **>(&D.d.pos))) return 1;
+    }
+  }
+  for (int q = 0; q < DNLP_NPROG; ++q) o->prog[q].assign(t->prog[q], t->prog[q] + t->prog_len[q]);
+  if (o->reset_outputs()) return 1;
+  CKB(cudaStreamSynchronize(o->stream));
+  return 0;
+}
+
+int dnlp_batch_create(const dnlp_tape_desc *t, int device, int32_t batch, dnlp_batch **out) {
+  *out = nullptr;
+  if (batch <= 0) { g_batch_create_error = "batch must be positive"; return 1; }
+  dnlp_batch *o = new dnlp_batch();
+  o->device = device;
+  o->B = batch;
+  if (batch_create_impl(o, t)) {
+    g_batch_create_error = o->err;
+    dnlp_batch_destroy(o);
+    return 1;
+  }
+  *out = o;
+  return 0;
+}
+
+const char *dnlp_batch_last_error(dnlp_batch *o) { return o ? o->err.c_str() : g_batch_create_error.c_str(); }
+
+}  // extern "C"
+
+int dnlp_batch::reset_outputs() {
+  for (int s = 1; s < 6; ++s) {
+    if (out_len[s] <= 0) continue;
+    if (out_const[s]) {
+      bfill_kernel<<<grid_for(out_len[s] * B), 256, 0, stream>>>(out_const[s], out[s], out_len[s], B);
+      ++launches;
+    } else {
+      CKB(cudaMemsetAsync(out[s], 0, (size_t)out_len[s] * B * sizeof(double), stream));
+    }
+  }
+  return 0;
+}
+
+extern "C" {
+
+int dnlp_batch_upload(dnlp_batch *o, const double *X, const double *LAM, const double *SIGMA) {
+  std::string &err = o->err;
+  CKB(cudaSetDevice(o->device));
+  if (o->put(X, o->V, o->n)) return 1;
+  if (SIGMA) CKB(cudaMemcpyAsync(o->V + o->n * o->B, SIGMA, (size_t)o->B * sizeof(double), cudaMemcpyHostToDevice, o->stream));
+  if (LAM && o->m > 0) { if (o->put(LAM, o->V + (o->n + 1) * o->B, o->m)) return 1; }
+  CKB(cudaStreamSynchronize(o->stream));
+  return 0;
+}
+
+int dnlp_batch_eval(dnlp_batch *o, const double *X, const double *LAM, const double *SIGMA,
+                    double *F, double *GRAD, double *G, double *JAC, double *HESS) {
+  std::string &err = o->err;
+  CKB(cudaSetDevice(o->device));
+  if (o->put(X, o->V, o->n)) return 1;
+  const bool want_h = HESS != nullptr;
+  if (want_h) {
+    if (!SIGMA || (o->m > 0 && !LAM)) { err = "hessian requested without multipliers"; return 1; }
+    CKB(cudaMemcpyAsync(o->V + o->n * o->B, SIGMA, (size_t)o->B * sizeof(double), cudaMemcpyHostToDevice, o->stream));
+    if (o->m > 0) { if (o->put(LAM, o->V + (o->n + 1) * o->B, o->m)) return 1; }
+  }
+  double *outs[6] = {nullptr, F, GRAD, G, JAC, HESS};
+  for (int p = 0; p < 5; ++p)
+    if (outs[p + 1] && o->run_program(p)) return 1;
+  for (int s = 1; s < 6; ++s)
+    if (outs[s]) {
+      if (o->get(s, outs[s])) return 1;
+      CKB(cudaStreamSynchronize(o->stream));      // the staging buffer is reused by the next output
+    }
+  CKB(cudaStreamSynchronize(o->stream));
+  return 0;
+}
+
+int dnlp_batch_run_device(dnlp_batch *o, int32_t prog_mask, int32_t iters, float *elapsed_ms) {
+  std::string &err = o->err;
+  CKB(cudaSetDevice(o->device));
+  CKB(cudaEventRecord(o->ev0, o->stream));
+  for (int it = 0; it < iters; ++it)
+    for (int p = 0; p < DNLP_NPROG; ++p)
+      if (prog_mask & (1 << p))
+        if (o->run_program(p)) return 1;
+  CKB(cudaEventRecord(o->ev1, o->stream));
+  CKB(cudaEventSynchronize(o->ev1));
+  float ms = 0.f;
+  CKB(cudaEventElapsedTime(&ms, o->ev0, o->ev1));
+  if (elapsed_ms) *elapsed_ms = ms;
+  return 0;
+}
+
+int dnlp_batch_profile_instrs(dnlp_batch *o, int32_t p, int32_t iters, float *ms_per_instr) {
+  std::string &err = o->err;
+  CKB(cudaSetDevice(o->device));
+  for (size_t i = 0; i < o->instrs.size(); ++i) ms_per_instr[i] = 0.f;
+  for (int32_t id : o->prog[p]) if (o->launch(o->instrs[id])) return 1;
+  CKB(cudaStreamSynchronize(o->stream));
+  for (int it = 0; it < iters; ++it)
+    for (int32_t id : o->prog[p]) {
+      CKB(cudaEventRecord(o->ev0, o->stream));
+      if (o->launch(o->instrs[id])) return 1;
+      CKB(cudaEventRecord(o->ev1, o->stream));
+      CKB(cudaEventSynchronize(o->ev1));
+      float ms = 0.f;
+      CKB(cudaEventElapsedTime(&ms, o->ev0, o->ev1));
+      ms_per_instr[id] += ms / (float)iters;
+    }
+  return 0;
+}
+
+int64_t dnlp_batch_kernel_launches(dnlp_batch *o) { return o->launches; }
+
+}  // extern "C"

@@ -1,0 +1,194 @@
+// Batched (multi-start) execution of the same tape: B independent points evaluated in lock step.
+// Value buffer layout is slot-major with the batch index fastest, V[slot * B + b], so every
+// gather / elementwise / segmented-sum access is coalesced across the batch and the tape's
+// index and coefficient streams are warp-uniform (broadcast) loads.  The dense quad_form map
+// Q @ X becomes a real GEMM [n x n] x [n x B] and runs on the FP64 tensor cores (DMMA,
+// mma.sync.m8n8k4.f64) - the only place in this code base where tensor cores apply.
+#pragma once
+#include "dnlp_kernels.cuh"
+
+namespace dnlp {
+
+// ---- elementwise -------------------------------------------------------------------------------
+template <int F, bool BINARY>
+__global__ void __launch_bounds__(256)
+belem_kernel(double *__restrict__ V, int64_t a_off, int a_stride, int64_t b_off, int b_stride,
+             int64_t dst_off, int64_t count, double p, int B) {
+  const int64_t total = count * B;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t k = e / B;
+    const int b = (int)(e - k * B);
+    const double a = V[(a_off + k * a_stride) * B + b];
+    const double bb = BINARY ? V[(b_off + k * b_stride) * B + b] : 0.0;
+    V[dst_off * B + e] = apply_fn<F>(a, bb, p);
+  }
+}
+
+// ---- POLY / SCALE: one thread per (row, start) ---------------------------------------------------
+template <bool HAS_F2>
+__global__ void __launch_bounds__(256)
+bpoly_kernel(const double *__restrict__ V, double *__restrict__ dst, const int64_t *__restrict__ ptr,
+             int row_len, const double *__restrict__ coef, const int32_t *__restrict__ f1,
+             const int32_t *__restrict__ f2, const int32_t *__restrict__ pos, int64_t count,
+             int accumulate, int B) {
+  const int bchunks = (B + blockDim.x - 1) / blockDim.x;
+  const int64_t nblk = count * bchunks;
+  for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+    const int64_t row = blk / bchunks;
+    const int b = (int)(blk - row * bchunks) * blockDim.x + threadIdx.x;
+    if (b >= B) continue;
+    int64_t t0, t1;
+    if (ptr) { t0 = __ldg(ptr + row); t1 = __ldg(ptr + row + 1); }
+    else { t0 = row * (int64_t)row_len; t1 = t0 + row_len; }
+    double acc = 0.0;
+    for (int64_t t = t0; t < t1; ++t) {
+      const int i1 = __ldg(f1 + t);
+      double v = __ldg(coef + t);
+      if (i1 >= 0) v *= V[(int64_t)i1 * B + b];
+      if (HAS_F2) { const int i2 = __ldg(f2 + t); if (i2 >= 0) v *= V[(int64_t)i2 * B + b]; }
+      acc += v;
+    }
+    const int64_t d = (pos ? (int64_t)__ldg(pos + row) : row) * B + b;
+    dst[d] = accumulate ? dst[d] + acc : acc;
+  }
+}
+
+static __global__ void __launch_bounds__(256)
+bscale_kernel(const double *__restrict__ V, int64_t s_slot, const double *__restrict__ coef,
+              double *__restrict__ dst, const int32_t *__restrict__ pos, int64_t count, int accumulate, int B) {
+  const int64_t total = count * B;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t k = e / B;
+    const int b = (int)(e - k * B);
+    const double v = V[s_slot * B + b] * __ldg(coef + k);
+    const int64_t d = (pos ? (int64_t)__ldg(pos + k) : k) * B + b;
+    dst[d] = accumulate ? dst[d] + v : v;
+  }
+}
+
+// ---- layout changes between the caller's per-start arrays and the batch-fastest device layout -----
+// in:  src[b * len + i]  (start b contiguous)  ->  dst[i * B + b]
+static __global__ void __launch_bounds__(256)
+to_batch_major_kernel(const double *__restrict__ src, double *__restrict__ dst, int64_t len, int B) {
+  __shared__ double tile[32][33];
+  const int64_t tiles_i = (len + 31) / 32, tiles_b = (B + 31) / 32;
+  for (int64_t t = blockIdx.x; t < tiles_i * tiles_b; t += gridDim.x) {
+    const int64_t ti = t % tiles_i, tb = t / tiles_i;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 x 8 threads
+    for (int r = ty; r < 32; r += 8) {
+      const int64_t b = tb * 32 + r, i = ti * 32 + tx;
+      tile[r][tx] = (b < B && i < len) ? src[b * len + i] : 0.0;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+      const int64_t i = ti * 32 + r, b = tb * 32 + tx;
+      if (i < len && b < B) dst[i * B + b] = tile[tx][r];
+    }
+    __syncthreads();
+  }
+}
+// out: src[i * B + b] -> dst[b * len + i]
+static __global__ void __launch_bounds__(256)
+from_batch_major_kernel(const double *__restrict__ src, double *__restrict__ dst, int64_t len, int B) {
+  __shared__ double tile[32][33];
+  const int64_t tiles_i = (len + 31) / 32, tiles_b = (B + 31) / 32;
+  for (int64_t t = blockIdx.x; t < tiles_i * tiles_b; t += gridDim.x) {
+    const int64_t tb = t % tiles_b, ti = t / tiles_b;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) {
+      const int64_t i = ti * 32 + r, b = tb * 32 + tx;
+      tile[r][tx] = (i < len && b < B) ? src[i * B + b] : 0.0;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+      const int64_t b = tb * 32 + r, i = ti * 32 + tx;
+      if (b < B && i < len) dst[b * len + i] = tile[tx][r];
+    }
+    __syncthreads();
+  }
+}
+// broadcast a per-entry constant over the batch: dst[i * B + b] = c[i]
+static __global__ void __launch_bounds__(256)
+bfill_kernel(const double *__restrict__ c, double *__restrict__ dst, int64_t len, int B) {
+  const int64_t total = len * B;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x)
+    dst[e] = c[e / B];
+}
+
+// ---- K7: FP64 tensor-core GEMM  Y[M x N] = alpha * Q[M x K] * X[K x N]  (all row-major) -----------
+// CTA tile 64 x 64, K step 16, 4 warps each owning a 32 x 32 sub-tile = 4 x 4 DMMA m8n8k4 tiles
+// (32 fp64 accumulators per thread).  Operand tiles are staged in shared memory with cp.async,
+// double buffered.  Edge tiles are zero-padded on load and masked on store.
+__device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+constexpr int GM = 64, GN = 64, GK = 16;
+
+static __global__ void __launch_bounds__(128)
+bgemm_dmma_kernel(const double *__restrict__ Q, const double *__restrict__ X, double *__restrict__ Y,
+                  int M, int N, int K, double alpha) {
+  __shared__ __align__(16) double As[2][GM][GK + 4];     // row stride = 4 (mod 16) doubles: conflict-free fragment reads
+  __shared__ __align__(16) double Bs[2][GK][GN + 4];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+  const int g = lane >> 2, tg = lane & 3;
+  const int tiles_n = (N + GN - 1) / GN, tiles_m = (M + GM - 1) / GM;
+  for (int tile = blockIdx.x; tile < tiles_m * tiles_n; tile += gridDim.x) {
+    const int m0 = (tile / tiles_n) * GM, n0 = (tile % tiles_n) * GN;
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    auto load_tiles = [&](int buf, int k0) {
+      // A tile: 64 x 16 doubles = 1024 elements, 8 per thread
+      for (int e = tid; e < GM * GK; e += 128) {
+        const int r = e / GK, c = e % GK;
+        const int gm = m0 + r, gk = k0 + c;
+        As[buf][r][c] = (gm < M && gk < K) ? __ldg(Q + (int64_t)gm * K + gk) : 0.0;
+      }
+      // B tile: 16 x 64
+      for (int e = tid; e < GK * GN; e += 128) {
+        const int r = e / GN, c = e % GN;
+        const int gk = k0 + r, gn = n0 + c;
+        Bs[buf][r][c] = (gk < K && gn < N) ? X[(int64_t)gk * N + gn] : 0.0;
+      }
+    };
+    const int ksteps = (K + GK - 1) / GK;
+    load_tiles(0, 0);
+    __syncthreads();
+    for (int ks = 0; ks < ksteps; ++ks) {
+      const int buf = ks & 1;
+      if (ks + 1 < ksteps) load_tiles(buf ^ 1, (ks + 1) * GK);
+#pragma unroll
+      for (int kk = 0; kk < GK; kk += 4) {
+        double a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = As[buf][wm + i * 8 + g][kk + tg];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = Bs[buf][kk + tg][wn + j * 8 + g];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = m0 + wm + i * 8 + g, c = n0 + wn + j * 8 + tg * 2;
+        if (r < M) {
+          if (c < N) Y[(int64_t)r * N + c] = alpha * acc[i][j][0];
+          if (c + 1 < N) Y[(int64_t)r * N + c + 1] = alpha * acc[i][j][1];
+        }
+      }
+    __syncthreads();
+  }
+}
+
+}  // namespace dnlp

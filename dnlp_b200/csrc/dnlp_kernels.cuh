@@ -226,7 +226,7 @@ gemv_kernel(const double *__restrict__ Q, const double *__restrict__ V, int64_t 
 }
 
 // ---- SCALE: dst[pos?[k]] = V[s] * coef[k]  (dense quad_form Hessian: 2*sigma*Q_lower) -------
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 scale_kernel(const double *__restrict__ V, int64_t s_slot, const double *__restrict__ coef,
              double *__restrict__ dst, const int32_t *__restrict__ pos, int64_t count, int accumulate) {
   const double s = __ldg(V + s_slot);
@@ -563,7 +563,7 @@ __device__ __forceinline__ void elem_tile(double *__restrict__ V, const ElemDesc
   }
 }
 
-__global__ void __launch_bounds__(256, 3)
+static __global__ void __launch_bounds__(256, 3)
 elem_batch_kernel(double *__restrict__ V, const ElemDesc *__restrict__ descs, int ndesc, int64_t total_tiles) {
   __shared__ ElemDesc d;
   for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -659,7 +659,7 @@ poly_reduce_kernel(const double *__restrict__ V, double *__restrict__ dst, const
 }
 
 // ---- compaction of the x/lambda-dependent entries of an output before the D2H copy ----------
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 gather_kernel(const double *__restrict__ src, const int32_t *__restrict__ pos, double *__restrict__ dst,
               int64_t count) {
   for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += (int64_t)gridDim.x * blockDim.x)

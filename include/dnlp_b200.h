@@ -139,6 +139,23 @@ int dnlp_read_output(dnlp_oracle *o, int32_t dst_space, double *out);   /* D2H o
 int64_t dnlp_kernel_launches(dnlp_oracle *o);                           /* launches since create */
 int dnlp_set_cache(dnlp_oracle *o, int32_t enabled);                    /* x-keyed forward cache on/off */
 
+/* ---- batched multi-start evaluation (BASELINE config 4; the reference's serial `best_of` loop,
+ *      cvxpy/problems/problem.py:1249-1275, evaluates one start at a time) ----
+ * The same tape is evaluated at `batch` independent points in lock step.  Host arrays hold one
+ * start per contiguous block: X[b*n + i], LAM[b*m + j], SIGMA[b], and likewise every output
+ * (F[b], GRAD[b*n + i], G[b*m + j], JAC[b*nnz_jac + k], HESS[b*nnz_hess + k]).  A NULL output is
+ * skipped together with its program.  Dense quad_form maps become FP64 tensor-core GEMMs. */
+typedef struct dnlp_batch dnlp_batch;
+int dnlp_batch_create(const dnlp_tape_desc *tape, int device, int32_t batch, dnlp_batch **out);
+void dnlp_batch_destroy(dnlp_batch *b);
+const char *dnlp_batch_last_error(dnlp_batch *b);
+int dnlp_batch_eval(dnlp_batch *b, const double *X, const double *LAM, const double *SIGMA,
+                    double *F, double *GRAD, double *G, double *JAC, double *HESS);
+int dnlp_batch_upload(dnlp_batch *b, const double *X, const double *LAM, const double *SIGMA);
+int dnlp_batch_run_device(dnlp_batch *b, int32_t prog_mask, int32_t iters, float *elapsed_ms);
+int dnlp_batch_profile_instrs(dnlp_batch *b, int32_t prog, int32_t iters, float *ms_per_instr);
+int64_t dnlp_batch_kernel_launches(dnlp_batch *b);
+
 #ifdef __cplusplus
 }
 #endif

@@ -155,3 +155,99 @@ def test_gpu_constant_entry_elision(name, gpu_mod, monkeypatch):
             assert_close(o.hessian(p["x"], p["lam"], float(p["sigma"])), p["hess"], "hess[%d]" % i)
     finally:
         o.close()
+
+
+def test_gpu_unconstrained_and_scalar_edge_cases(gpu_mod):
+    """m = 0 (no constraints: empty g / J / lambda), n = 1, and an objective that is constant."""
+    from dnlp_b200 import ir
+    x = ir.Variable(5)
+    p0 = ir.ProblemIR(ir.sum(ir.exp(x)) + ir.sum(ir.power(x, 4)), [], x0=np.linspace(-1, 1, 5))
+    _cmp_with_oracle(p0, gpu_mod)
+    o = gpu_mod(p0)
+    try:
+        assert o.constraints(p0.x0).size == 0 and o.jacobian(p0.x0).size == 0
+        assert o.jacobianstructure()[0].size == 0
+    finally:
+        o.close()
+    s = ir.Variable(1)
+    p1 = ir.ProblemIR(ir.sum(ir.logistic(s)), [ir.sum(ir.power(s, 2)) + (-1.0)], x0=np.array([0.3]))
+    _cmp_with_oracle(p1, gpu_mod)
+    y = ir.Variable(3)
+    p2 = ir.ProblemIR(ir.Constant(0.0), [ir.sum(ir.exp(y)) + (-3.0), y[0] + (-1.0) * y[1]], x0=np.array([0.1, 0.2, 0.3]))
+    _cmp_with_oracle(p2, gpu_mod)
+
+
+def test_gpu_knitro_style_calls(gpu_mod):
+    """Knitro's wrappers pass Python lists and may pass sigma = 0 (knitro_nlpif.py:272-289)."""
+    g = Golden("hs071")
+    ref = RefOracles(g.problem)
+    ref.jacobianstructure(), ref.hessianstructure()
+    o = gpu_mod(g.problem)
+    try:
+        p = g.points[1]
+        x, lam = list(p["x"]), list(p["lam"])
+        assert_close(o.objective(x), ref.objective(np.array(x)), "f")
+        assert_close(o.hessian(x, lam, 0.0), ref.hessian(np.array(x), np.array(lam), 0.0), "hess sigma=0")
+        assert o.gradient(x) is o.gradient(x)        # same buffer object every call (nlp_solver.py:184,235)
+        o.intermediate(0, 7, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0)
+        assert o.iterations == 7
+        with pytest.raises(ValueError):
+            o.objective(np.zeros(3))
+    finally:
+        o.close()
+
+
+@pytest.mark.parametrize("name,B", [("c4_qcqp_small", 37), ("c2_eigen_qcqp_small", 64), ("c5_microbench_small", 5),
+                                    ("hs071", 33), ("rel_entr_vector", 8), ("matmul_var_var", 3),
+                                    ("quad_over_lin_var_denominator", 40)])
+def test_gpu_batched_multistart_matches_per_start_oracle(name, B):
+    """BatchedOracles (B starts in lock step, DMMA GEMM for dense quad_form) vs the CPU oracle run
+    start by start."""
+    from dnlp_b200.multistart import BatchedOracles
+    g = Golden(name)
+    ref = RefOracles(g.problem)
+    ref.jacobianstructure(), ref.hessianstructure()
+    rng = np.random.default_rng(99)
+    x0 = g.points[0]["x"]
+    X = x0[None, :] * (1 + 0.05 * rng.standard_normal((B, x0.size)))
+    LAM = rng.standard_normal((B, g.problem.m))
+    SIG = rng.uniform(0.5, 1.5, B)
+    o = BatchedOracles(g.problem, B)
+    try:
+        res = o.eval(X, LAM, SIG)
+        with np.errstate(all="ignore"):
+            for b in range(B):
+                assert_close(res["f"][b], ref.objective(X[b]), "f[%d]" % b)
+                assert_close(res["grad"][b], ref.gradient(X[b]), "grad[%d]" % b)
+                assert_close(res["g"][b], ref.constraints(X[b]), "g[%d]" % b)
+                assert_close(res["jac"][b], ref.jacobian(X[b]), "jac[%d]" % b)
+                assert_close(res["hess"][b], ref.hessian(X[b], LAM[b], float(SIG[b])), "hess[%d]" % b)
+        only = o.eval(X, want=("f", "g"))
+        assert_close(only["f"], res["f"], "f only")
+    finally:
+        o.close()
+
+
+def test_gpu_batched_medium_qcqp_dmma():
+    """n = 200 (not a multiple of the 64 x 64 GEMM tile), k = 3, B = 100: exercises tile edges."""
+    from dnlp_b200 import workloads as W
+    from dnlp_b200.multistart import BatchedOracles
+    P, q, rng = W.qcqp_data(200, 3)
+    prob = W.qcqp(P, q)
+    ref = RefOracles(prob)
+    ref.jacobianstructure(), ref.hessianstructure()
+    B = 100
+    X = rng.uniform(-1, 1, (B, 200))
+    LAM = rng.standard_normal((B, 3))
+    SIG = np.ones(B)
+    o = BatchedOracles(prob, B)
+    try:
+        res = o.eval(X, LAM, SIG)
+        for b in (0, 1, 50, 99):
+            assert_close(res["f"][b], ref.objective(X[b]), "f")
+            assert_close(res["grad"][b], ref.gradient(X[b]), "grad")
+            assert_close(res["g"][b], ref.constraints(X[b]), "g")
+            assert_close(res["jac"][b], ref.jacobian(X[b]), "jac")
+            assert_close(res["hess"][b], ref.hessian(X[b], LAM[b], 1.0), "hess")
+    finally:
+        o.close()
