@@ -252,6 +252,11 @@ def bench_multistart(args, rank, local_rank, world, dist, metric, hbm_peak, peak
         ms, e2e_ms = [float(v) for v in t.tolist()]
     if rank == 0:
         per = o.profile_instrs("all", iters=2)
+        if os.environ.get("DNLP_BENCH_PROFILE"):
+            for i in o.tape.programs["all"]:
+                ii = o.tape.instrs[i]
+                sys.stderr.write("[binstr %3d] kind=%d dst=%d rows=%-8d terms=%-9d %8.4f ms\n" % (
+                    i, ii.kind, ii.dst_space, ii.count, 0 if ii.coef is None else ii.coef.size, per[i]))
         top = int(np.argmax(per))
         ins = o.tape.instrs[top]
         if ins.kind == 3:      # GEMM on the FP64 tensor cores

@@ -25,6 +25,7 @@ thread_local std::string g_batch_create_error;
 struct BInstr {
   dnlp_instr_desc d;
   bool has_f2 = false;
+  int32_t *smallk_slots = nullptr;   // device: the K slots every row combines (tall-skinny GEMM path)
 };
 }  // namespace
 
@@ -62,6 +63,7 @@ struct dnlp_batch {
   }
   int launch(const BInstr &I);
   int run_program(int p);
+  int run_union(int32_t prog_mask);
   int reset_outputs();
   int put(const double *host, double *dev_batch_major, int64_t len);
   int get(int space, double *host);
@@ -102,6 +104,32 @@ int dnlp_batch::launch(const BInstr &I) {
       if (!launch_belem(this, d, grid_for(d.count * B))) { err = "unknown elementwise function code"; return 1; }
       break;
     case DNLP_POLY: {
+      if (I.smallk_slots) {
+        const int threads = B >= 256 ? 256 : ((B + 31) / 32) * 32;
+        const int bchunks = (B + threads * 4 - 1) / (threads * 4);
+        int64_t want_blocks = (int64_t)sm_count * 8;
+        int64_t rblocks = want_blocks / bchunks > 0 ? want_blocks / bchunks : 1;
+        int rows_per_block = (int)((d.count + rblocks - 1) / rblocks);
+        if (rows_per_block < 1) rows_per_block = 1;
+        const int64_t blocks = ((d.count + rows_per_block - 1) / rows_per_block) * bchunks;
+#define SK(Lc) case Lc: bsmallk_kernel<Lc, 4><<<(int)blocks, threads, 0, stream>>>(                    \
+            V, dst, d.coef, I.smallk_slots, d.pos, d.count, d.accumulate, B, rows_per_block); break;
+        switch (d.row_len) {
+          SK(2) SK(3) SK(4) SK(5) SK(6) SK(7) SK(8) SK(9) SK(10) SK(11) SK(12) SK(13) SK(14) SK(15) SK(16)
+          default: err = "small-K kernel: unsupported row length"; return 1;
+        }
+#undef SK
+        break;
+      }
+      if (d.count > 0 && d.nterms / d.count >= 128) {
+        int64_t blocks = d.count * ((B + 31) / 32), cap = (int64_t)sm_count * 8;
+        int grid = (int)(blocks < cap ? blocks : cap);
+        if (I.has_f2)
+          bpoly_long_kernel<true><<<grid, 256, 0, stream>>>(V, dst, d.ptr, d.row_len, d.coef, d.f1, d.f2, d.pos, d.count, d.accumulate, B);
+        else
+          bpoly_long_kernel<false><<<grid, 256, 0, stream>>>(V, dst, d.ptr, d.row_len, d.coef, d.f1, d.f2, d.pos, d.count, d.accumulate, B);
+        break;
+      }
       const int threads = B >= 256 ? 256 : ((B + 31) / 32) * 32;
       const int bchunks = (B + threads - 1) / threads;
       int64_t blocks = d.count * bchunks, cap = (int64_t)sm_count * 16;
@@ -134,6 +162,17 @@ int dnlp_batch::launch(const BInstr &I) {
 
 int dnlp_batch::run_program(int p) {
   for (int32_t id : prog[p]) if (launch(instrs[id])) return 1;
+  return 0;
+}
+
+int dnlp_batch::run_union(int32_t prog_mask) {
+  // there is no per-x cache in batch mode: run every needed instruction exactly once
+  std::vector<uint8_t> need(instrs.size(), 0);
+  for (int p = 0; p < DNLP_NPROG; ++p)
+    if (prog_mask & (1 << p))
+      for (int32_t id : prog[p]) need[id] = 1;
+  for (size_t id = 0; id < instrs.size(); ++id)       // ids are in topological order
+    if (need[id] && launch(instrs[id])) return 1;
   return 0;
 }
 
@@ -213,6 +252,14 @@ static int batch_create_impl(dnlp_batch *o, const dnlp_tape_desc *t) {
       if (o->upload(h.f1, h.nterms, const_cast<int32_t **>(&D.d.f1))) return 1;
       if (h.f2) { if (o->upload(h.f2, h.nterms, const_cast<int32_t **>(&D.d.f2))) return 1; }
       D.has_f2 = h.f2 != nullptr;
+      // every row combines the same <= 16 slots?  (uniform rows, single factor)
+      if (!h.ptr && !h.f2 && h.row_len >= 2 && h.row_len <= 16 && h.count >= 1024) {
+        bool same = true;
+        for (int64_t r = 1; r < h.count && same; ++r)
+          for (int j = 0; j < h.row_len; ++j)
+            if (h.f1[r * h.row_len + j] != h.f1[j]) { same = false; break; }
+        if (same) { if (o->upload(h.f1, (int64_t)h.row_len, &D.smallk_slots)) return 1; }
+      }
     } else if (h.kind == DNLP_GEMV) {
       if (o->upload(h.Q, h.count * h.ncols, const_cast<double **>(&D.d.Q))) return 1;
     } else if (h.kind == DNLP_SCALE) {
@@ -284,8 +331,10 @@ int dnlp_batch_eval(dnlp_batch *o, const double *X, const double *LAM, const dou
     if (o->m > 0) { if (o->put(LAM, o->V + (o->n + 1) * o->B, o->m)) return 1; }
   }
   double *outs[6] = {nullptr, F, GRAD, G, JAC, HESS};
+  int32_t mask = 0;
   for (int p = 0; p < 5; ++p)
-    if (outs[p + 1] && o->run_program(p)) return 1;
+    if (outs[p + 1]) mask |= 1 << p;
+  if (o->run_union(mask)) return 1;
   for (int s = 1; s < 6; ++s)
     if (outs[s]) {
       if (o->get(s, outs[s])) return 1;
@@ -300,9 +349,7 @@ int dnlp_batch_run_device(dnlp_batch *o, int32_t prog_mask, int32_t iters, float
   CKB(cudaSetDevice(o->device));
   CKB(cudaEventRecord(o->ev0, o->stream));
   for (int it = 0; it < iters; ++it)
-    for (int p = 0; p < DNLP_NPROG; ++p)
-      if (prog_mask & (1 << p))
-        if (o->run_program(p)) return 1;
+    if (o->run_union(prog_mask)) return 1;
   CKB(cudaEventRecord(o->ev1, o->stream));
   CKB(cudaEventSynchronize(o->ev1));
   float ms = 0.f;

@@ -53,6 +53,111 @@ bpoly_kernel(const double *__restrict__ V, double *__restrict__ dst, const int64
   }
 }
 
+// Rows that all combine the SAME few slots (Hessian of a QCQP: out[row] = sum_i C[row, i] * lambda_i):
+// a tall-skinny GEMM with K <= 16.  Each thread owns NB starts, keeps their K slot values in
+// registers and streams the coefficient rows with warp-uniform loads, so the kernel is bound by
+// the output write instead of by load-instruction issue (27 loads per output in bpoly_kernel).
+template <int L, int NB>
+__global__ void __launch_bounds__(256, 2)
+bsmallk_kernel(const double *__restrict__ V, double *__restrict__ dst, const double *__restrict__ coef,
+               const int32_t *__restrict__ slots, const int32_t *__restrict__ pos, int64_t count,
+               int accumulate, int B, int rows_per_block) {
+  constexpr int TR = 64;                       // coefficient rows staged per shared-memory tile
+  __shared__ double ctile[2][TR * L];
+  const int bchunks = (B + blockDim.x * NB - 1) / (blockDim.x * NB);
+  const int64_t rblocks = (count + rows_per_block - 1) / rows_per_block;
+  for (int64_t blk = blockIdx.x; blk < rblocks * bchunks; blk += gridDim.x) {
+    const int bc = (int)(blk % bchunks);
+    const int64_t r0 = (blk / bchunks) * rows_per_block;
+    const int64_t r1 = r0 + rows_per_block < count ? r0 + rows_per_block : count;
+    const int b0 = bc * NB * blockDim.x + threadIdx.x;      // this thread's starts: b0 + u * blockDim.x
+    double lam[L][NB];
+#pragma unroll
+    for (int j = 0; j < L; ++j) {
+      const int s = __ldg(slots + j);
+#pragma unroll
+      for (int u = 0; u < NB; ++u) {
+        const int b = b0 + u * blockDim.x;
+        lam[j][u] = b < B ? (s >= 0 ? V[(int64_t)s * B + b] : 1.0) : 0.0;
+      }
+    }
+    // double-buffered tiles of coefficient rows: coalesced global reads, broadcast LDS in the loop
+    auto stage = [&](int buf, int64_t rs) {
+      const int n = (int)((r1 - rs < TR ? r1 - rs : TR) * L);
+      const double *__restrict__ src = coef + rs * L;
+      for (int e = threadIdx.x; e < n; e += blockDim.x) ctile[buf][e] = __ldg(src + e);
+    };
+    __syncthreads();
+    stage(0, r0);
+    __syncthreads();
+    int buf = 0;
+    for (int64_t rs = r0; rs < r1; rs += TR, buf ^= 1) {
+      if (rs + TR < r1) stage(buf ^ 1, rs + TR);
+      const int nr = (int)(r1 - rs < TR ? r1 - rs : TR);
+      const double *c = ctile[buf];
+      double *__restrict__ out = dst + (pos ? 0 : rs * (int64_t)B) + b0;
+      for (int rr = 0; rr < nr; ++rr, c += L) {
+        double acc[NB];
+#pragma unroll
+        for (int u = 0; u < NB; ++u) acc[u] = 0.0;
+#pragma unroll
+        for (int j = 0; j < L; ++j) {
+          const double cj = c[j];
+#pragma unroll
+          for (int u = 0; u < NB; ++u) acc[u] = fma(cj, lam[j][u], acc[u]);
+        }
+        double *__restrict__ o = pos ? dst + (int64_t)__ldg(pos + rs + rr) * B + b0 : out + (int64_t)rr * B;
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+          if (b0 + u * (int)blockDim.x < B) {
+            if (accumulate) o[u * blockDim.x] += acc[u]; else __stcs(o + u * blockDim.x, acc[u]);
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// Rows with hundreds of terms but few (row, start) pairs (f = x'P0x + q'x of every start): the 8
+// warps of a CTA split the terms of one row for 32 consecutive starts, then reduce in shared memory.
+template <bool HAS_F2>
+__global__ void __launch_bounds__(256)
+bpoly_long_kernel(const double *__restrict__ V, double *__restrict__ dst, const int64_t *__restrict__ ptr,
+                  int row_len, const double *__restrict__ coef, const int32_t *__restrict__ f1,
+                  const int32_t *__restrict__ f2, const int32_t *__restrict__ pos, int64_t count,
+                  int accumulate, int B) {
+  __shared__ double part[8][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int bchunks = (B + 31) / 32;
+  for (int64_t blk = blockIdx.x; blk < count * bchunks; blk += gridDim.x) {
+    const int64_t row = blk / bchunks;
+    const int b = (int)(blk - row * bchunks) * 32 + lane;
+    int64_t t0, t1;
+    if (ptr) { t0 = __ldg(ptr + row); t1 = __ldg(ptr + row + 1); }
+    else { t0 = row * (int64_t)row_len; t1 = t0 + row_len; }
+    double acc = 0.0;
+    if (b < B)
+      for (int64_t t = t0 + warp; t < t1; t += 8) {
+        const int i1 = __ldg(f1 + t);
+        double v = __ldg(coef + t);
+        if (i1 >= 0) v *= V[(int64_t)i1 * B + b];
+        if (HAS_F2) { const int i2 = __ldg(f2 + t); if (i2 >= 0) v *= V[(int64_t)i2 * B + b]; }
+        acc += v;
+      }
+    part[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0 && b < B) {
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += part[w][lane];
+      const int64_t d = (pos ? (int64_t)__ldg(pos + row) : row) * B + b;
+      dst[d] = accumulate ? dst[d] + t : t;
+    }
+    __syncthreads();
+  }
+}
+
 static __global__ void __launch_bounds__(256)
 bscale_kernel(const double *__restrict__ V, int64_t s_slot, const double *__restrict__ coef,
               double *__restrict__ dst, const int32_t *__restrict__ pos, int64_t count, int accumulate, int B) {
