@@ -57,8 +57,12 @@ def _emit_output(b, sv, space):
     return const, b.emit_output(sv.gather(dyn), space, pos=dyn.astype(np.int64))
 
 
-def compile_problem(prob):
-    """ProblemIR -> Tape (host arrays only; ``GpuOracles`` uploads it through the C-ABI)."""
+def compile_problem(prob, with_hessian=True):
+    """ProblemIR -> Tape (host arrays only; ``GpuOracles`` uploads it through the C-ABI).
+
+    ``with_hessian=False`` skips the Hessian program (the reference can serve first-order
+    callbacks for expressions whose ``hess_vec`` rule rejects them; cyipopt then falls back to
+    L-BFGS when the object has no usable ``hessian``)."""
     b = Builder(prob)
     tape = b.tape
     n, m = prob.n, prob.m
@@ -103,6 +107,8 @@ def compile_problem(prob):
         for vid in var_ids:
             if vid in jd:
                 r, c, v = jd[vid]
+                if not (np.size(r) == np.size(c) == v.K):
+                    raise ValueError("row, column, and data array must all be the same length")
                 R.append(r + coff)
                 C.append(c + off[vid])
                 V.append(v)
@@ -128,15 +134,20 @@ def compile_problem(prob):
             for v2 in var_ids:
                 if (v1, v2) in hd:
                     r, c, v = hd[(v1, v2)]
+                    if not (np.size(r) == np.size(c) == v.K):
+                        # what scipy's coo_matrix raises inside sum_coo (nlp_solver.py:359-364) when a
+                        # rule emits ragged triplets, e.g. multiply(promote(s), x) (binary_operators.py:529-535)
+                        raise ValueError("row, column, and data array must all be the same length")
                     HR.append(np.asarray(r, np.int64) + off[v1])
                     HC.append(np.asarray(c, np.int64) + off[v2])
                     HV.append(v)
 
-    parse(b.hv(prob.objective, SymVec.slots([tape.sigma_slot])))
-    coff = 0
-    for con in prob.constraints:
-        parse(b.hv(con, SymVec.slot_range(tape.lam_slot + coff, con.size)))
-        coff += con.size
+    if with_hessian:
+        parse(b.hv(prob.objective, SymVec.slots([tape.sigma_slot])))
+        coff = 0
+        for con in prob.constraints:
+            parse(b.hv(con, SymVec.slot_range(tape.lam_slot + coff, con.size)))
+            coff += con.size
     if HR:
         hr, hc, hv = Builder._coo_sum_duplicates(np.concatenate(HR), np.concatenate(HC), SymVec.concat(HV))
         low = np.where(hr >= hc)[0]

@@ -231,6 +231,14 @@ __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, do
 
 constexpr int GM = 64, GN = 64, GK = 16;
 
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
 static __global__ void __launch_bounds__(128)
 bgemm_dmma_kernel(const double *__restrict__ Q, const double *__restrict__ X, double *__restrict__ Y,
                   int M, int N, int K, double alpha) {
@@ -240,6 +248,9 @@ bgemm_dmma_kernel(const double *__restrict__ Q, const double *__restrict__ X, do
   const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
   const int g = lane >> 2, tg = lane & 3;
   const int tiles_n = (N + GN - 1) / GN, tiles_m = (M + GM - 1) / GM;
+  // 16-byte asynchronous copies need even leading dimensions and 16-byte aligned bases
+  const bool aligned = (K & 1) == 0 && (N & 1) == 0 &&
+                       ((reinterpret_cast<uintptr_t>(Q) | reinterpret_cast<uintptr_t>(X)) & 15) == 0;
   for (int tile = blockIdx.x; tile < tiles_m * tiles_n; tile += gridDim.x) {
     const int m0 = (tile / tiles_n) * GM, n0 = (tile % tiles_n) * GN;
     double acc[4][4][2];
@@ -249,25 +260,34 @@ bgemm_dmma_kernel(const double *__restrict__ Q, const double *__restrict__ X, do
       for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     auto load_tiles = [&](int buf, int k0) {
-      // A tile: 64 x 16 doubles = 1024 elements, 8 per thread
-      for (int e = tid; e < GM * GK; e += 128) {
-        const int r = e / GK, c = e % GK;
+      // A tile 64 x 16: 8 chunks of 2 doubles per row; B tile 16 x 64: 32 chunks per row
+      for (int e = tid; e < GM * (GK / 2); e += 128) {
+        const int r = e >> 3, c = (e & 7) * 2;
         const int gm = m0 + r, gk = k0 + c;
-        As[buf][r][c] = (gm < M && gk < K) ? __ldg(Q + (int64_t)gm * K + gk) : 0.0;
+        if (aligned && gm < M && gk + 1 < K) cp_async16(&As[buf][r][c], Q + (int64_t)gm * K + gk);
+        else {
+          As[buf][r][c] = (gm < M && gk < K) ? __ldg(Q + (int64_t)gm * K + gk) : 0.0;
+          As[buf][r][c + 1] = (gm < M && gk + 1 < K) ? __ldg(Q + (int64_t)gm * K + gk + 1) : 0.0;
+        }
       }
-      // B tile: 16 x 64
-      for (int e = tid; e < GK * GN; e += 128) {
-        const int r = e / GN, c = e % GN;
+      for (int e = tid; e < GK * (GN / 2); e += 128) {
+        const int r = e >> 5, c = (e & 31) * 2;
         const int gk = k0 + r, gn = n0 + c;
-        Bs[buf][r][c] = (gk < K && gn < N) ? X[(int64_t)gk * N + gn] : 0.0;
+        if (aligned && gk < K && gn + 1 < N) cp_async16(&Bs[buf][r][c], X + (int64_t)gk * N + gn);
+        else {
+          Bs[buf][r][c] = (gk < K && gn < N) ? X[(int64_t)gk * N + gn] : 0.0;
+          Bs[buf][r][c + 1] = (gk < K && gn + 1 < N) ? X[(int64_t)gk * N + gn + 1] : 0.0;
+        }
       }
+      cp_async_commit();
     };
     const int ksteps = (K + GK - 1) / GK;
     load_tiles(0, 0);
-    __syncthreads();
     for (int ks = 0; ks < ksteps; ++ks) {
       const int buf = ks & 1;
-      if (ks + 1 < ksteps) load_tiles(buf ^ 1, (ks + 1) * GK);
+      if (ks + 1 < ksteps) { load_tiles(buf ^ 1, (ks + 1) * GK); cp_async_wait<1>(); }
+      else cp_async_wait<0>();
+      __syncthreads();
 #pragma unroll
       for (int kk = 0; kk < GK; kk += 4) {
         double a[4], b[4];

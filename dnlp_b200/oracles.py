@@ -23,10 +23,11 @@ class GpuOracles:
     ELIDE_MIN = 4096               # outputs shorter than this are always copied whole
     ELIDE_MAX_FRACTION = 0.5       # elide constants when at most this share of entries is dynamic
 
-    def __init__(self, problem_ir, device=0, pinned_outputs=True):
+    def __init__(self, problem_ir, device=0, pinned_outputs=True, with_hessian=True):
         """``problem_ir``: a ``dnlp_b200.ir.ProblemIR`` (see frontend_cvxpy.data_to_ir)."""
         self.problem = problem_ir
-        self.tape = compile_problem(problem_ir)
+        self.with_hessian = with_hessian
+        self.tape = compile_problem(problem_ir, with_hessian=with_hessian)
         self.dev = _cabi.DeviceTape(self.tape, device)
         self.n, self.m = self.tape.n, self.tape.m
         self.num_constraints = self.m
@@ -117,6 +118,8 @@ class GpuOracles:
         return self.tape.jac_rows, self.tape.jac_cols
 
     def hessian(self, x, duals, obj_factor):
+        if not self.with_hessian:
+            raise RuntimeError("this oracle was compiled without the Hessian program")
         lam = np.asarray(duals, dtype=np.float64).reshape(-1)
         if lam.size != self.m:
             raise ValueError("duals has %d entries, expected %d" % (lam.size, self.m))

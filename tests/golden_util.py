@@ -37,3 +37,29 @@ def assert_close(got, want, what, rtol=1e-10, atol=1e-12):
     if not ok.all():
         bad = np.where(~ok)[0][:5]
         raise AssertionError("%s mismatch at %s: got %s want %s" % (what, bad, got[bad], want[bad]))
+
+
+ATOMS_DIR = os.path.join(GOLDEN_DIR, "atoms")
+
+
+def atom_golden_names():
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(ATOMS_DIR, "*.npz")))
+
+
+class AtomGolden:
+    """Fixtures written by tests/golden/make_golden_atoms.py (raw rules, no Dnlp2Smooth)."""
+
+    def __init__(self, name):
+        z = np.load(os.path.join(ATOMS_DIR, name + ".npz"), allow_pickle=False)
+        self.name = name
+        self.jac_error, self.hess_error = str(z["jac_error"]), str(z["hess_error"])
+        arrays = {k[3:]: z[k] for k in z.files if k.startswith("ir_a")}
+        self.problem = ir.load_problem(str(z["ir_json"]), arrays)
+        if not self.jac_error:
+            self.jac_rows, self.jac_cols = z["jac_rows"], z["jac_cols"]
+        if not self.hess_error:
+            self.hess_rows, self.hess_cols = z["hess_rows"], z["hess_cols"]
+        self.points = []
+        for i in range(int(z["npoints"])):
+            self.points.append({k: z["%s_%d" % (k, i)] for k in ("x", "lam", "sigma", "f", "grad", "g", "jac", "hess")
+                                if "%s_%d" % (k, i) in z.files})
