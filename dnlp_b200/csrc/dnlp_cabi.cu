@@ -177,10 +177,11 @@ int dnlp_oracle::launch(const DevInstr &I) {
           poly1_stream_kernel<4, false><<<grid, 256, 0, stream>>>(V, dst, d.coef, d.f1, d.f2, d.pos, d.count, d.accumulate);
         break;
       }
-      // lanes per row: smallest power of two >= half the mean row length (measured on B200:
-      // L=5 -> 4, L=10 -> 8, L=16 -> 8; profiles/r01_kbench.txt), two rows in flight per group
+      // lanes per row: largest power of two <= 0.8 * mean row length (measured on B200 with
+      // tools/kbench: L=5 -> 4, L=10 -> 8, L=16/17 -> 8; 16 lanes on 16-term rows lose 2x),
+      // two rows in flight per lane group
       int G = 1;
-      while (G < 32 && (double)G * 2.0 < I.mean_len) G <<= 1;
+      while (G < 32 && (double)(2 * G) <= 0.8 * I.mean_len) G <<= 1;
       int grid = grid_for((d.count + 1) / 2, G);
       switch (G) {
         case 1: launch_poly_g<1>(this, I, dst, grid); break;
