@@ -444,8 +444,14 @@ def main():
         alg_bytes = ins.nbytes_algorithmic()
         achieved = alg_bytes / (per[top] * 1e-3) / 1e9 if per[top] > 0 else 0.0
         total_alg = sum(o.tape.instrs[i].nbytes_algorithmic() for i in o.tape.programs["all"])
-        small_n = prob.n <= (1 << 18)
-        h2d = (prob.n * 8 if small_n else 5 * prob.n * 8) + (prob.m + 1) * 8
+        h2d = prob.n * 8 + (prob.m + 1) * 8        # x once per step (unchanged-point detection), lambda + sigma
+        kname = o.instr_kernel(top)
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
+            traffic = tj.get(args.workload, {}).get(kname, {}).get("dram_bytes_per_launch_max")
+        except Exception:
+            pass
         full = {"grad": prob.n, "g": prob.m, "jac": o.nnz_jac, "hess": o.nnz_hess}
         d2h = 8 * (1 + sum(o._dyn[k][0].size if k in o._dyn else v for k, v in full.items()))
         line = {
@@ -464,9 +470,11 @@ def main():
                     "api": "GpuOracles.objective/gradient/constraints/jacobian/hessian (5 callbacks)",
                     "fused_eval_all_value": world * e2e_steps / (fused_ms * 1e-3)},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "%s_kernel (instr %d, %d rows)" % (kind, top, ins.count),
+            "roofline": {"bound": "hbm", "kernel": "%s (instr %d, %d rows)" % (kname or kind, top, ins.count),
                          "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": None, "algorithmic_bytes": int(alg_bytes), "ms": float(per[top]),
+                         "traffic": traffic, "traffic_source": "profiles/r01_ncu_traffic.json (ncu --set full, dram read+write)"
+                         if traffic else None,
+                         "algorithmic_bytes": int(alg_bytes), "ms": float(per[top]),
                          "peak_source": peak_src,
                          "share_of_step": float(per[top] / max(per.sum(), 1e-12))},
         }

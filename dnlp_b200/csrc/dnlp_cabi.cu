@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -33,6 +34,7 @@ struct DevInstr {
   dnlp_instr_desc d;       // pointers rewritten to device memory
   double mean_len = 1.0;
   bool has_f2 = false;
+  std::string kname;       // kernel that executes this instruction (as ncu prints it)
 };
 
 // All x-only elementwise instructions of one program, fused into a single launch.
@@ -58,7 +60,7 @@ struct dnlp_oracle {
   ElemBatch batch[DNLP_NPROG];
   std::vector<void *> owned;           // device allocations to free
   std::vector<uint8_t> valid;          // per instruction: result valid for the current x
-  std::vector<double> last_x;          // host copy of the last uploaded point (small n only)
+  double *hx = nullptr;                // pinned host copy of the last uploaded point
   bool have_last_x = false;
   bool cache_enabled = true;
   int64_t launches = 0;
@@ -93,7 +95,7 @@ struct dnlp_oracle {
     return (int)need;
   }
 
-  int launch(const DevInstr &I);
+  int launch(DevInstr &I);
   int build_batches();
   int run_program(int p, bool force);
   int put_x(const double *x);
@@ -145,7 +147,7 @@ void launch_poly_g(const dnlp_oracle *o, const DevInstr &I, double *dst, int gri
 
 }  // namespace
 
-int dnlp_oracle::launch(const DevInstr &I) {
+int dnlp_oracle::launch(DevInstr &I) {
   const dnlp_instr_desc &d = I.d;
   if (d.count <= 0) return 0;
   double *dst = (d.dst_space == DNLP_DST_V) ? V + d.dst_off : out[d.dst_space] + d.dst_off;
@@ -153,6 +155,7 @@ int dnlp_oracle::launch(const DevInstr &I) {
     case DNLP_ELEM: {
       int grid = grid_for((d.count + 1) / 2, 1);
       if (!launch_elem(this, d, grid)) { err = "unknown elementwise function code"; return 1; }
+      if (I.kname.empty()) I.kname = "elem_kernel<" + std::to_string(d.fcode) + ", " + (d.fcode >= 40 ? "1" : "0") + ">";
       break;
     }
     case DNLP_POLY: {
@@ -165,6 +168,7 @@ int dnlp_oracle::launch(const DevInstr &I) {
           poly_reduce_kernel<true><<<grid, 256, 0, stream>>>(V, dst, d.coef, d.f1, d.f2, d.nterms, d.accumulate, scratch, ticket);
         else
           poly_reduce_kernel<false><<<grid, 256, 0, stream>>>(V, dst, d.coef, d.f1, d.f2, d.nterms, d.accumulate, scratch, ticket);
+        if (I.kname.empty()) I.kname = std::string("poly_reduce_kernel<") + (I.has_f2 ? "1" : "0") + ">";
         break;
       }
       if (d.ptr == nullptr && d.row_len == 1) {
@@ -175,6 +179,7 @@ int dnlp_oracle::launch(const DevInstr &I) {
           poly1_stream_kernel<4, true><<<grid, 256, 0, stream>>>(V, dst, d.coef, d.f1, d.f2, d.pos, d.count, d.accumulate);
         else
           poly1_stream_kernel<4, false><<<grid, 256, 0, stream>>>(V, dst, d.coef, d.f1, d.f2, d.pos, d.count, d.accumulate);
+        if (I.kname.empty()) I.kname = std::string("poly1_stream_kernel<4, ") + (I.has_f2 ? "1" : "0") + ">";
         break;
       }
       // lanes per row: largest power of two <= 0.8 * mean row length (measured on B200 with
@@ -191,6 +196,9 @@ int dnlp_oracle::launch(const DevInstr &I) {
         case 16: launch_poly_g<16>(this, I, dst, grid); break;
         default: launch_poly_g<32>(this, I, dst, grid); break;
       }
+      if (I.kname.empty())
+        I.kname = "poly_rows_kernel<" + std::to_string(G) + ", 2, " + (I.has_f2 ? "1" : "0") + ", " +
+                  (d.ptr == nullptr ? "1" : "0") + ">";
       break;
     }
     case DNLP_GEMV: {
@@ -200,6 +208,7 @@ int dnlp_oracle::launch(const DevInstr &I) {
         int64_t cap = (int64_t)sm_count * 2;
         int grid = (int)(d.count < cap ? d.count : cap);
         gemv_cta_kernel<4, 16><<<grid, 512, smem, stream>>>(d.Q, V, d.x_off, dst, d.count, d.ncols, d.alpha);
+        if (I.kname.empty()) I.kname = "gemv_cta_kernel<4, 16>";
       } else {
         int in_smem = smem <= 96 * 1024 ? 1 : 0;
         if (!in_smem) smem = 0;
@@ -207,13 +216,15 @@ int dnlp_oracle::launch(const DevInstr &I) {
         int64_t cap = (int64_t)sm_count * (in_smem && smem > 48 * 1024 ? 2 : 4);
         int grid = (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
         gemv_kernel<8><<<grid, 256, smem, stream>>>(d.Q, V, d.x_off, dst, d.count, d.ncols, d.alpha, in_smem);
+        if (I.kname.empty()) I.kname = "gemv_kernel<8>";
       }
       break;
     }
     case DNLP_SCALE: {
       int grid = grid_for((d.count + 1) / 2, 1);
       if (!d.pos && !d.accumulate && ((reinterpret_cast<uintptr_t>(d.coef) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0)
-        scale_stream_kernel<4><<<sm_count * 16, 256, 0, stream>>>(V, d.s_slot, d.coef, dst, d.count);
+        { scale_stream_kernel<4><<<sm_count * 16, 256, 0, stream>>>(V, d.s_slot, d.coef, dst, d.count);
+          if (I.kname.empty()) I.kname = "scale_stream_kernel<4>"; }
       else
         scale_kernel<<<grid, 256, 0, stream>>>(V, d.s_slot, d.coef, dst, d.pos, d.count, d.accumulate);
       break;
@@ -291,18 +302,46 @@ int dnlp_oracle::run_program(int p, bool force) {
   return 0;
 }
 
+// Copy x into the pinned staging buffer and report whether it differs from the point already on
+// the device.  IPOPT issues its five callbacks at the same iterate with fresh copies of x, so an
+// unchanged point keeps every x-only instruction valid (no upload, no recomputation).  Large
+// points are handled by a few host threads: a single core copies ~10 GB/s, which would otherwise
+// dominate the callback for n in the millions.
+static bool stage_point(double *dst, const double *src, int64_t n, bool have_old) {
+  const size_t bytes = (size_t)n * sizeof(double);
+  auto work = [&](int64_t lo, int64_t hi, bool *changed) {
+    const size_t b = (size_t)(hi - lo) * sizeof(double);
+    if (have_old && memcmp(dst + lo, src + lo, b) == 0) { *changed = false; return; }
+    memcpy(dst + lo, src + lo, b);
+    *changed = true;
+  };
+  if (bytes < (4u << 20)) {
+    bool ch = true;
+    work(0, n, &ch);
+    return ch;
+  }
+  unsigned hw = std::thread::hardware_concurrency();
+  int T = (int)(hw >= 16 ? 8 : (hw >= 4 ? hw / 2 : 1));
+  std::vector<std::thread> th;
+  std::vector<char> flags(T, 0);
+  const int64_t chunk = (n + T - 1) / T;
+  for (int t = 0; t < T; ++t) {
+    const int64_t lo = t * chunk, hi = lo + chunk < n ? lo + chunk : n;
+    if (lo >= hi) break;
+    th.emplace_back([&, lo, hi, t] { bool ch = true; work(lo, hi, &ch); flags[t] = ch ? 1 : 0; });
+  }
+  for (auto &t : th) t.join();
+  for (char f : flags) if (f) return true;
+  return false;
+}
+
 int dnlp_oracle::put_x(const double *x) {
   const size_t bytes = (size_t)n * sizeof(double);
-  const bool small = n <= (1 << 18);
-  if (cache_enabled && small && have_last_x && memcmp(last_x.data(), x, bytes) == 0) return 0;
-  if (n > 0) CK(cudaMemcpyAsync(V, x, bytes, cudaMemcpyHostToDevice, stream));
+  const bool changed = stage_point(hx, x, n, have_last_x && cache_enabled);
+  if (!changed && have_last_x && cache_enabled) return 0;
+  if (n > 0) CK(cudaMemcpyAsync(V, hx, bytes, cudaMemcpyHostToDevice, stream));
   std::fill(valid.begin(), valid.end(), 0);
-  if (small) {
-    last_x.assign(x, x + n);
-    have_last_x = true;
-  } else {
-    have_last_x = false;
-  }
+  have_last_x = true;
   return 0;
 }
 
@@ -339,6 +378,7 @@ void dnlp_destroy(dnlp_oracle *o) {
   cudaSetDevice(o->device);
   if (o->stream) cudaStreamSynchronize(o->stream);
   for (void *p : o->owned) cudaFree(p);
+  if (o->hx) cudaFreeHost(o->hx);
   if (o->ev0) cudaEventDestroy(o->ev0);
   if (o->ev1) cudaEventDestroy(o->ev1);
   if (o->stream) cudaStreamDestroy(o->stream);
@@ -362,6 +402,8 @@ static int create_impl(dnlp_oracle *o, const dnlp_tape_desc *t) {
   o->V = static_cast<double *>(p);
   CK(cudaMemset(o->V, 0, (size_t)(t->nslots + 2) * sizeof(double)));
 
+  CK(cudaMallocHost(&p, (size_t)(t->n + 2) * sizeof(double)));
+  o->hx = static_cast<double *>(p);
   CK(cudaMalloc(&p, 4096 * sizeof(double)));
   o->owned.push_back(p);
   o->scratch = static_cast<double *>(p);
@@ -582,6 +624,11 @@ int dnlp_read_output(dnlp_oracle *o, int32_t space, double *out) {
 }
 
 int64_t dnlp_kernel_launches(dnlp_oracle *o) { return o->launches; }
+
+const char *dnlp_instr_kernel(dnlp_oracle *o, int32_t instr) {
+  if (instr < 0 || (size_t)instr >= o->instrs.size()) return "";
+  return o->instrs[instr].kname.c_str();
+}
 
 int dnlp_set_cache(dnlp_oracle *o, int32_t enabled) {
   o->cache_enabled = enabled != 0;

@@ -43,7 +43,7 @@ class GpuOracles:
         self._g = alloc(self.m)
         self._jac = alloc(self.nnz_jac)
         self._hess = alloc(self.nnz_hess)
-        self._x = alloc(self.n)
+        self._x_ref = None
         self._lam = alloc(max(self.m, 1))
         # Constant-entry elision: when only a small part of an output depends on x / lambda
         # (affine Jacobian rows, reference quirk Q5), only that part crosses PCIe per call; the
@@ -79,11 +79,13 @@ class GpuOracles:
         return pos, compact
 
     def _stage_x(self, x):
-        x = np.asarray(x, dtype=np.float64).reshape(-1)
+        # the library stages x into its own pinned buffer (multi-threaded for large n) and detects an
+        # unchanged point, so no copy is made here
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
         if x.size != self.n:
             raise ValueError("x has %d entries, expected %d" % (x.size, self.n))
-        np.copyto(self._x, x)
-        return _ptr(self._x)
+        self._x_ref = x
+        return _ptr(x)
 
     # ---- the seven callbacks --------------------------------------------------
     def objective(self, x):
@@ -176,6 +178,9 @@ class GpuOracles:
         out = np.empty(n)
         self.dev.check(self.dev._L.dnlp_read_output(self.dev.h, space, _ptr(out)))
         return out
+
+    def instr_kernel(self, instr):
+        return self.dev._L.dnlp_instr_kernel(self.dev.h, int(instr)).decode()
 
     def kernel_launches(self):
         return int(self.dev._L.dnlp_kernel_launches(self.dev.h))

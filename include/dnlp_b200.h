@@ -137,6 +137,7 @@ int dnlp_run_device(dnlp_oracle *o, int32_t prog_mask, int32_t iters, float *ela
 int dnlp_profile_instrs(dnlp_oracle *o, int32_t prog, int32_t iters, float *ms_per_instr /* n_instr */);
 int dnlp_read_output(dnlp_oracle *o, int32_t dst_space, double *out);   /* D2H of one output array */
 int64_t dnlp_kernel_launches(dnlp_oracle *o);                           /* launches since create */
+const char *dnlp_instr_kernel(dnlp_oracle *o, int32_t instr);           /* kernel name of an executed instruction */
 int dnlp_set_cache(dnlp_oracle *o, int32_t enabled);                    /* x-keyed forward cache on/off */
 
 /* ---- batched multi-start evaluation (BASELINE config 4; the reference's serial `best_of` loop,

@@ -1,16 +1,15 @@
 #!/bin/bash
-# ncu evidence for the bench workload (run under gpurun; outputs in gpurun_out/).
-#   tools/profile.sh c2      -> launch list + full capture of the two dominant kernels
-set -x
+# ncu evidence for a bench workload (run under gpurun; outputs in gpurun_out/).
+#   tools/profile.sh c2      -> launch list + full capture of the dominant kernels
 W=${1:-c2}
 mkdir -p gpurun_out
 export DNLP_BENCH_WORKLOAD=$W
 # every launch with its device time (cold cache, serialised: compare shares)
-ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
     --log-file gpurun_out/launches_$W.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench_$W.log 2>&1
-# the dominant kernels, full set
+# the dominant kernels, full set (one launch of each kind)
 ncu --set full --clock-control none --import-source on \
-    -k regex:'gemv_cta_kernel|scale_stream_kernel|poly_rows_kernel|poly1_stream_kernel' -s 4 -c 4 \
-    -o gpurun_out/prof_$W python bench.py --steps 1 --warmup 3 --no-cpu-baseline >> gpurun_out/ncu_bench_$W.log 2>&1
+    -k regex:'gemv_cta_kernel|scale_stream_kernel|poly_rows_kernel|poly1_stream_kernel|poly_reduce_kernel|elem_batch_kernel|bgemm_dmma|bsmallk' \
+    -s 8 -c 10 -o gpurun_out/prof_$W python bench.py --steps 1 --warmup 3 --no-cpu-baseline >> gpurun_out/ncu_bench_$W.log 2>&1
 ncu -i gpurun_out/prof_$W.ncu-rep --page raw --csv > gpurun_out/prof_${W}_raw.csv 2>/dev/null
-ls -la gpurun_out/
+ls -la gpurun_out/ | grep $W
