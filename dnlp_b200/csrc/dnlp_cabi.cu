@@ -61,7 +61,9 @@ struct dnlp_oracle {
   std::vector<void *> owned;           // device allocations to free
   std::vector<uint8_t> valid;          // per instruction: result valid for the current x
   double *hx = nullptr;                // pinned host copy of the last uploaded point
+  double *hlam = nullptr;              // pinned host copy of (sigma, lambda)
   bool have_last_x = false;
+  bool have_last_lam = false;
   bool cache_enabled = true;
   int64_t launches = 0;
   std::string err;
@@ -346,9 +348,14 @@ int dnlp_oracle::put_x(const double *x) {
 }
 
 int dnlp_oracle::put_lam(const double *lam, double sigma) {
-  // sigma and lambda are adjacent in V: [n] = sigma, [n+1, n+1+m) = lambda
-  CK(cudaMemcpyAsync(V + n, &sigma, sizeof(double), cudaMemcpyHostToDevice, stream));
-  if (m > 0) CK(cudaMemcpyAsync(V + n + 1, lam, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, stream));
+  // sigma and lambda are adjacent in V: [n] = sigma, [n+1, n+1+m) = lambda; staged (multi-threaded
+  // for large m) into one pinned buffer and uploaded with a single copy, skipped when unchanged
+  bool changed = !have_last_lam || hlam[0] != sigma;
+  hlam[0] = sigma;
+  if (m > 0) changed = stage_point(hlam + 1, lam, m, have_last_lam) || changed;
+  if (!changed) return 0;
+  CK(cudaMemcpyAsync(V + n, hlam, (size_t)(m + 1) * sizeof(double), cudaMemcpyHostToDevice, stream));
+  have_last_lam = true;
   return 0;
 }
 
@@ -379,6 +386,7 @@ void dnlp_destroy(dnlp_oracle *o) {
   if (o->stream) cudaStreamSynchronize(o->stream);
   for (void *p : o->owned) cudaFree(p);
   if (o->hx) cudaFreeHost(o->hx);
+  if (o->hlam) cudaFreeHost(o->hlam);
   if (o->ev0) cudaEventDestroy(o->ev0);
   if (o->ev1) cudaEventDestroy(o->ev1);
   if (o->stream) cudaStreamDestroy(o->stream);
@@ -404,6 +412,8 @@ static int create_impl(dnlp_oracle *o, const dnlp_tape_desc *t) {
 
   CK(cudaMallocHost(&p, (size_t)(t->n + 2) * sizeof(double)));
   o->hx = static_cast<double *>(p);
+  CK(cudaMallocHost(&p, (size_t)(t->m + 2) * sizeof(double)));
+  o->hlam = static_cast<double *>(p);
   CK(cudaMalloc(&p, 4096 * sizeof(double)));
   o->owned.push_back(p);
   o->scratch = static_cast<double *>(p);
@@ -570,6 +580,7 @@ void dnlp_host_free(void *p) { if (p) cudaFreeHost(p); }
 int dnlp_upload_point(dnlp_oracle *o, const double *x, const double *lam, double sigma) {
   ENTER(o);
   o->have_last_x = false;
+  o->have_last_lam = false;
   if (o->put_x(x)) return 1;
   if (lam != nullptr || o->m == 0) { if (o->put_lam(lam, sigma)) return 1; }
   CK(cudaStreamSynchronize(o->stream));

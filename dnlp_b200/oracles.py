@@ -78,6 +78,13 @@ class GpuOracles:
                                                 None if lam is None else _ptr(lam), float(sigma), _ptr(compact)))
         return pos, compact
 
+    def _stage_lam(self, duals):
+        lam = np.ascontiguousarray(duals, dtype=np.float64).reshape(-1)
+        if lam.size != self.m:
+            raise ValueError("duals has %d entries, expected %d" % (lam.size, self.m))
+        self._lam_ref = lam if self.m else self._lam      # m = 0: any valid pointer
+        return self._lam_ref
+
     def _stage_x(self, x):
         # the library stages x into its own pinned buffer (multi-threaded for large n) and detects an
         # unchanged point, so no copy is made here
@@ -122,15 +129,12 @@ class GpuOracles:
     def hessian(self, x, duals, obj_factor):
         if not self.with_hessian:
             raise RuntimeError("this oracle was compiled without the Hessian program")
-        lam = np.asarray(duals, dtype=np.float64).reshape(-1)
-        if lam.size != self.m:
-            raise ValueError("duals has %d entries, expected %d" % (lam.size, self.m))
-        self._lam[:self.m] = lam
+        lam = self._stage_lam(duals)
         if "hess" in self._dyn:
-            pos, compact = self._eval_dyn("hess", 4, x, self._lam, obj_factor)
+            pos, compact = self._eval_dyn("hess", 4, x, lam, obj_factor)
             self._hess[pos] = compact
             return self._hess
-        self.dev.check(self.dev._L.dnlp_eval_hess(self.dev.h, self._stage_x(x), _ptr(self._lam),
+        self.dev.check(self.dev._L.dnlp_eval_hess(self.dev.h, self._stage_x(x), _ptr(lam),
                                                  float(obj_factor), _ptr(self._hess)))
         return self._hess
 
@@ -143,11 +147,18 @@ class GpuOracles:
 
     # ---- fused evaluation of the whole set at one point ------------------------
     def eval_all(self, x, duals, obj_factor, want=("f", "grad", "g", "jac", "hess")):
-        lam = np.asarray(duals, dtype=np.float64).reshape(-1)
-        self._lam[:self.m] = lam
+        if self._dyn:
+            # constant-entry elision is active: the per-callback path moves far fewer bytes, and the
+            # x-keyed cache makes the five calls share one upload and one forward sweep
+            out = {}
+            for k in want:
+                out[k] = {"f": self.objective, "grad": self.gradient, "g": self.constraints,
+                          "jac": self.jacobian}[k](x) if k != "hess" else self.hessian(x, duals, obj_factor)
+            return out
+        lam = self._stage_lam(duals)
         bufs = {"f": self._f, "grad": self.grad_obj, "g": self._g, "jac": self._jac, "hess": self._hess}
         args = [_ptr(bufs[k]) if k in want else None for k in ("f", "grad", "g", "jac", "hess")]
-        self.dev.check(self.dev._L.dnlp_eval_all(self.dev.h, self._stage_x(x), _ptr(self._lam),
+        self.dev.check(self.dev._L.dnlp_eval_all(self.dev.h, self._stage_x(x), _ptr(lam),
                                                 float(obj_factor), *args))
         return {k: (np.float64(self._f[0]) if k == "f" else bufs[k]) for k in want}
 
