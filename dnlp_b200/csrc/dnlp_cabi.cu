@@ -569,6 +569,21 @@ int dnlp_eval_dyn(dnlp_oracle *o, int32_t prog, const double *x, const double *l
   return 0;
 }
 
+int dnlp_run(dnlp_oracle *o, int32_t prog, const double *x, const double *lam, double sigma) {
+  ENTER(o);
+  if (prog < 0 || prog >= DNLP_NPROG) { err = "bad program id"; return 1; }
+  if (o->put_x(x)) return 1;
+  if ((prog == DNLP_PROG_HESS || prog == DNLP_PROG_ALL) && o->put_lam(lam, sigma)) return 1;
+  if (o->run_program(prog, false)) return 1;
+  CK(cudaStreamSynchronize(o->stream));
+  return 0;
+}
+
+void *dnlp_output_ptr(dnlp_oracle *o, int32_t space) {
+  if (space < DNLP_DST_F || space > DNLP_DST_HESS) return nullptr;
+  return o->out[space];
+}
+
 void *dnlp_host_alloc(int64_t bytes) {
   void *p = nullptr;
   if (cudaMallocHost(&p, (size_t)bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }

@@ -19,6 +19,15 @@ def _ptr(a):
     return a.ctypes.data_as(_f64p)
 
 
+class _DeviceArray:
+    """Minimal CUDA array interface (v3) over memory owned by a GpuOracles instance."""
+
+    def __init__(self, ptr, count, owner):
+        self._owner = owner
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": "<f8", "data": (ptr, False),
+                                         "version": 3, "strides": None}
+
+
 class GpuOracles:
     ELIDE_MIN = 4096               # outputs shorter than this are always copied whole
     ELIDE_MAX_FRACTION = 0.5       # elide constants when at most this share of entries is dynamic
@@ -161,6 +170,21 @@ class GpuOracles:
         self.dev.check(self.dev._L.dnlp_eval_all(self.dev.h, self._stage_x(x), _ptr(lam),
                                                 float(obj_factor), *args))
         return {k: (np.float64(self._f[0]) if k == "f" else bufs[k]) for k in want}
+
+    # ---- device-resident results (multi-GPU assembly) ---------------------------
+    def run(self, name, x, duals=None, obj_factor=1.0):
+        """Execute one program and leave its output in HBM (no D2H)."""
+        lam = self._stage_lam(duals) if duals is not None else None
+        self.dev.check(self.dev._L.dnlp_run(self.dev.h, _cabi.PROG_IDS[name], self._stage_x(x),
+                                           None if lam is None else _ptr(lam), float(obj_factor)))
+
+    def output_device_array(self, name):
+        """Object exposing ``__cuda_array_interface__`` for the full device output ``name``
+        (zero-copy view for torch.as_tensor / cupy)."""
+        space = {"f": 1, "grad": 2, "g": 3, "jac": 4, "hess": 5}[name]
+        n = {"f": 1, "grad": self.n, "g": self.m, "jac": self.nnz_jac, "hess": self.nnz_hess}[name]
+        ptr = self.dev._L.dnlp_output_ptr(self.dev.h, space)
+        return _DeviceArray(int(ptr), n, self)
 
     # ---- device-resident measurement hooks (bench.py) ---------------------------
     def upload_point(self, x, duals=None, obj_factor=1.0):

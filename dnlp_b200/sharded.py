@@ -81,6 +81,107 @@ class _TorchComm:
         return t.cpu().numpy() if self.cuda else vec
 
 
+def _runs(idx):
+    """Contiguous runs of an index map: [(src_start, src_stop, dst_start)]; shard maps are a few long
+    ranges, so gathering through slices is a memcpy instead of a fancy-index pass."""
+    idx = np.asarray(idx, dtype=np.int64)
+    if idx.size == 0:
+        return []
+    brk = np.where(np.diff(idx) != 1)[0] + 1
+    starts = np.concatenate([[0], brk])
+    stops = np.concatenate([brk, [idx.size]])
+    return [(int(idx[a]), int(idx[a]) + int(b - a), int(a)) for a, b in zip(starts, stops)]
+
+
+def _take(src, runs, out):
+    if len(runs) > 64:
+        raise ValueError("index map too fragmented")
+    for s0, s1, d0 in runs:
+        out[d0:d0 + (s1 - s0)] = src[s0:s1]
+    return out
+
+
+class _DeviceAssembler:
+    """NCCL path of ``RowShardedOracles``: local outputs stay in HBM, entries that several ranks
+    contribute to are all-reduced, entries owned by one rank are all-gathered, and the global
+    output is assembled on the device, so one contiguous D2H per callback reaches the host."""
+
+    def __init__(self, owner, device):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.o = torch, dist, owner
+        self.dev = torch.device("cuda", device)
+        self.world = dist.get_world_size()
+        self.plan = {}
+        for name in ("grad", "g", "jac", "hess"):
+            self.plan[name] = self._plan(name)
+        self._f = torch.zeros(1, dtype=torch.float64, device=self.dev)
+
+    def _plan(self, name):
+        torch, dist, o = self.torch, self.dist, self.o
+        dyn = o.gs.dynamic[name].astype(np.int64)
+        nd = dyn.size
+        sel, cidx = o._sel[name], o._cidx[name]
+        cnt = torch.from_numpy(np.bincount(cidx, minlength=max(nd, 1)).astype(np.int64)).to(self.dev)
+        dist.all_reduce(cnt)
+        cnt = cnt.cpu().numpy()[:nd] if nd else np.zeros(0, np.int64)
+        shared_slots = np.where(cnt > 1)[0]
+        mine_shared = cnt[cidx] > 1 if nd else np.zeros(0, bool)
+        sel_sh, tgt_sh = sel[mine_shared], np.searchsorted(shared_slots, cidx[mine_shared])
+        sel_ow, slot_ow = sel[~mine_shared], cidx[~mine_shared]
+        n_ow = torch.tensor([sel_ow.size], dtype=torch.int64, device=self.dev)
+        sizes = [torch.zeros(1, dtype=torch.int64, device=self.dev) for _ in range(self.world)]
+        dist.all_gather(sizes, n_ow)
+        maxown = max(1, max(int(t.item()) for t in sizes))
+        pad = np.full(maxown, -1, dtype=np.int64)
+        pad[:slot_ow.size] = slot_ow
+        all_slots = torch.empty(self.world * maxown, dtype=torch.int64, device=self.dev)
+        dist.all_gather_into_tensor(all_slots, torch.from_numpy(pad).to(self.dev))
+        valid = torch.nonzero(all_slots >= 0).reshape(-1)
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int64)).to(self.dev)  # noqa: E731
+        dense = nd > 0.5 * o._out[name].size
+        p = {"nd": nd, "maxown": maxown, "sel_ow": t(sel_ow), "n_ow": int(sel_ow.size),
+             "sel_sh": t(sel_sh), "tgt_sh": t(tgt_sh), "shared_slots": t(shared_slots), "n_sh": int(shared_slots.size),
+             "valid": valid, "valid_slots": all_slots[valid], "dense": dense,
+             "ow_buf": torch.zeros(maxown, dtype=torch.float64, device=self.dev),
+             "gbuf": torch.empty(self.world * maxown, dtype=torch.float64, device=self.dev),
+             "full": torch.zeros(max(nd, 1), dtype=torch.float64, device=self.dev)}
+        if dense:
+            p["out_dev"] = torch.from_numpy(np.ascontiguousarray(o.gs.const[name], dtype=np.float64)).to(self.dev)
+            p["dyn_pos"] = t(dyn)
+            p["host"] = torch.from_numpy(o._out[name])
+        return p
+
+    def objective(self, f_loc):
+        self._f[0] = f_loc
+        self.dist.all_reduce(self._f)
+        return float(self._f.item())
+
+    def assemble(self, name):
+        """Local result of program ``name`` is in HBM; returns the assembled global host array."""
+        torch, dist, o, p = self.torch, self.dist, self.o, self.plan[name]
+        t = torch.as_tensor(o.local.output_device_array(name), device=self.dev)
+        full = p["full"]
+        full.zero_()
+        if p["n_ow"]:
+            p["ow_buf"][:p["n_ow"]] = t.index_select(0, p["sel_ow"])
+        dist.all_gather_into_tensor(p["gbuf"], p["ow_buf"])
+        full[p["valid_slots"]] = p["gbuf"][p["valid"]]
+        if p["n_sh"]:
+            sh = torch.zeros(p["n_sh"], dtype=torch.float64, device=self.dev)
+            if p["sel_sh"].numel():
+                sh.index_add_(0, p["tgt_sh"], t.index_select(0, p["sel_sh"]))
+            dist.all_reduce(sh)
+            full[p["shared_slots"]] = sh
+        out = o._out[name]
+        if p["dense"]:
+            p["out_dev"][p["dyn_pos"]] = full[:p["nd"]]
+            p["host"].copy_(p["out_dev"])
+        elif p["nd"]:
+            out[o.gs.dynamic[name]] = full[:p["nd"]].cpu().numpy()
+        return out
+
+
 class RowShardedOracles:
     """Same seven callbacks as ``GpuOracles``; every call is collective over the group."""
 
@@ -118,6 +219,18 @@ class RowShardedOracles:
             out = np.array(gs.const[name], dtype=np.float64, copy=True)
             self._out[name] = out
         self.grad_obj = self._out["grad"]
+        self._var_runs, self._con_runs = None, None
+        try:
+            vr, cr = _runs(lay.var_map), _runs(lay.con_map)
+            if len(vr) <= 64 and len(cr) <= 64:
+                self._var_runs, self._con_runs = vr, cr
+                self._xl, self._ll = np.empty(lay.var_map.size), np.empty(max(lay.con_map.size, 1))
+        except Exception:
+            pass
+        # device-side assembly over NCCL when the local evaluator keeps its outputs in HBM
+        self._devasm = None
+        if getattr(self.comm, "cuda", False) and hasattr(self.local, "output_device_array"):
+            self._devasm = _DeviceAssembler(self, device)
 
     @staticmethod
     def _hess_lookup(gs, lay, lhr, lhc):
@@ -132,7 +245,16 @@ class RowShardedOracles:
 
     # ------------------------------------------------------------------------------------------
     def _local_x(self, x):
-        return np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(-1)[self.layout.var_map])
+        x = np.asarray(x, dtype=np.float64).reshape(-1)
+        if self._var_runs is not None:
+            return _take(x, self._var_runs, self._xl)
+        return np.ascontiguousarray(x[self.layout.var_map])
+
+    def _local_lam(self, lam):
+        lam = np.asarray(lam, dtype=np.float64).reshape(-1)
+        if self._con_runs is not None:
+            return _take(lam, self._con_runs, self._ll)[:self.layout.con_map.size]
+        return np.ascontiguousarray(lam[self.layout.con_map])
 
     def _reduce_into(self, name, local_vals, extra=None):
         """Scatter-add the local dynamic entries into the compact global vector, all-reduce it
@@ -153,24 +275,33 @@ class RowShardedOracles:
     def objective(self, x):
         # constants of the objective live in rank 0's local problem (it carries every non-row term)
         f_loc = float(self.local.objective(self._local_x(x)))
+        if self._devasm is not None:
+            return np.float64(self._devasm.objective(f_loc))
         return np.float64(self.comm.allreduce(np.array([f_loc]))[0])
 
+    def _callback(self, name, x, lam=None, sigma=1.0):
+        xl = self._local_x(x)
+        if self._devasm is not None:
+            self.local.run(name, xl, lam, sigma)
+            return self._devasm.assemble(name)
+        fn = {"grad": self.local.gradient, "g": self.local.constraints, "jac": self.local.jacobian}
+        vals = self.local.hessian(xl, lam, sigma) if name == "hess" else fn[name](xl)
+        return self._reduce_into(name, vals)[0]
+
     def gradient(self, x):
-        return self._reduce_into("grad", self.local.gradient(self._local_x(x)))[0]
+        return self._callback("grad", x)
 
     def constraints(self, x):
-        return self._reduce_into("g", self.local.constraints(self._local_x(x)))[0]
+        return self._callback("g", x)
 
     def jacobian(self, x):
-        return self._reduce_into("jac", self.local.jacobian(self._local_x(x)))[0]
+        return self._callback("jac", x)
 
     def jacobianstructure(self):
         return self.gs.jac_rows, self.gs.jac_cols
 
     def hessian(self, x, duals, obj_factor):
-        lam = np.asarray(duals, dtype=np.float64).reshape(-1)
-        lam_loc = np.ascontiguousarray(lam[self.layout.con_map])
-        return self._reduce_into("hess", self.local.hessian(self._local_x(x), lam_loc, obj_factor))[0]
+        return self._callback("hess", x, self._local_lam(duals), obj_factor)
 
     def hessianstructure(self):
         return self.gs.hess_rows, self.gs.hess_cols

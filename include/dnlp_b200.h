@@ -123,6 +123,13 @@ int dnlp_set_dynamic(dnlp_oracle *o, int32_t dst_space, const int32_t *pos, int6
 int dnlp_eval_dyn(dnlp_oracle *o, int32_t prog, const double *x, const double *lam, double sigma,
                   double *compact);
 
+/* ---- device-resident results (multi-GPU assembly: outputs are reduced / gathered over NVLink
+ *      without a host round trip) ----
+ * dnlp_run stages the inputs and executes program `prog`, leaving the result in HBM;
+ * dnlp_output_ptr returns the device address of a full output array (length n, m, nnz_jac, nnz_hess). */
+int dnlp_run(dnlp_oracle *o, int32_t prog, const double *x, const double *lam, double sigma);
+void *dnlp_output_ptr(dnlp_oracle *o, int32_t dst_space);
+
 /* ---- pinned host memory for callers that want true async copies ---- */
 void *dnlp_host_alloc(int64_t bytes);
 void dnlp_host_free(void *p);
