@@ -76,10 +76,17 @@ class GpuOracles:
         return arr
 
     def close(self):
-        self.dev.close()
-        for h in self._handles:
+        if getattr(self, "dev", None) is not None:
+            self.dev.close()
+        for h in getattr(self, "_handles", []):
             h.free()
         self._handles = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def _eval_dyn(self, name, prog, x, lam=None, sigma=1.0):
         pos, compact = self._dyn[name]

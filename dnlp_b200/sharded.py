@@ -149,7 +149,11 @@ class _DeviceAssembler:
         if dense:
             p["out_dev"] = torch.from_numpy(np.ascontiguousarray(o.gs.const[name], dtype=np.float64)).to(self.dev)
             p["dyn_pos"] = t(dyn)
-            p["host"] = torch.from_numpy(o._out[name])
+            p["host"] = torch.empty(o._out[name].size, dtype=torch.float64, pin_memory=True)   # pinned: D2H at PCIe rate
+            p["host"].copy_(torch.from_numpy(o._out[name]))
+            o._out[name] = p["host"].numpy()
+            if name == "grad":
+                o.grad_obj = o._out[name]
         return p
 
     def objective(self, f_loc):
