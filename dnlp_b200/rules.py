@@ -464,13 +464,23 @@ class Builder:
 
     @staticmethod
     def _coo_sum_duplicates(rows, cols, sv):
-        """``coo_matrix.sum_duplicates``: lexsort by (row, col), merge equal pairs."""
+        """``coo_matrix.sum_duplicates``: sort by (row, col), merge equal pairs.  One int64 key and a
+        stable sort (timsort merges the few pre-sorted runs the rules emit in linear time); already
+        canonical input is returned untouched."""
         if sv.K == 0:
             return rows, cols, sv
-        order = np.lexsort((cols, rows))
+        rows = np.asarray(rows, dtype=np.int64)
+        cols = np.asarray(cols, dtype=np.int64)
+        key = rows * (int(cols.max()) + 1) + cols
+        if key.size < 2 or bool(np.all(key[1:] > key[:-1])):
+            return rows, cols, sv
+        order = np.argsort(key, kind="stable")
+        key = key[order]
+        new = np.ones(key.size, dtype=bool)
+        new[1:] = key[1:] != key[:-1]
         r, c = rows[order], cols[order]
-        new = np.ones(r.size, dtype=bool)
-        new[1:] = (r[1:] != r[:-1]) | (c[1:] != c[:-1])
+        if bool(new.all()):
+            return r, c, sv.gather(order)
         grp = np.cumsum(new) - 1
         return r[new], c[new], sv.gather(order).group_sum(grp, int(grp[-1]) + 1)
 
