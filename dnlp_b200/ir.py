@@ -246,7 +246,7 @@ def neg(x):
 
 def sum(x, axis=None, keepdims=False):  # noqa: A001  (mirrors cvxpy.sum)
     x = as_node(x)
-    shape = np.sum(np.empty(x.shape), axis=axis, keepdims=keepdims).shape
+    shape = np.sum(np.zeros(x.shape), axis=axis, keepdims=keepdims).shape
     return _const_fold("sum", [x], shape, axis=axis, keepdims=keepdims)
 
 
@@ -331,7 +331,7 @@ def multiply(a, b):
 def _mul_shape(a, b):
     if a.ndim == 0 or b.ndim == 0:
         return b.shape if a.ndim == 0 else a.shape
-    return np.matmul(np.empty(a.shape), np.empty(b.shape)).shape
+    return np.matmul(np.zeros(a.shape), np.zeros(b.shape)).shape
 
 
 def matmul(a, b):

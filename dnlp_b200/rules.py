@@ -270,7 +270,7 @@ class Builder:
             v = self.value(arg)
             if node.attrs["axis"] is None:
                 return v.sum_all()
-            out_keep = np.sum(np.empty(arg.shape), axis=node.attrs["axis"], keepdims=True).shape
+            out_keep = np.sum(np.zeros(arg.shape), axis=node.attrs["axis"], keepdims=True).shape
             G = int(np.prod(out_keep, dtype=np.int64))
             I = np.arange(G, dtype=np.int64).reshape(out_keep, order="F")
             grp = _flatF(np.broadcast_to(I, arg.shape))

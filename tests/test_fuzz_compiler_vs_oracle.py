@@ -1,0 +1,189 @@
+"""Differential fuzzing: random smooth problems, DAG compiler (+ NumPy tape interpreter) vs the CPU
+oracle (which is itself pinned to the live reference by the golden tests).
+
+Every generated problem must either compile to patterns bit-identical to the oracle's and values
+within 1e-10, or be rejected by BOTH with the same exception type.  Seeds are fixed, so the suite is
+deterministic; the GPU variant runs a subset through the CUDA path."""
+import numpy as np
+import pytest
+
+from dnlp_b200 import ir
+from dnlp_b200.compiler import compile_problem
+from golden_util import assert_close
+from oracle.dnlp_oracle import RefOracles
+from tape_interp import TapeInterp
+
+UNARY = ["exp", "log", "entr", "logistic", "sin", "cos", "tan", "sinh", "tanh", "asinh", "atanh", "xexp"]
+
+
+def _atom(rng, v):
+    k = rng.integers(0, len(UNARY) + 3)
+    if k < len(UNARY):
+        return ir.Node(UNARY[k], [v], v.shape)
+    p = [2, 3, 0.5, 1.5, 2.5][rng.integers(0, 5)]
+    return ir.power(v, p)
+
+
+def _affine_wrap(rng, e, depth=0):
+    """Random shape-preserving or reducing affine atom on top of ``e``."""
+    k = rng.integers(0, 9)
+    if k == 0:
+        return ir.neg(e)
+    if k == 1 and e.ndim >= 1:
+        c = rng.uniform(-2, 2, e.shape)
+        c[rng.random(e.shape) < 0.2] = 0.0
+        if not c.any():
+            c.flat[0] = 1.0
+        return ir.multiply(c, e) if rng.random() < 0.5 else ir.multiply(e, c)
+    if k == 2 and e.ndim == 2:
+        return ir.sum(e, axis=int(rng.integers(0, 2)), keepdims=bool(rng.integers(0, 2)))
+    if k == 3 and e.ndim >= 1:
+        return ir.sum(e)
+    if k == 4 and e.ndim == 1 and e.shape[0] >= 3:
+        lo = int(rng.integers(0, 2))
+        return ir.index(e, slice(lo, e.shape[0], int(rng.integers(1, 3))))
+    if k == 5 and e.ndim == 2:
+        return ir.transpose(e)
+    if k == 6 and e.ndim >= 1:
+        A = rng.uniform(-1, 1, (int(rng.integers(1, 4)), e.shape[0]))
+        A[rng.random(A.shape) < 0.3] = 0.0
+        if not A.any():
+            # an all-zero constant empties the Jacobian block; the reference then indexes with an empty
+            # FLOAT array in Oracles.gradient (nlp_solver.py:232) and crashes - not a case worth pinning
+            A[0, 0] = 1.0
+        return ir.matmul(A, e)
+    if k == 7 and e.ndim == 2:
+        B = rng.uniform(-1, 1, (e.shape[1], int(rng.integers(1, 4))))
+        return ir.matmul(e, B)
+    if k == 8 and e.ndim == 1 and e.shape[0] >= 2:
+        idx = [int(i) for i in rng.integers(0, e.shape[0], int(rng.integers(1, 4)))]
+        return ir.index(e, idx)
+    return e
+
+
+def random_problem(seed):
+    rng = np.random.default_rng(seed)
+    shapes = [(int(rng.integers(2, 5)),), (int(rng.integers(2, 4)), int(rng.integers(2, 4))), ()]
+    nvars = int(rng.integers(1, 4))
+    variables = [ir.Variable(shapes[int(rng.integers(0, 3))]) for _ in range(nvars)]
+
+    def term():
+        v = variables[int(rng.integers(0, nvars))]
+        r = rng.random()
+        if r < 0.12 and nvars >= 2:
+            a, b = rng.choice(nvars, 2, replace=False)
+            va, vb = variables[a], variables[b]
+            if va.shape == vb.shape and va.ndim >= 1:
+                e = ir.Node("multiply", [va, vb], va.shape)
+            elif va.ndim == 2 and vb.ndim == 2 and va.shape[1] == vb.shape[0]:
+                e = ir.Node("matmul", [va, vb], (va.shape[0], vb.shape[1]))
+            elif va.ndim >= 1 and vb.ndim >= 1 and va.size == vb.size and rng.random() < 0.5:
+                e = ir.Node("rel_entr", [va, vb], va.shape) if va.shape == vb.shape else _atom(rng, va)
+            else:
+                e = _atom(rng, va)
+        elif r < 0.2 and v.ndim >= 1:
+            e = v if rng.random() < 0.5 else ir.multiply(rng.uniform(-1, 1, v.shape), v)
+        elif r < 0.27 and v.ndim == 1:
+            Q = rng.uniform(-1, 1, (v.size, v.size))
+            Q = Q + Q.T
+            Q[rng.random(Q.shape) < 0.2] = 0.0
+            e = ir.Node("quad_form", [v, ir.Constant(Q)], ())
+        else:
+            e = _atom(rng, v)
+        for _ in range(int(rng.integers(0, 3))):
+            e = _affine_wrap(rng, e)
+        return e
+
+    def scalarise(e):
+        return e if e.size == 1 and e.ndim == 0 else ir.sum(e)
+
+    obj = scalarise(term())
+    for _ in range(int(rng.integers(0, 3))):
+        t = scalarise(term())
+        obj = ir.Node("add", [obj, t] if obj.op != "add" else obj.args + [t], ())
+    cons = []
+    for _ in range(int(rng.integers(0, 4))):
+        e = term()
+        if rng.random() < 0.4:
+            t2 = term()
+            if t2.shape == e.shape:
+                e = ir.Node("add", [e, ir.neg(t2)], e.shape)
+        cons.append(e)
+    prob = ir.ProblemIR(obj, cons)
+    prob.x0 = rng.uniform(0.3, 0.9, prob.n)       # only the variables that actually appear
+    return prob, rng
+
+
+def _outcome(fn):
+    try:
+        return "ok", fn()
+    except Exception as e:            # noqa: BLE001
+        return type(e).__name__, None
+
+
+def _check(seed, make_evaluator):
+    prob, rng = random_problem(seed)
+
+    def build_ref():
+        r = RefOracles(prob)
+        r.jacobianstructure()
+        r.hessianstructure()
+        return r
+    s_ref, ref = _outcome(build_ref)
+    s_cmp, tape = _outcome(lambda: compile_problem(prob))
+    assert s_ref == s_cmp, "seed %d: oracle %s vs compiler %s" % (seed, s_ref, s_cmp)
+    if s_ref != "ok":
+        return False
+    np.testing.assert_array_equal(tape.jac_rows, ref.jac_rows)
+    np.testing.assert_array_equal(tape.jac_cols, ref.jac_cols)
+    np.testing.assert_array_equal(tape.hess_rows, ref.hess_rows)
+    np.testing.assert_array_equal(tape.hess_cols, ref.hess_cols)
+    ev = make_evaluator(prob, tape)
+    with np.errstate(all="ignore"):
+        for _ in range(2):
+            x = prob.x0 * (1 + 0.1 * rng.standard_normal(prob.n))
+            x = np.clip(x, 0.05, 0.95)
+            lam = rng.standard_normal(prob.m)
+            sigma = float(rng.uniform(0.5, 1.5))
+            assert_close(ev("f", x, lam, sigma), ref.objective(x), "f seed %d" % seed)
+            assert_close(ev("grad", x, lam, sigma), ref.gradient(x), "grad seed %d" % seed)
+            if prob.m:
+                assert_close(ev("g", x, lam, sigma), ref.constraints(x), "g seed %d" % seed)
+            assert_close(ev("jac", x, lam, sigma), ref.jacobian(x), "jac seed %d" % seed)
+            assert_close(ev("hess", x, lam, sigma), ref.hessian(x, lam, sigma), "hess seed %d" % seed)
+    return True
+
+
+def _interp_evaluator(prob, tape):
+    it = TapeInterp(tape)
+    return lambda name, x, lam, sigma: it.eval(name, x, lam, sigma)
+
+
+@pytest.mark.parametrize("block", range(10))
+def test_fuzz_compiler_vs_oracle(block):
+    accepted = 0
+    for seed in range(block * 40, block * 40 + 40):
+        accepted += bool(_check(seed, _interp_evaluator))
+    assert accepted >= 10, "generator produced too few valid problems (%d)" % accepted
+
+
+@pytest.mark.gpu
+def test_fuzz_gpu_vs_oracle():
+    from dnlp_b200.oracles import GpuOracles
+    opened = []
+
+    def gpu_evaluator(prob, tape):
+        o = GpuOracles(prob)
+        opened.append(o)
+        fn = {"f": lambda x, l, s: o.objective(x), "grad": lambda x, l, s: o.gradient(x),
+              "g": lambda x, l, s: o.constraints(x), "jac": lambda x, l, s: o.jacobian(x),
+              "hess": lambda x, l, s: o.hessian(x, l, s)}
+        return lambda name, x, lam, sigma: fn[name](x, lam, sigma)
+    try:
+        for seed in range(1000, 1120):
+            _check(seed, gpu_evaluator)
+            while opened:
+                opened.pop().close()
+    finally:
+        while opened:
+            opened.pop().close()
