@@ -88,6 +88,11 @@ def random_problem(seed):
             Q = Q + Q.T
             Q[rng.random(Q.shape) < 0.2] = 0.0
             e = ir.Node("quad_form", [v, ir.Constant(Q)], ())
+        elif r < 0.32:
+            # an atom applied to a non-variable argument: Dnlp2Smooth would have lifted it; both the
+            # reference rules and the compiler must reject it with ValueError (atoms/atom.py:509-510)
+            inner = _affine_wrap(rng, v)
+            e = ir.Node(UNARY[int(rng.integers(0, len(UNARY)))], [inner], inner.shape)
         else:
             e = _atom(rng, v)
         for _ in range(int(rng.integers(0, 3))):
