@@ -49,7 +49,7 @@ EXPORTS = [
     "dnlp_device_count", "dnlp_version", "dnlp_create", "dnlp_destroy", "dnlp_last_error",
     "dnlp_eval_f", "dnlp_eval_grad", "dnlp_eval_g", "dnlp_eval_jac", "dnlp_eval_hess", "dnlp_eval_all",
     "dnlp_host_alloc", "dnlp_host_free", "dnlp_upload_point", "dnlp_run_device", "dnlp_profile_instrs",
-    "dnlp_read_output", "dnlp_kernel_launches", "dnlp_set_cache", "dnlp_set_dynamic", "dnlp_eval_dyn", "dnlp_instr_kernel", "dnlp_run", "dnlp_output_ptr",
+    "dnlp_read_output", "dnlp_kernel_launches", "dnlp_set_cache", "dnlp_set_graphs", "dnlp_set_dynamic", "dnlp_eval_dyn", "dnlp_instr_kernel", "dnlp_run", "dnlp_output_ptr",
     "dnlp_batch_create", "dnlp_batch_destroy", "dnlp_batch_last_error", "dnlp_batch_eval", "dnlp_batch_upload",
     "dnlp_batch_run_device", "dnlp_batch_profile_instrs", "dnlp_batch_kernel_launches",
 ]
@@ -92,6 +92,7 @@ def lib():
     L.dnlp_kernel_launches.argtypes = [vp]
     L.dnlp_kernel_launches.restype = C.c_int64
     L.dnlp_set_cache.argtypes = [vp, C.c_int32]
+    L.dnlp_set_graphs.argtypes = [vp, C.c_int32]
     L.dnlp_run.argtypes = [vp, C.c_int32, c_f64p, c_f64p, C.c_double]
     L.dnlp_output_ptr.argtypes = [vp, C.c_int32]
     L.dnlp_output_ptr.restype = vp
@@ -127,15 +128,21 @@ def f64(a):
 
 
 def pinned_empty(count):
-    """float64 NumPy array backed by cudaMallocHost memory (freed with the returned handle)."""
+    """float64 NumPy array backed by cudaMallocHost memory.
+
+    The pinned block is released when the LAST view of it disappears (the handle rides on the
+    ctypes buffer every view keeps as its base), so arrays handed to a solver stay valid even after
+    the oracle that produced them was closed."""
     L = lib()
     nbytes = max(int(count), 1) * 8
     ptr = L.dnlp_host_alloc(nbytes)
     if not ptr:
         raise MemoryError("cudaMallocHost(%d) failed" % nbytes)
     buf = (C.c_double * max(int(count), 1)).from_address(ptr)
+    handle = _PinnedHandle(ptr)
+    buf._dnlp_handle = handle
     arr = np.frombuffer(buf, dtype=np.float64, count=int(count))
-    return arr, _PinnedHandle(ptr)
+    return arr, handle
 
 
 class _PinnedHandle:
@@ -143,9 +150,15 @@ class _PinnedHandle:
         self.ptr = ptr
 
     def free(self):
-        if self.ptr:
-            lib().dnlp_host_free(self.ptr)
-            self.ptr = None
+        """Kept for API compatibility: release happens when the last array view is collected."""
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                lib().dnlp_host_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
 
 
 def make_tape_desc(tape):

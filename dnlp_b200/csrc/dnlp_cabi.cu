@@ -12,6 +12,7 @@
 #include <cstring>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 namespace {
@@ -68,6 +69,19 @@ struct dnlp_oracle {
   int64_t launches = 0;
   std::string err;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // CUDA graphs of the launch sequences actually encountered: key = (program, which of its cacheable
+  // instructions are already valid).  IPOPT's call order produces a handful of distinct sequences;
+  // replaying them as graphs removes the per-kernel launch gaps that dominate small problems.
+  struct GraphEntry {
+    cudaGraphExec_t exec = nullptr;
+    int64_t nlaunch = 0;
+    int prog = -1;                 // the exact sequence this graph replays (verified on every hit:
+    bool with_batch = false;       // a hash collision must never replay the wrong kernels)
+    std::vector<int32_t> plan;
+  };
+  std::unordered_map<uint64_t, GraphEntry> graphs;
+  bool graphs_enabled = true;
+  bool capturing = false;
   int32_t *dyn_pos[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   double *dyn_buf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int64_t dyn_len[6] = {0, 0, 0, 0, 0, 0};
@@ -279,26 +293,76 @@ int dnlp_oracle::build_batches() {
 }
 
 int dnlp_oracle::run_program(int p, bool force) {
+  // 1. which launches does this call need?  (depends only on the validity flags)
   ElemBatch &B = batch[p];
+  bool use_batch = false;
   if (!B.members.empty()) {
-    bool all_invalid = true;
+    use_batch = true;
     if (cache_enabled && !force)
-      for (int32_t id : B.members) if (valid[id]) { all_invalid = false; break; }
-    if (all_invalid) {
+      for (int32_t id : B.members) if (valid[id]) { use_batch = false; break; }
+  }
+  std::vector<int32_t> plan;
+  uint64_t key = 1469598103934665603ull;
+  key = (key ^ (uint64_t)(p + 1)) * 1099511628211ull;
+  key = (key ^ (uint64_t)(use_batch ? 2 : 1)) * 1099511628211ull;
+  std::vector<uint8_t> covered;
+  if (use_batch) { covered.assign(instrs.size(), 0); for (int32_t id : B.members) covered[id] = 1; }
+  for (int32_t id : prog[p]) {
+    DevInstr &I = instrs[id];
+    const bool cacheable = !I.d.uses_lam && I.d.dst_space == DNLP_DST_V;
+    if (use_batch && covered[id]) continue;
+    if (cacheable && valid[id] && !force) continue;
+    plan.push_back(id);
+    key = (key ^ (uint64_t)(id + 1)) * 1099511628211ull;
+  }
+  if (!use_batch && plan.empty()) return 0;
+
+  // 2. replay a captured graph, capture one, or launch directly
+  auto issue = [&]() -> int {
+    if (use_batch) {
       int64_t cap = (int64_t)sm_count * 8;
       int grid = (int)(B.total_tiles < cap ? B.total_tiles : cap);
       dnlp::elem_batch_kernel<<<grid, 256, 0, stream>>>(V, B.descs, B.ndesc, B.total_tiles);
       ++launches;
       cudaError_t e = cudaPeekAtLastError();
       if (e != cudaSuccess) { err = std::string("kernel launch failed: ") + cudaGetErrorString(e); return 1; }
-      for (int32_t id : B.members) valid[id] = 1;
     }
-  }
-  for (int32_t id : prog[p]) {
-    DevInstr &I = instrs[id];
-    const bool cacheable = !I.d.uses_lam && I.d.dst_space == DNLP_DST_V;
-    if (cacheable && valid[id] && !force) continue;
-    if (launch(I)) return 1;
+    for (int32_t id : plan) if (launch(instrs[id])) return 1;
+    return 0;
+  };
+  const int nl = (int)plan.size() + (use_batch ? 1 : 0);
+  if (graphs_enabled && !capturing && nl >= 2) {
+    auto it = graphs.find(key);
+    if (it != graphs.end()) {
+      const GraphEntry &ge = it->second;
+      if (ge.prog == p && ge.with_batch == use_batch && ge.plan == plan) {
+        CK(cudaGraphLaunch(ge.exec, stream));
+        launches += ge.nlaunch;
+      } else if (issue()) return 1;          // hash collision: launch directly
+    } else if (graphs.size() < 64) {
+      const int64_t before = launches;
+      capturing = true;
+      CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+      const int rc = issue();
+      cudaGraph_t g = nullptr;
+      cudaError_t ce = cudaStreamEndCapture(stream, &g);
+      capturing = false;
+      if (rc) { if (g) cudaGraphDestroy(g); return 1; }
+      if (ce != cudaSuccess) { err = std::string("graph capture failed: ") + cudaGetErrorString(ce); return 1; }
+      GraphEntry ge;
+      ge.prog = p; ge.with_batch = use_batch; ge.plan = plan;
+      ge.nlaunch = launches - before;
+      CK(cudaGraphInstantiate(&ge.exec, g, 0));
+      cudaGraphDestroy(g);
+      graphs.emplace(key, ge);
+      CK(cudaGraphLaunch(ge.exec, stream));
+    } else if (issue()) return 1;
+  } else if (issue()) return 1;
+
+  // 3. bookkeeping: x-only results stay valid until x changes
+  if (use_batch) for (int32_t id : B.members) valid[id] = 1;
+  for (int32_t id : plan) {
+    const DevInstr &I = instrs[id];
     if (!I.d.uses_lam && I.d.dst_space == DNLP_DST_V) valid[id] = 1;
   }
   return 0;
@@ -384,6 +448,7 @@ void dnlp_destroy(dnlp_oracle *o) {
   if (!o) return;
   cudaSetDevice(o->device);
   if (o->stream) cudaStreamSynchronize(o->stream);
+  for (auto &kv : o->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   for (void *p : o->owned) cudaFree(p);
   if (o->hx) cudaFreeHost(o->hx);
   if (o->hlam) cudaFreeHost(o->hlam);
@@ -604,17 +669,43 @@ int dnlp_upload_point(dnlp_oracle *o, const double *x, const double *lam, double
 
 int dnlp_run_device(dnlp_oracle *o, int32_t prog_mask, int32_t iters, float *elapsed_ms) {
   ENTER(o);
-  CK(cudaEventRecord(o->ev0, o->stream));
-  for (int it = 0; it < iters; ++it) {
+  // one step = every cache invalidated, then the requested programs; the whole step is captured
+  // once into a CUDA graph and replayed `iters` times
+  auto step = [&]() -> int {
     std::fill(o->valid.begin(), o->valid.end(), 0);   // a new point every step: nothing is reused
     for (int p = 0; p < DNLP_NPROG; ++p)
       if (prog_mask & (1 << p))
         if (o->run_program(p, false)) return 1;
+    return 0;
+  };
+  cudaGraphExec_t exec = nullptr;
+  int64_t per_step = 0;
+  if (iters <= 0) { if (elapsed_ms) *elapsed_ms = 0.f; return 0; }
+  if (o->graphs_enabled) {
+    const int64_t before = o->launches;
+    o->capturing = true;
+    CK(cudaStreamBeginCapture(o->stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = step();
+    cudaGraph_t g = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(o->stream, &g);
+    o->capturing = false;
+    if (rc) { if (g) cudaGraphDestroy(g); return 1; }
+    if (ce != cudaSuccess) { err = std::string("graph capture failed: ") + cudaGetErrorString(ce); return 1; }
+    per_step = o->launches - before;
+    o->launches = before;
+    CK(cudaGraphInstantiate(&exec, g, 0));
+    cudaGraphDestroy(g);
+  }
+  CK(cudaEventRecord(o->ev0, o->stream));
+  for (int it = 0; it < iters; ++it) {
+    if (exec) { CK(cudaGraphLaunch(exec, o->stream)); o->launches += per_step; }
+    else if (step()) return 1;
   }
   CK(cudaEventRecord(o->ev1, o->stream));
   CK(cudaEventSynchronize(o->ev1));
   float ms = 0.f;
   CK(cudaEventElapsedTime(&ms, o->ev0, o->ev1));
+  if (exec) cudaGraphExecDestroy(exec);
   if (elapsed_ms) *elapsed_ms = ms;
   return 0;
 }
@@ -627,15 +718,19 @@ int dnlp_profile_instrs(dnlp_oracle *o, int32_t p, int32_t iters, float *ms_per_
   for (int32_t id : o->prog[p])                      // untimed pass: lazy module load, caches
     if (o->launch(o->instrs[id])) return 1;
   CK(cudaStreamSynchronize(o->stream));
+  // each instruction: `reps` back-to-back launches between one event pair, so that the event and
+  // launch overhead (~2 us) does not distort the bandwidth of ~100 us kernels
+  const int reps = 3;
   for (int it = 0; it < iters; ++it) {
     for (int32_t id : o->prog[p]) {
       CK(cudaEventRecord(o->ev0, o->stream));
-      if (o->launch(o->instrs[id])) return 1;
+      for (int r = 0; r < reps; ++r)
+        if (o->launch(o->instrs[id])) return 1;
       CK(cudaEventRecord(o->ev1, o->stream));
       CK(cudaEventSynchronize(o->ev1));
       float ms = 0.f;
       CK(cudaEventElapsedTime(&ms, o->ev0, o->ev1));
-      ms_per_instr[id] += ms / (float)iters;
+      ms_per_instr[id] += ms / (float)(iters * reps);
     }
   }
   return 0;
@@ -654,6 +749,11 @@ int64_t dnlp_kernel_launches(dnlp_oracle *o) { return o->launches; }
 const char *dnlp_instr_kernel(dnlp_oracle *o, int32_t instr) {
   if (instr < 0 || (size_t)instr >= o->instrs.size()) return "";
   return o->instrs[instr].kname.c_str();
+}
+
+int dnlp_set_graphs(dnlp_oracle *o, int32_t enabled) {
+  o->graphs_enabled = enabled != 0;
+  return 0;
 }
 
 int dnlp_set_cache(dnlp_oracle *o, int32_t enabled) {

@@ -227,5 +227,8 @@ class GpuOracles:
     def kernel_launches(self):
         return int(self.dev._L.dnlp_kernel_launches(self.dev.h))
 
+    def set_graphs(self, enabled):
+        self.dev._L.dnlp_set_graphs(self.dev.h, int(bool(enabled)))
+
     def set_cache(self, enabled):
         self.dev._L.dnlp_set_cache(self.dev.h, int(bool(enabled)))

@@ -146,6 +146,7 @@ int dnlp_read_output(dnlp_oracle *o, int32_t dst_space, double *out);   /* D2H o
 int64_t dnlp_kernel_launches(dnlp_oracle *o);                           /* launches since create */
 const char *dnlp_instr_kernel(dnlp_oracle *o, int32_t instr);           /* kernel name of an executed instruction */
 int dnlp_set_cache(dnlp_oracle *o, int32_t enabled);                    /* x-keyed forward cache on/off */
+int dnlp_set_graphs(dnlp_oracle *o, int32_t enabled);                   /* CUDA-graph replay of launch sequences on/off */
 
 /* ---- batched multi-start evaluation (BASELINE config 4; the reference's serial `best_of` loop,
  *      cvxpy/problems/problem.py:1249-1275, evaluates one start at a time) ----

@@ -285,3 +285,25 @@ def test_gpu_atom_rules(name, gpu_mod):
                 assert_close(o.hessian(p["x"], p["lam"], float(p["sigma"])), p["hess"], "hess")
     finally:
         o.close()
+
+
+@pytest.mark.parametrize("graphs", [True, False])
+def test_gpu_graph_replay_on_and_off(graphs, gpu_mod):
+    """Launch sequences are replayed as CUDA graphs by default; results must not depend on it, and the
+    IPOPT call pattern (five callbacks per iterate, many iterates) must hit the replay path."""
+    g = Golden("clnlbeam")
+    o = gpu_mod(g.problem)
+    o.set_graphs(graphs)
+    try:
+        for rep in range(3):
+            for i, p in enumerate(g.points):
+                assert_close(o.objective(p["x"]), p["f"], "f")
+                assert_close(o.gradient(p["x"]), p["grad"], "grad")
+                assert_close(o.constraints(p["x"]), p["g"], "g")
+                assert_close(o.jacobian(p["x"]), p["jac"], "jac")
+                assert_close(o.hessian(p["x"], p["lam"], float(p["sigma"])), p["hess"], "hess")
+        ms = o.run_device(iters=3)
+        assert ms > 0
+        assert_close(o.read_output("hess"), g.points[-1]["hess"], "hess after run_device")
+    finally:
+        o.close()
