@@ -177,7 +177,7 @@ int dnlp_oracle::launch(DevInstr &I) {
     case DNLP_POLY: {
       if (d.count == 1 && d.nterms >= 2048 && !d.pos) {
         // one long row: grid-wide deterministic reduction in a single launch
-        int64_t blocks = (d.nterms + 256 * 16 - 1) / (256 * 16);
+        int64_t blocks = (d.nterms + 256 * 4 - 1) / (256 * 4);     // one 4-term batch per thread until the grid is full
         int64_t cap = (int64_t)sm_count * 4;
         int grid = (int)(blocks < cap ? blocks : cap);
         if (I.has_f2)
