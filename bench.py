@@ -187,12 +187,24 @@ def cpu_port_c4(budget_s=10.0):
 def bench_sharded(args, rank, local_rank, world, dist, metric):
     """C3 with rows of A~ block-distributed over the ranks; one packed all-reduce per callback."""
     from dnlp_b200 import workloads as W
-    from dnlp_b200.sharded import GlobalStructure, RowShardedOracles, shard_logistic_regression
-    m, n = max(64, int(2_000_000 * args.scale)), max(16, int(4096 * (args.scale ** 0.5)))
-    At, x_init = W.logistic_data(m, n, 16)
-    glob = W.logistic_regression(At, x_init)
+    from dnlp_b200.sharded import (GlobalStructure, RowShardedOracles, shard_logistic_regression,
+                                   shard_microbench)
+    if args.workload == "c3s":
+        m, n = max(64, int(2_000_000 * args.scale)), max(16, int(4096 * (args.scale ** 0.5)))
+        At, x_init = W.logistic_data(m, n, 16)
+        glob = W.logistic_regression(At, x_init)
+        local, layout = shard_logistic_regression(At, x_init, rank, world)
+        wl = ("c3 row-sharded: sparse logistic-type regression m=%d n=%d, 16 nnz/row, rows of A block-distributed, "
+              "lifted variables sharded, x replicated" % (m, n))
+    else:
+        N = max(64, int(10_000_000 * args.scale) // 8 * 8)
+        m = max(8, N // 2)
+        A5, x5 = W.microbench_data(N, m, 10)
+        glob = W.microbench(A5, x5)
+        local, layout = shard_microbench(A5, x5, rank, world)
+        wl = ("c5 row-sharded: %d-node elementwise DAG + %d-nnz CSR Jacobian, constraint rows block-distributed, "
+              "all variables replicated, Hessian contributions all-reduced (%d doubles)" % (N, A5.nnz, N))
     gs = GlobalStructure.from_problem(glob)
-    local, layout = shard_logistic_regression(At, x_init, rank, world)
     comm = None
     if dist is None:
         class _Solo:
@@ -201,7 +213,7 @@ def bench_sharded(args, rank, local_rank, world, dist, metric):
             def allreduce(self, v):
                 return v
         comm = _Solo()
-    o = RowShardedOracles(local, layout, gs, comm=comm, device=local_rank)
+    o = RowShardedOracles(local, layout, gs, comm=comm, device=local_rank, root_only=True)
     rng = np.random.default_rng(3)
     x = glob.x0 * (1 + 0.01 * rng.standard_normal(glob.n))
     lam, sigma = rng.standard_normal(glob.m), 1.0
@@ -238,9 +250,8 @@ def bench_sharded(args, rank, local_rank, world, dist, metric):
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
-                "config": {"workload": "c3 row-sharded: sparse logistic-type regression m=%d n=%d, 16 nnz/row, rows of A "
-                           "block-distributed, one packed all-reduce per callback" % (m, n),
-                           "parallelism": "row-sharded x%d" % world,
+                "config": {"workload": wl, "parallelism": "row-sharded x%d, NCCL all-reduce + all-gather, device-side "
+                           "assembly, outputs delivered to rank 0" % world,
                            "value_is": "max over ranks of the local tapes' CUDA-event time (collective excluded)"},
                 "e2e": {"value": args.steps / (e2e_ms * 1e-3), "unit": "evals/s",
                         "api": "RowShardedOracles five callbacks, host buffers, all-reduce inside",
@@ -407,7 +418,7 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
 
-    if args.workload == "c3s":
+    if args.workload in ("c3s", "c5s"):
         return bench_sharded(args, rank, local_rank, world, dist, metric)
     if args.workload == "c4":
         return bench_multistart(args, rank, local_rank, world, dist, metric, hbm_peak, peak_src)

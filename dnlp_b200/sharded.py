@@ -178,6 +178,9 @@ class _DeviceAssembler:
             dist.all_reduce(sh)
             full[p["shared_slots"]] = sh
         out = o._out[name]
+        if o.root_only and dist.get_rank() != 0:
+            torch.cuda.current_stream().synchronize()
+            return out
         if p["dense"]:
             p["out_dev"][p["dyn_pos"]] = full[:p["nd"]]
             p["host"].copy_(p["out_dev"])
@@ -189,7 +192,11 @@ class _DeviceAssembler:
 class RowShardedOracles:
     """Same seven callbacks as ``GpuOracles``; every call is collective over the group."""
 
-    def __init__(self, local_problem, layout, global_structure, comm=None, oracle_factory=None, device=0):
+    def __init__(self, local_problem, layout, global_structure, comm=None, oracle_factory=None, device=0,
+                 root_only=False):
+        """``root_only``: only rank 0 (where the solver runs) copies assembled outputs to the host;
+        the other ranks still take part in every collective but return their arrays un-refreshed."""
+        self.root_only = root_only
         if oracle_factory is None:
             from .oracles import GpuOracles
             oracle_factory = lambda p: GpuOracles(p, device=device)  # noqa: E731
@@ -356,3 +363,40 @@ def shard_logistic_regression(At, x_init, rank, world):
         x0 = np.concatenate([A_loc @ x_init, x_init])
         prob = ir.ProblemIR(data_obj, [c1], variables, x0=x0)
     return prob, ShardLayout(m + 3 * n, m + 2 * n, var_map, con_map)
+
+
+# ------------------------------------------------------------------------------------------------
+# shard builder for the C5 microbenchmark (dnlp_b200.workloads.microbench)
+# ------------------------------------------------------------------------------------------------
+def shard_microbench(A, x0, rank, world, ops=None):
+    """Rows [r0, r1) of the constraint matrix go to rank ``rank``; every variable is replicated.
+
+    g and J are row-owned (disjoint), while every rank contributes ``A_r' lambda_r`` to the diagonal
+    Hessian of the replicated variables: the all-reduce of Hessian contributions the north star
+    names (N doubles per evaluation).  The objective lives on rank 0."""
+    import scipy.sparse as sp
+
+    from . import ir
+    from .ir import Node
+    from .workloads import C5_OPS, _add, _c, _pow, _sum
+    ops = C5_OPS if ops is None else ops
+    m, N = A.shape
+    S = len(ops)
+    seg = N // S
+    r0, r1 = (m * rank) // world, (m * (rank + 1)) // world
+    mr = r1 - r0
+    A_loc = sp.csc_array(sp.csr_array(A)[r0:r1])
+    xs = [ir.Variable(seg) for _ in ops]
+
+    def phi(op, v):
+        return _pow(v, op[1]) if isinstance(op, tuple) else Node(op, [v], v.shape)
+    terms = [Node("matmul", [_c(sp.csr_array(A_loc[:, s * seg:(s + 1) * seg])), phi(op, v)], (mr,))
+             for s, (op, v) in enumerate(zip(ops, xs))]
+    con = _add(terms + [_c(-np.zeros(mr))], (mr,))
+    if rank == 0:
+        obj = _add([_sum(phi(op, v)) for op, v in zip(ops, xs)], ())
+    else:
+        obj = _c(0.0)
+    # the variable order of the local problem must be the global one even when the objective is absent
+    prob = ir.ProblemIR(obj, [con], xs, x0=np.asarray(x0, dtype=np.float64))
+    return prob, ShardLayout(N, m, np.arange(N), np.arange(r0, r1))
