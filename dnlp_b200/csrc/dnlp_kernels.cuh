@@ -120,6 +120,9 @@ elem_kernel(double *__restrict__ V, int64_t a_off, int a_stride, int64_t b_off, 
 }
 
 // ---- K2/K3/K4/K5: POLY - segmented sums of coef * V[f1] * V[f2] --------------------------
+// (poly_kernel / poly1_kernel / gemv_kernel / scale_kernel below are the first-cut versions; the
+//  library now launches the tuned variants further down and keeps these as the measured baselines
+//  of tools/kbench and as the general fallbacks for odd shapes.)
 // One kernel covers CSR SpMV (A@x, A^T lambda on the CSC copy), Jacobian value fill
 // (one term per row), and the Hessian fill (w[j] * phi''(x_j) : two factors).
 // G lanes cooperate on one row (G = 1 thread-per-row ... 32 warp-per-row), chosen on the host

@@ -181,13 +181,6 @@ def as_node(x):
     return x if isinstance(x, Node) else Constant(x)
 
 
-def const_value(node):
-    """Numeric value of a constant subtree (constants are folded eagerly)."""
-    if node.op != "const":
-        raise ValueError("not a folded constant: %r" % node)
-    return node.attrs["value"]
-
-
 # --------------------------------------------------------------------------
 # affine atoms
 # --------------------------------------------------------------------------

@@ -219,14 +219,10 @@ class Builder:
         def simple(sv):
             return bool(np.all(sv.term_counts() <= 1)) and (sv.nterms == 0 or int(sv.arity().max()) <= 1)
         if not simple(a):
-            a = self._materialise_entries(a)
+            a = self.materialise(a)
         if not a.can_multiply_directly(b) and not simple(b):
-            b = self._materialise_entries(b)
+            b = self.materialise(b)
         return a.mul_simple(b)
-
-    def _materialise_entries(self, sv):
-        """Materialise only the distinct non-trivial entries when the vector is a gather of few."""
-        return self.materialise(sv)
 
     # ---- variables -----------------------------------------------------------
     def var_slots(self, v):
@@ -484,7 +480,7 @@ class Builder:
         grp = np.cumsum(new) - 1
         return r[new], c[new], sv.gather(order).group_sum(grp, int(grp[-1]) + 1)
 
-    def _merge_dicts(self, parts, shape_of):
+    def _merge_dicts(self, parts):
         """Shared body of AddExpression._jacobian / _hess_vec (affine/add_expr.py:149-222)."""
         out, need = {}, set()
         for d in parts:
@@ -500,7 +496,7 @@ class Builder:
         return out
 
     def _jac_add(self, node):                              # affine/add_expr.py:190-222
-        return self._merge_dicts([self.jac(a) for a in node.args if not a.is_constant()], None)
+        return self._merge_dicts([self.jac(a) for a in node.args if not a.is_constant()])
 
     def _jac_neg(self, node):                              # affine/unary_operators.py:129-136
         return {k: (r, c, v.neg()) for k, (r, c, v) in self.jac(node.args[0]).items()}
@@ -766,7 +762,7 @@ class Builder:
         return getattr(self, "_hv_" + (node.op if node.op not in T.UNARY_TABLE else "unary"))(node, vec)
 
     def _hv_add(self, node, vec):                          # affine/add_expr.py:149-184
-        return self._merge_dicts([self.hv(a, vec) for a in node.args if not a.is_affine()], None)
+        return self._merge_dicts([self.hv(a, vec) for a in node.args if not a.is_affine()])
 
     def _hv_neg(self, node, vec):                          # affine/unary_operators.py:122-124
         return self.hv(node.args[0], vec.neg())

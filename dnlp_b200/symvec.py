@@ -131,9 +131,6 @@ class SymVec:
             return int(s[0])
         return None
 
-    def single_term_mask(self):
-        return self.term_counts() == 1
-
     # ---- linear operations --------------------------------------------------
     def neg(self):
         return SymVec(self.K, self.row, -self.coef, self.f1, self.f2)
