@@ -307,3 +307,40 @@ def test_gpu_graph_replay_on_and_off(graphs, gpu_mod):
         assert_close(o.read_output("hess"), g.points[-1]["hess"], "hess after run_device")
     finally:
         o.close()
+
+
+def test_gpu_cabi_error_paths():
+    """Errors come back as return codes + dnlp_last_error text, never as crashes."""
+    import ctypes as C
+    from dnlp_b200 import _cabi
+    from dnlp_b200.compiler import compile_problem
+    L = _cabi.lib()
+    g = Golden("hs071")
+    tape = compile_problem(g.problem)
+    td, keep = _cabi.make_tape_desc(tape)
+    bad = np.array([0, 10 ** 6], dtype=np.int32)            # a program that references a missing instruction
+    td.prog[0] = bad.ctypes.data_as(_cabi.c_i32p)
+    td.prog_len[0] = 2
+    h = C.c_void_p()
+    assert L.dnlp_create(C.byref(td), 0, C.byref(h)) != 0
+    assert b"unknown instruction" in L.dnlp_last_error(None)
+    assert not h.value
+    with pytest.raises(RuntimeError):
+        _cabi.DeviceTape(tape, device=10 ** 4)                # no such device
+    dev = _cabi.DeviceTape(tape)
+    pos = np.array([10 ** 6], dtype=np.int32)
+    assert L.dnlp_set_dynamic(dev.h, 4, pos.ctypes.data_as(_cabi.c_i32p), 1) != 0
+    assert b"out of range" in L.dnlp_last_error(dev.h)
+    assert L.dnlp_eval_dyn(dev.h, 0, None, None, 1.0, None) != 0     # program id without a dynamic form
+    dev.close()
+    from dnlp_b200.multistart import BatchedOracles
+    with pytest.raises(RuntimeError):
+        BatchedOracles(g.problem, 0)
+    o = BatchedOracles(g.problem, 4)
+    try:
+        with pytest.raises(ValueError):
+            o.eval(np.zeros((3, g.problem.n)))
+        with pytest.raises(ValueError):
+            o.eval(np.zeros((4, g.problem.n)), want=("hess",))
+    finally:
+        o.close()

@@ -1,0 +1,80 @@
+"""Unit tests of the symbolic value algebra (host logic of the DAG compiler)."""
+import numpy as np
+
+from dnlp_b200.symvec import NONE, SymVec
+
+
+def ev(sv, V):
+    """Reference evaluation of a SymVec against a value buffer."""
+    t = sv.coef.copy()
+    m1 = sv.f1 != NONE
+    t[m1] *= V[sv.f1[m1]]
+    m2 = sv.f2 != NONE
+    t[m2] *= V[sv.f2[m2]]
+    out = np.zeros(sv.K)
+    np.add.at(out, sv.row, t)
+    return out
+
+
+def test_constructors_and_predicates():
+    V = np.arange(10.0) + 1
+    c = SymVec.const([1.0, 0.0, -2.0])
+    s = SymVec.slot_range(3, 4)
+    assert c.is_const_mask().all() and not s.is_const_mask().any()
+    np.testing.assert_array_equal(c.const_values(), [1.0, 0.0, -2.0])
+    np.testing.assert_array_equal(ev(s, V), V[3:7])
+    assert s.contiguous_start() == 3 and SymVec.slots([5, 2]).contiguous_start() is None
+    assert s.is_unit() and c.is_unit()
+    assert SymVec.zeros(3).K == 3 and SymVec.zeros(3).nterms == 0
+
+
+def test_linear_ops_match_numpy():
+    rng = np.random.default_rng(0)
+    V = rng.standard_normal(12)
+    a = SymVec.slots([0, 3, 5, 7]).scale([2.0, -1.0, 0.5, 3.0])
+    b = SymVec.const([1.0, 2.0, 3.0, 4.0])
+    np.testing.assert_allclose(ev(a.add(b), V), ev(a, V) + ev(b, V))
+    np.testing.assert_allclose(ev(a.neg(), V), -ev(a, V))
+    idx = np.array([3, 3, 0, 1])
+    np.testing.assert_allclose(ev(a.gather(idx), V), ev(a, V)[idx])
+    grp = np.array([1, 0, 1, 1])
+    np.testing.assert_allclose(ev(a.group_sum(grp, 2), V), np.bincount(grp, weights=ev(a, V), minlength=2))
+    np.testing.assert_allclose(ev(a.sum_all(), V), [ev(a, V).sum()])
+    sc = a.scatter_into(6, [5, 0, 2, 3])
+    want = np.zeros(6)
+    want[[5, 0, 2, 3]] = ev(a, V)
+    np.testing.assert_allclose(ev(sc, V), want)
+    cat = SymVec.concat([a, b])
+    np.testing.assert_allclose(ev(cat, V), np.concatenate([ev(a, V), ev(b, V)]))
+    M = rng.standard_normal((3, 4))
+    r, c = np.nonzero(M)
+    np.testing.assert_allclose(ev(a.linear_map(r, c, M[r, c], 3), V), M @ ev(a, V))
+
+
+def test_gather_of_multi_term_entries():
+    V = np.arange(8.0) + 1
+    a = SymVec.slots([0, 1, 2]).add(SymVec.slots([3, 4, 5])).add(SymVec.const([1, 1, 1]))   # 3 terms per entry
+    assert not a.is_unit() and (a.term_counts() == 3).all()
+    np.testing.assert_allclose(ev(a.gather([2, 0, 2]), V), ev(a, V)[[2, 0, 2]])
+
+
+def test_products():
+    V = np.arange(8.0) + 1
+    a = SymVec.slots([0, 1, 2]).scale([2, 3, 4])
+    b = SymVec.slots([5, 6, 7])
+    assert a.can_multiply_directly(b)
+    np.testing.assert_allclose(ev(a.mul_simple(b), V), ev(a, V) * ev(b, V))
+    c = SymVec.const([2.0, 0.5, -1.0])
+    np.testing.assert_allclose(ev(a.mul_simple(b).mul_simple(c), V), ev(a, V) * ev(b, V) * ev(c, V))
+    assert not a.mul_simple(b).can_multiply_directly(b)          # would need three factors
+    assert not a.add(b).can_multiply_directly(b)                 # two terms per entry
+
+
+def test_simplify_merges_like_terms_and_drops_zeros():
+    V = np.arange(6.0) + 1
+    a = SymVec.slots([0, 1]).add(SymVec.slots([0, 1]).scale([2.0, -1.0])).add(SymVec.const([0.0, 5.0]))
+    s = a.simplify()
+    np.testing.assert_allclose(ev(s, V), ev(a, V))
+    assert s.nterms == 2                   # entry 0: 3*V0 ; entry 1: 0*V1 dropped, const 5 kept
+    z = SymVec.slots([2, 3]).add(SymVec.const([0.0, 0.0])).drop_zero_constants()
+    assert z.nterms == 2 and z.is_unit()
