@@ -1,0 +1,94 @@
+"""Full-size checks through size-independent properties (the CPU oracle cannot run these sizes in
+seconds): derivative consistency by central differences along random directions - the check IPOPT's
+own `derivative_test` option performs and to which the reference's test-suite delegates derivative
+correctness - plus linearity of the Hessian of the Lagrangian in (sigma, lambda) and agreement of the
+fused eval_all with the individual callbacks.  Sizes are BASELINE.json's (C2 full, C3/C5 scaled to
+keep the GPU suite short; set DNLP_FULLSIZE=1 for the full C3/C5)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+FULL = os.environ.get("DNLP_FULLSIZE") == "1"
+
+
+def _spmv(rows, cols, vals, d, nrows):
+    return np.bincount(rows, weights=vals * d[cols], minlength=nrows)
+
+
+def _check_derivatives(prob, seed=0, h_scale=1e-6, rtol=2e-6):
+    from dnlp_b200.oracles import GpuOracles
+    o = GpuOracles(prob)
+    try:
+        rng = np.random.default_rng(seed)
+        n, m = prob.n, prob.m
+        x = np.asarray(prob.x0, dtype=np.float64) * (1 + 0.01 * rng.standard_normal(n))
+        d = rng.standard_normal(n)
+        d /= np.linalg.norm(d)
+        h = h_scale * max(1.0, np.linalg.norm(x) / np.sqrt(n))
+        lam = rng.standard_normal(m)
+        sigma = 0.7
+        jr, jc = o.jacobianstructure()
+        hr, hc = o.hessianstructure()
+
+        def grad_lagrangian(z):
+            gL = sigma * np.array(o.gradient(z), dtype=np.float64)
+            if m:
+                jv = np.array(o.jacobian(z), dtype=np.float64)
+                gL = gL + np.bincount(jc, weights=jv * lam[jr], minlength=n)
+            return gL
+
+        f0 = float(o.objective(x))
+        grad = np.array(o.gradient(x), dtype=np.float64)
+        g0 = np.array(o.constraints(x), dtype=np.float64) if m else np.zeros(0)
+        jac = np.array(o.jacobian(x), dtype=np.float64)
+        hess = np.array(o.hessian(x, lam, sigma), dtype=np.float64)
+        assert np.isfinite(f0) and np.isfinite(grad).all() and np.isfinite(jac).all() and np.isfinite(hess).all()
+        xp, xm = x + h * d, x - h * d
+
+        def close(a, b, what):
+            scale = max(np.linalg.norm(a), np.linalg.norm(b), 1e-300)
+            err = np.linalg.norm(a - b) / scale
+            assert err < rtol, "%s: relative error %.3e" % (what, err)
+
+        close(np.array([(float(o.objective(xp)) - float(o.objective(xm))) / (2 * h)]), np.array([grad @ d]), "df")
+        if m:
+            gp, gm = np.array(o.constraints(xp), dtype=np.float64), np.array(o.constraints(xm), dtype=np.float64)
+            close((gp - gm) / (2 * h), _spmv(jr, jc, jac, d, m), "J d")
+        Hd = _spmv(hr, hc, hess, d, n)
+        off = hr != hc
+        Hd += np.bincount(hc[off], weights=hess[off] * d[hr[off]], minlength=n)     # the upper triangle
+        close((grad_lagrangian(xp) - grad_lagrangian(xm)) / (2 * h), Hd, "H d")
+        # linearity in the multipliers, sigma = 0 path (Knitro's EVALH_NO_F)
+        lam2 = rng.standard_normal(m)
+        h1 = hess.copy()
+        h2 = np.array(o.hessian(x, lam2, 0.0), dtype=np.float64).copy()
+        h12 = np.array(o.hessian(x, lam + lam2, sigma), dtype=np.float64)
+        np.testing.assert_allclose(h12, h1 + h2, rtol=1e-9, atol=1e-9 * max(1.0, np.abs(h12).max()))
+        # fused evaluation equals the five callbacks
+        res = o.eval_all(x, lam, sigma)
+        np.testing.assert_allclose(np.array(res["hess"]), hess, rtol=1e-12, atol=0)
+        np.testing.assert_allclose(np.array(res["jac"]), jac, rtol=1e-12, atol=0)
+        assert float(res["f"]) == f0
+    finally:
+        o.close()
+
+
+def test_c2_full_size_eigen_qcqp():
+    from dnlp_b200 import workloads as W
+    _check_derivatives(W.eigen_qcqp(8192))
+
+
+def test_c3_logistic_regression():
+    from dnlp_b200 import workloads as W
+    m, n = (2_000_000, 4096) if FULL else (400_000, 1024)
+    At, x0 = W.logistic_data(m, n, 16)
+    _check_derivatives(W.logistic_regression(At, x0), rtol=2e-5)
+
+
+def test_c5_microbench():
+    from dnlp_b200 import workloads as W
+    N = 10_000_000 if FULL else 800_000
+    A, x0 = W.microbench_data(N, N // 2, 10)
+    _check_derivatives(W.microbench(A, x0), rtol=2e-5)
