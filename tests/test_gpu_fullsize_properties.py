@@ -52,7 +52,12 @@ def _check_derivatives(prob, seed=0, h_scale=1e-6, rtol=2e-6):
             err = np.linalg.norm(a - b) / scale
             assert err < rtol, "%s: relative error %.3e" % (what, err)
 
-        close(np.array([(float(o.objective(xp)) - float(o.objective(xm))) / (2 * h)]), np.array([grad @ d]), "df")
+        # the objective is a sum of up to millions of terms: use a larger step so that the difference
+        # stays above the fp64 cancellation noise (|f| * 1e-16 / h)
+        hf = 100 * h
+        fd = (float(o.objective(x + hf * d)) - float(o.objective(x - hf * d))) / (2 * hf)
+        assert abs(fd - grad @ d) <= 10 * rtol * max(abs(fd), abs(grad @ d), abs(f0) * 1e-16 / hf * 1e3, 1e-300), \
+            "df: %r vs %r" % (fd, grad @ d)
         if m:
             gp, gm = np.array(o.constraints(xp), dtype=np.float64), np.array(o.constraints(xm), dtype=np.float64)
             close((gp - gm) / (2 * h), _spmv(jr, jc, jac, d, m), "J d")
