@@ -25,6 +25,8 @@ thread_local std::string g_batch_create_error;
 struct BInstr {
   dnlp_instr_desc d;
   bool has_f2 = false;
+  int gemm_group = -1;               // index into dnlp_batch::groups when this GEMV runs in a grouped launch
+  dnlp::GemmDesc *one_desc = nullptr;   // device descriptor for launching this GEMV on its own
   int32_t *smallk_slots = nullptr;   // device: the K slots every row combines (tall-skinny GEMM path)
 };
 }  // namespace
@@ -41,6 +43,9 @@ struct dnlp_batch {
   double *stage = nullptr;               // staging for layout changes (max(len) x B)
   int64_t stage_len = 0;
   std::vector<BInstr> instrs;
+  // independent dense maps of identical shape (the k+1 quad forms of a QCQP) launched as one grid
+  struct GemmGroup { std::vector<int32_t> members; dnlp::GemmDesc *descs = nullptr; int64_t M = 0, K = 0; };
+  std::vector<GemmGroup> groups;
   std::vector<int32_t> prog[DNLP_NPROG];
   std::vector<void *> owned;
   int64_t launches = 0;
@@ -141,10 +146,10 @@ int dnlp_batch::launch(const BInstr &I) {
       break;
     }
     case DNLP_GEMV: {
+      // (a GEMV that belongs to a group never reaches here: run_union launches the group once)
       const int tiles = (int)(((d.count + GM - 1) / GM) * ((B + GN - 1) / GN));
       const int cap = sm_count * 4;
-      bgemm_dmma_kernel<<<tiles < cap ? tiles : cap, 128, 0, stream>>>(d.Q, V + d.x_off * B, dst, (int)d.count, B,
-                                                                      (int)d.ncols, d.alpha);
+      bgemm_dmma_kernel<<<tiles < cap ? tiles : cap, 128, BGEMM_SMEM, stream>>>(I.one_desc, 1, (int)d.count, B, (int)d.ncols);
       break;
     }
     case DNLP_SCALE:
@@ -171,8 +176,26 @@ int dnlp_batch::run_union(int32_t prog_mask) {
   for (int p = 0; p < DNLP_NPROG; ++p)
     if (prog_mask & (1 << p))
       for (int32_t id : prog[p]) need[id] = 1;
-  for (size_t id = 0; id < instrs.size(); ++id)       // ids are in topological order
-    if (need[id] && launch(instrs[id])) return 1;
+  std::vector<uint8_t> group_done(groups.size(), 0);
+  for (size_t id = 0; id < instrs.size(); ++id) {     // ids are in topological order
+    if (!need[id]) continue;
+    const int gi = instrs[id].gemm_group;
+    if (gi >= 0) {
+      if (group_done[gi]) continue;
+      // all members read only x: running the not-needed ones as well is harmless and keeps one launch
+      GemmGroup &G = groups[gi];
+      const int64_t tiles = ((G.M + GM - 1) / GM) * ((B + GN - 1) / GN) * (int64_t)G.members.size();
+      const int64_t cap = (int64_t)sm_count * 4;
+      bgemm_dmma_kernel<<<(int)(tiles < cap ? tiles : cap), 128, BGEMM_SMEM, stream>>>(
+          G.descs, (int)G.members.size(), (int)G.M, B, (int)G.K);
+      ++launches;
+      cudaError_t e = cudaPeekAtLastError();
+      if (e != cudaSuccess) { err = std::string("kernel launch failed: ") + cudaGetErrorString(e); return 1; }
+      group_done[gi] = 1;
+      continue;
+    }
+    if (launch(instrs[id])) return 1;
+  }
   return 0;
 }
 
@@ -270,7 +293,35 @@ static int batch_create_impl(dnlp_batch *o, const dnlp_tape_desc *t) {
     }
   }
   for (int q = 0; q < DNLP_NPROG; ++q) o->prog[q].assign(t->prog[q], t->prog[q] + t->prog_len[q]);
+  // group the dense maps that depend on x only and share a shape
+  for (int i = 0; i < t->n_instr; ++i) {
+    const dnlp_instr_desc &d = o->instrs[i].d;
+    if (d.kind != DNLP_GEMV) continue;
+    {
+      double *dst = (d.dst_space == DNLP_DST_V) ? o->V + d.dst_off * B : o->out[d.dst_space] + d.dst_off * B;
+      dnlp::GemmDesc one{d.Q, o->V + d.x_off * B, dst, d.alpha};
+      if (o->upload(&one, 1, &o->instrs[i].one_desc)) return 1;
+    }
+    if (d.level != 0 || d.dst_space != DNLP_DST_V) continue;
+    int gi = -1;
+    for (size_t g = 0; g < o->groups.size(); ++g)
+      if (o->groups[g].M == d.count && o->groups[g].K == d.ncols) { gi = (int)g; break; }
+    if (gi < 0) { o->groups.emplace_back(); gi = (int)o->groups.size() - 1; o->groups[gi].M = d.count; o->groups[gi].K = d.ncols; }
+    o->groups[gi].members.push_back(i);
+  }
+  for (size_t g = 0; g < o->groups.size(); ++g) {
+    auto &G = o->groups[g];
+    if (G.members.size() < 2) continue;                 // a lone map keeps the plain path
+    std::vector<dnlp::GemmDesc> hd;
+    for (int32_t id : G.members) {
+      const dnlp_instr_desc &d = o->instrs[id].d;
+      hd.push_back(dnlp::GemmDesc{d.Q, o->V + d.x_off * B, o->V + d.dst_off * B, d.alpha});
+      o->instrs[id].gemm_group = (int)g;
+    }
+    if (o->upload(hd.data(), (int64_t)hd.size(), &G.descs)) return 1;
+  }
   if (o->reset_outputs()) return 1;
+  CKB(cudaFuncSetAttribute(dnlp::bgemm_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dnlp::BGEMM_SMEM));
   CKB(cudaStreamSynchronize(o->stream));
   return 0;
 }

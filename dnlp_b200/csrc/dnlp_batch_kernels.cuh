@@ -239,19 +239,44 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
+constexpr int GSTAGES = 3;
+constexpr int GA_LD = GK + 4;      // row strides = 4 (mod 16) doubles: conflict-free fragment reads
+constexpr int GB_LD = GN + 4;
+constexpr size_t BGEMM_SMEM = (size_t)GSTAGES * (GM * GA_LD + GK * GB_LD) * sizeof(double);   // 56 832 B
+
+// Three cp.async stages, ONE __syncthreads per k-step: the stage refilled in step ks is the one every
+// warp finished reading in step ks-1 (they all passed the barrier at the top of step ks).
+// One problem of a grouped launch: Y = alpha * Q X, all groups share (M, N, K).
+struct GemmDesc {
+  const double *Q;
+  const double *X;
+  double *Y;
+  double alpha;
+};
+
+// Grouped launch: the k+1 independent quad_form maps of a QCQP (9 x [512x512]x[512x4096]) fill the
+// machine as one grid of 4608 tiles instead of nine grids of 512 (512 tiles on 592 CTA slots waste
+// 14 % of the tensor pipe to quantisation).
 static __global__ void __launch_bounds__(128)
-bgemm_dmma_kernel(const double *__restrict__ Q, const double *__restrict__ X, double *__restrict__ Y,
-                  int M, int N, int K, double alpha) {
-  __shared__ __align__(16) double As[2][GM][GK + 4];     // row stride = 4 (mod 16) doubles: conflict-free fragment reads
-  __shared__ __align__(16) double Bs[2][GK][GN + 4];
+bgemm_dmma_kernel(const GemmDesc *__restrict__ descs, int ngroups, int M, int N, int K) {
+  extern __shared__ __align__(16) double gsm[];
+  double (*As)[GM][GA_LD] = reinterpret_cast<double (*)[GM][GA_LD]>(gsm);
+  double (*Bs)[GK][GB_LD] = reinterpret_cast<double (*)[GK][GB_LD]>(gsm + GSTAGES * GM * GA_LD);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
   const int g = lane >> 2, tg = lane & 3;
   const int tiles_n = (N + GN - 1) / GN, tiles_m = (M + GM - 1) / GM;
-  // 16-byte asynchronous copies need even leading dimensions and 16-byte aligned bases
-  const bool aligned = (K & 1) == 0 && (N & 1) == 0 &&
-                       ((reinterpret_cast<uintptr_t>(Q) | reinterpret_cast<uintptr_t>(X)) & 15) == 0;
-  for (int tile = blockIdx.x; tile < tiles_m * tiles_n; tile += gridDim.x) {
+  const int tiles_per = tiles_m * tiles_n;
+  for (int gt = blockIdx.x; gt < tiles_per * ngroups; gt += gridDim.x) {
+    const GemmDesc d = descs[gt / tiles_per];
+    const int tile = gt % tiles_per;
+    const double *__restrict__ Q = d.Q;
+    const double *__restrict__ X = d.X;
+    double *__restrict__ Y = d.Y;
+    const double alpha = d.alpha;
+    // 16-byte asynchronous copies need even leading dimensions and 16-byte aligned bases
+    const bool aligned = (K & 1) == 0 && (N & 1) == 0 &&
+                         ((reinterpret_cast<uintptr_t>(Q) | reinterpret_cast<uintptr_t>(X)) & 15) == 0;
     const int m0 = (tile / tiles_n) * GM, n0 = (tile % tiles_n) * GN;
     double acc[4][4][2];
 #pragma unroll
@@ -279,15 +304,20 @@ bgemm_dmma_kernel(const double *__restrict__ Q, const double *__restrict__ X, do
           Bs[buf][r][c + 1] = (gk < K && gn + 1 < N) ? X[(int64_t)gk * N + gn + 1] : 0.0;
         }
       }
-      cp_async_commit();
     };
     const int ksteps = (K + GK - 1) / GK;
-    load_tiles(0, 0);
+    __syncthreads();                                    // previous tile's reads are done
+#pragma unroll
+    for (int s = 0; s < GSTAGES - 1; ++s) {
+      if (s < ksteps) load_tiles(s, s * GK);
+      cp_async_commit();
+    }
     for (int ks = 0; ks < ksteps; ++ks) {
-      const int buf = ks & 1;
-      if (ks + 1 < ksteps) { load_tiles(buf ^ 1, (ks + 1) * GK); cp_async_wait<1>(); }
-      else cp_async_wait<0>();
+      cp_async_wait<GSTAGES - 2>();                     // stage ks has landed
       __syncthreads();
+      if (ks + GSTAGES - 1 < ksteps) load_tiles((ks + GSTAGES - 1) % GSTAGES, (ks + GSTAGES - 1) * GK);
+      cp_async_commit();
+      const int buf = ks % GSTAGES;
 #pragma unroll
       for (int kk = 0; kk < GK; kk += 4) {
         double a[4], b[4];
@@ -300,8 +330,8 @@ bgemm_dmma_kernel(const double *__restrict__ Q, const double *__restrict__ X, do
 #pragma unroll
           for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
       }
-      __syncthreads();
     }
+    cp_async_wait<0>();
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -312,7 +342,6 @@ bgemm_dmma_kernel(const double *__restrict__ Q, const double *__restrict__ X, do
           if (c + 1 < N) Y[(int64_t)r * N + c + 1] = alpha * acc[i][j][1];
         }
       }
-    __syncthreads();
   }
 }
 
