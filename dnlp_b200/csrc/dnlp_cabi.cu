@@ -36,6 +36,11 @@ struct DevInstr {
   double mean_len = 1.0;
   bool has_f2 = false;
   std::string kname;       // kernel that executes this instruction (as ncu prints it)
+  // contiguous special case detected at upload: f1[t] = s0 + t, f2[t] = s1 + t (or absent)
+  bool contig = false;
+  bool const_coef = false;
+  int64_t s0 = 0, s1 = 0;
+  double c0 = 1.0;
 };
 
 // All x-only elementwise instructions of one program, fused into a single launch.
@@ -175,6 +180,26 @@ int dnlp_oracle::launch(DevInstr &I) {
       break;
     }
     case DNLP_POLY: {
+      if (I.contig && I.const_coef && d.count == 1 && d.nterms >= 2048 && !d.pos) {
+        int64_t blocks = (d.nterms + 256 * 4 - 1) / (256 * 4);
+        int64_t cap = (int64_t)sm_count * 4;
+        int grid = (int)(blocks < cap ? blocks : cap);
+        if (I.has_f2)
+          sum_range_kernel<true><<<grid, 256, 0, stream>>>(V, dst, I.s0, I.s1, d.nterms, I.c0, d.accumulate, scratch, ticket);
+        else
+          sum_range_kernel<false><<<grid, 256, 0, stream>>>(V, dst, I.s0, I.s1, d.nterms, I.c0, d.accumulate, scratch, ticket);
+        if (I.kname.empty()) I.kname = std::string("sum_range_kernel<") + (I.has_f2 ? "1" : "0") + ">";
+        break;
+      }
+      if (I.contig && d.ptr == nullptr && d.row_len == 1 && !d.pos && !d.accumulate && d.count >= 4096) {
+        int grid = grid_for(d.count, 1);
+        if (I.has_f2)
+          poly1_contig_kernel<true><<<grid, 256, 0, stream>>>(V, dst, d.coef, I.s0, I.s1, d.count);
+        else
+          poly1_contig_kernel<false><<<grid, 256, 0, stream>>>(V, dst, d.coef, I.s0, I.s1, d.count);
+        if (I.kname.empty()) I.kname = std::string("poly1_contig_kernel<") + (I.has_f2 ? "1" : "0") + ">";
+        break;
+      }
       if (d.count == 1 && d.nterms >= 2048 && !d.pos) {
         // one long row: grid-wide deterministic reduction in a single launch
         int64_t blocks = (d.nterms + 256 * 4 - 1) / (256 * 4);     // one 4-term batch per thread until the grid is full
@@ -516,6 +541,21 @@ static int create_impl(dnlp_oracle *o, const dnlp_tape_desc *t) {
       if (h.f2) { if (o->upload(h.f2, h.nterms, const_cast<int32_t **>(&D.d.f2))) return 1; }
       D.has_f2 = h.f2 != nullptr;
       D.mean_len = h.count > 0 ? (double)h.nterms / (double)h.count : 1.0;
+      // contiguous slots and (for reductions) one shared coefficient?  -> index-free kernels
+      if (h.nterms >= 2048 && (h.count == 1 || (!h.ptr && h.row_len == 1)) && h.f1[0] >= 0 &&
+          (!h.f2 || h.f2[0] >= 0)) {
+        bool contig = true, cc = true;
+        for (int64_t t2 = 1; t2 < h.nterms && contig; ++t2) {
+          if (h.f1[t2] != h.f1[0] + t2) contig = false;
+          else if (h.f2 && h.f2[t2] != h.f2[0] + t2) contig = false;
+          if (h.coef[t2] != h.coef[0]) cc = false;
+        }
+        D.contig = contig;
+        D.const_coef = contig && cc;
+        D.s0 = h.f1[0];
+        D.s1 = h.f2 ? h.f2[0] : 0;
+        D.c0 = h.coef[0];
+      }
     } else if (h.kind == DNLP_GEMV) {
       if (o->upload(h.Q, h.count * h.ncols, const_cast<double **>(&D.d.Q))) return 1;
     } else if (h.kind == DNLP_SCALE) {

@@ -669,4 +669,62 @@ gather_kernel(const double *__restrict__ src, const int32_t *__restrict__ pos, d
     dst[k] = src[pos[k]];
 }
 
+// ---- contiguous special cases found at upload time (no index stream, no gather) ----------------
+// dst[0] (+)= c * sum_{t < n} V[s0 + t] (* V[s1 + t]):   f = sum_i phi(t_i), x'(Qx), sum x^2
+template <bool HAS_F2>
+__global__ void __launch_bounds__(256)
+sum_range_kernel(const double *__restrict__ V, double *__restrict__ dst, int64_t s0, int64_t s1, int64_t n,
+                 double c, int accumulate, double *__restrict__ scratch, unsigned int *__restrict__ ticket) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += 4 * stride) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t i = k + u * stride;
+      if (i < n) acc[u] += HAS_F2 ? V[s0 + i] * V[s1 + i] : V[s0 + i];
+    }
+  }
+  double v = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+  __shared__ double wsum[8];
+  __shared__ bool last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) wsum[warp] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += wsum[w];
+    scratch[blockIdx.x] = t;
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last && warp == 0) {
+    __threadfence();
+    double t = 0.0;
+    for (int i = lane; i < (int)gridDim.x; i += 32) t += __ldcg(scratch + i);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) t += __shfl_xor_sync(0xffffffffu, t, s);
+    if (lane == 0) {
+      dst[0] = accumulate ? dst[0] + c * t : c * t;
+      *ticket = 0;
+    }
+  }
+}
+
+// dst[k] = coef[k] * V[s0 + k] (* V[s1 + k]):  gradient / diagonal-Hessian fills over contiguous slots
+template <bool HAS_F2>
+__global__ void __launch_bounds__(256)
+poly1_contig_kernel(const double *__restrict__ V, double *__restrict__ dst, const double *__restrict__ coef,
+                    int64_t s0, int64_t s1, int64_t count) {
+  const uint64_t pf = l2_policy_evict_first();
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += (int64_t)gridDim.x * blockDim.x) {
+    double v = ld_stream_f64(coef + k, pf) * V[s0 + k];
+    if (HAS_F2) v *= V[s1 + k];
+    st_stream_f64(dst + k, v, pf);
+  }
+}
+
 }  // namespace dnlp
