@@ -32,6 +32,7 @@ class InstrDesc(C.Structure):
         ("level", C.c_int32), ("reserved", C.c_int32),
         ("Q", c_f64p), ("ncols", C.c_int64), ("x_off", C.c_int64), ("alpha", C.c_double),
         ("s_slot", C.c_int64),
+        ("deps", c_i32p), ("n_deps", C.c_int64),
     ]
 
 
@@ -49,7 +50,7 @@ EXPORTS = [
     "dnlp_device_count", "dnlp_version", "dnlp_create", "dnlp_destroy", "dnlp_last_error",
     "dnlp_eval_f", "dnlp_eval_grad", "dnlp_eval_g", "dnlp_eval_jac", "dnlp_eval_hess", "dnlp_eval_all",
     "dnlp_host_alloc", "dnlp_host_free", "dnlp_upload_point", "dnlp_run_device", "dnlp_profile_instrs",
-    "dnlp_read_output", "dnlp_kernel_launches", "dnlp_set_cache", "dnlp_set_graphs", "dnlp_set_dynamic", "dnlp_eval_dyn", "dnlp_instr_kernel", "dnlp_run", "dnlp_output_ptr",
+    "dnlp_read_output", "dnlp_kernel_launches", "dnlp_set_cache", "dnlp_set_graphs", "dnlp_set_parallel", "dnlp_set_dynamic", "dnlp_eval_dyn", "dnlp_instr_kernel", "dnlp_run", "dnlp_output_ptr",
     "dnlp_batch_create", "dnlp_batch_destroy", "dnlp_batch_last_error", "dnlp_batch_eval", "dnlp_batch_upload",
     "dnlp_batch_run_device", "dnlp_batch_profile_instrs", "dnlp_batch_kernel_launches",
 ]
@@ -93,6 +94,7 @@ def lib():
     L.dnlp_kernel_launches.restype = C.c_int64
     L.dnlp_set_cache.argtypes = [vp, C.c_int32]
     L.dnlp_set_graphs.argtypes = [vp, C.c_int32]
+    L.dnlp_set_parallel.argtypes = [vp, C.c_int32]
     L.dnlp_run.argtypes = [vp, C.c_int32, c_f64p, c_f64p, C.c_double]
     L.dnlp_output_ptr.argtypes = [vp, C.c_int32]
     L.dnlp_output_ptr.restype = vp
@@ -196,6 +198,10 @@ def make_tape_desc(tape):
             coef = f64(ins.coef)
             keep.append(coef)
             d.coef = _p(coef, c_f64p)
+        if len(ins.deps):
+            deps = np.ascontiguousarray(sorted(ins.deps), dtype=np.int32)
+            keep.append(deps)
+            d.deps, d.n_deps = _p(deps, c_i32p), int(deps.size)
         if ins.pos is not None:
             pos = np.ascontiguousarray(ins.pos, dtype=np.int32)
             keep.append(pos)

@@ -36,6 +36,7 @@ struct DevInstr {
   double mean_len = 1.0;
   bool has_f2 = false;
   std::string kname;       // kernel that executes this instruction (as ncu prints it)
+  std::vector<int32_t> deps;   // instructions whose V ranges this one reads
   // contiguous special case detected at upload: f1[t] = s0 + t, f2[t] = s1 + t (or absent)
   bool contig = false;
   bool const_coef = false;
@@ -80,9 +81,8 @@ struct dnlp_oracle {
   struct GraphEntry {
     cudaGraphExec_t exec = nullptr;
     int64_t nlaunch = 0;
-    int prog = -1;                 // the exact sequence this graph replays (verified on every hit:
-    bool with_batch = false;       // a hash collision must never replay the wrong kernels)
-    std::vector<int32_t> plan;
+    std::vector<int32_t> plan;     // the exact node sequence this graph replays (verified on every
+                                   // hit: a hash collision must never replay the wrong kernels)
   };
   std::unordered_map<uint64_t, GraphEntry> graphs;
   bool graphs_enabled = true;
@@ -90,8 +90,17 @@ struct dnlp_oracle {
   int32_t *dyn_pos[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   double *dyn_buf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int64_t dyn_len[6] = {0, 0, 0, 0, 0, 0};
-  double *scratch = nullptr;           // partials of the single-row reduction kernel
-  unsigned int *ticket = nullptr;
+  double *scratch = nullptr;           // partials of the single-row reduction kernels: one 4096-double
+  unsigned int *ticket = nullptr;      // block (and one ticket) per lane, lanes may reduce concurrently
+  // Lanes: lane 0 is `stream`, the others are side streams that only ever run inside a capture.
+  // Independent instructions of a launch sequence are captured on different lanes, so the replayed
+  // graph has one branch per independent chain instead of a single serial chain.
+  static constexpr int NLANE = 8;
+  cudaStream_t lane[NLANE] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t cur = nullptr;          // the lane launch() issues on
+  int cur_lane = 0;
+  std::vector<cudaEvent_t> ev_pool;    // capture-time dependency markers
+  bool parallel_enabled = true;
 
   template <typename T>
   int upload(const T *host, int64_t count, T **dev) {
@@ -118,7 +127,12 @@ struct dnlp_oracle {
 
   int launch(DevInstr &I);
   int build_batches();
-  int run_program(int p, bool force);
+  int run_program(int p, bool force) { return run_programs(&p, 1, force); }
+  int run_programs(const int *progs, int nprogs, bool force);
+  int issue_serial(const std::vector<int32_t> &nodes);
+  int issue_parallel(const std::vector<int32_t> &nodes);
+  int launch_node(int32_t node);
+  cudaEvent_t event_at(size_t i);
   int put_x(const double *x);
   int put_lam(const double *lam, double sigma);
   int fetch(int space, double *host);
@@ -133,7 +147,7 @@ using namespace dnlp;
 
 template <int F, bool B>
 void launch_elem_t(const dnlp_oracle *o, const dnlp_instr_desc &d, int grid) {
-  elem_kernel<F, B><<<grid, 256, 0, o->stream>>>(o->V, d.a_off, d.a_stride, d.b_off, d.b_stride,
+  elem_kernel<F, B><<<grid, 256, 0, o->cur>>>(o->V, d.a_off, d.a_stride, d.b_off, d.b_stride,
                                                 d.dst_off, d.count, d.param);
 }
 
@@ -159,7 +173,7 @@ void launch_poly_g(const dnlp_oracle *o, const DevInstr &I, double *dst, int gri
   const dnlp_instr_desc &d = I.d;
   const bool uni = d.ptr == nullptr;
 #define LP(H, Un)                                                                                   \
-  poly_rows_kernel<G, 2, H, Un><<<grid, 256, 0, o->stream>>>(o->V, dst, d.ptr, d.row_len, d.coef,   \
+  poly_rows_kernel<G, 2, H, Un><<<grid, 256, 0, o->cur>>>(o->V, dst, d.ptr, d.row_len, d.coef,   \
                                                              d.f1, d.f2, d.pos, d.count, d.accumulate)
   if (I.has_f2) { if (uni) LP(true, true); else LP(true, false); }
   else { if (uni) LP(false, true); else LP(false, false); }
@@ -172,6 +186,7 @@ int dnlp_oracle::launch(DevInstr &I) {
   const dnlp_instr_desc &d = I.d;
   if (d.count <= 0) return 0;
   double *dst = (d.dst_space == DNLP_DST_V) ? V + d.dst_off : out[d.dst_space] + d.dst_off;
+  if (cur == nullptr) { cur = stream; cur_lane = 0; }
   switch (d.kind) {
     case DNLP_ELEM: {
       int grid = grid_for((d.count + 1) / 2, 1);
@@ -185,18 +200,18 @@ int dnlp_oracle::launch(DevInstr &I) {
         int64_t cap = (int64_t)sm_count * 4;
         int grid = (int)(blocks < cap ? blocks : cap);
         if (I.has_f2)
-          sum_range_kernel<true><<<grid, 256, 0, stream>>>(V, dst, I.s0, I.s1, d.nterms, I.c0, d.accumulate, scratch, ticket);
+          sum_range_kernel<true><<<grid, 256, 0, cur>>>(V, dst, I.s0, I.s1, d.nterms, I.c0, d.accumulate, scratch + cur_lane * 4096, ticket + cur_lane * 16);
         else
-          sum_range_kernel<false><<<grid, 256, 0, stream>>>(V, dst, I.s0, I.s1, d.nterms, I.c0, d.accumulate, scratch, ticket);
+          sum_range_kernel<false><<<grid, 256, 0, cur>>>(V, dst, I.s0, I.s1, d.nterms, I.c0, d.accumulate, scratch + cur_lane * 4096, ticket + cur_lane * 16);
         if (I.kname.empty()) I.kname = std::string("sum_range_kernel<") + (I.has_f2 ? "1" : "0") + ">";
         break;
       }
       if (I.contig && d.ptr == nullptr && d.row_len == 1 && !d.pos && !d.accumulate && d.count >= 4096) {
         int grid = grid_for(d.count, 1);
         if (I.has_f2)
-          poly1_contig_kernel<true><<<grid, 256, 0, stream>>>(V, dst, d.coef, I.s0, I.s1, d.count);
+          poly1_contig_kernel<true><<<grid, 256, 0, cur>>>(V, dst, d.coef, I.s0, I.s1, d.count);
         else
-          poly1_contig_kernel<false><<<grid, 256, 0, stream>>>(V, dst, d.coef, I.s0, I.s1, d.count);
+          poly1_contig_kernel<false><<<grid, 256, 0, cur>>>(V, dst, d.coef, I.s0, I.s1, d.count);
         if (I.kname.empty()) I.kname = std::string("poly1_contig_kernel<") + (I.has_f2 ? "1" : "0") + ">";
         break;
       }
@@ -206,9 +221,9 @@ int dnlp_oracle::launch(DevInstr &I) {
         int64_t cap = (int64_t)sm_count * 4;
         int grid = (int)(blocks < cap ? blocks : cap);
         if (I.has_f2)
-          poly_reduce_kernel<true><<<grid, 256, 0, stream>>>(V, dst, d.coef, d.f1, d.f2, d.nterms, d.accumulate, scratch, ticket);
+          poly_reduce_kernel<true><<<grid, 256, 0, cur>>>(V, dst, d.coef, d.f1, d.f2, d.nterms, d.accumulate, scratch + cur_lane * 4096, ticket + cur_lane * 16);
         else
-          poly_reduce_kernel<false><<<grid, 256, 0, stream>>>(V, dst, d.coef, d.f1, d.f2, d.nterms, d.accumulate, scratch, ticket);
+          poly_reduce_kernel<false><<<grid, 256, 0, cur>>>(V, dst, d.coef, d.f1, d.f2, d.nterms, d.accumulate, scratch + cur_lane * 4096, ticket + cur_lane * 16);
         if (I.kname.empty()) I.kname = std::string("poly_reduce_kernel<") + (I.has_f2 ? "1" : "0") + ">";
         break;
       }
@@ -217,9 +232,9 @@ int dnlp_oracle::launch(DevInstr &I) {
         int grid = grid_for((d.count + 3) / 4, 1);
         if (grid > sm_count * 4) grid = sm_count * 4;
         if (I.has_f2)
-          poly1_stream_kernel<4, true><<<grid, 256, 0, stream>>>(V, dst, d.coef, d.f1, d.f2, d.pos, d.count, d.accumulate);
+          poly1_stream_kernel<4, true><<<grid, 256, 0, cur>>>(V, dst, d.coef, d.f1, d.f2, d.pos, d.count, d.accumulate);
         else
-          poly1_stream_kernel<4, false><<<grid, 256, 0, stream>>>(V, dst, d.coef, d.f1, d.f2, d.pos, d.count, d.accumulate);
+          poly1_stream_kernel<4, false><<<grid, 256, 0, cur>>>(V, dst, d.coef, d.f1, d.f2, d.pos, d.count, d.accumulate);
         if (I.kname.empty()) I.kname = std::string("poly1_stream_kernel<4, ") + (I.has_f2 ? "1" : "0") + ">";
         break;
       }
@@ -248,7 +263,7 @@ int dnlp_oracle::launch(DevInstr &I) {
         // whole CTA per row, 16 warps x 4 x 128-bit loads in flight, 2 CTAs per SM
         int64_t cap = (int64_t)sm_count * 2;
         int grid = (int)(d.count < cap ? d.count : cap);
-        gemv_cta_kernel<4, 16><<<grid, 512, smem, stream>>>(d.Q, V, d.x_off, dst, d.count, d.ncols, d.alpha);
+        gemv_cta_kernel<4, 16><<<grid, 512, smem, cur>>>(d.Q, V, d.x_off, dst, d.count, d.ncols, d.alpha);
         if (I.kname.empty()) I.kname = "gemv_cta_kernel<4, 16>";
       } else {
         int in_smem = smem <= 96 * 1024 ? 1 : 0;
@@ -256,7 +271,7 @@ int dnlp_oracle::launch(DevInstr &I) {
         int64_t blocks = (d.count + 7) / 8;
         int64_t cap = (int64_t)sm_count * (in_smem && smem > 48 * 1024 ? 2 : 4);
         int grid = (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
-        gemv_kernel<8><<<grid, 256, smem, stream>>>(d.Q, V, d.x_off, dst, d.count, d.ncols, d.alpha, in_smem);
+        gemv_kernel<8><<<grid, 256, smem, cur>>>(d.Q, V, d.x_off, dst, d.count, d.ncols, d.alpha, in_smem);
         if (I.kname.empty()) I.kname = "gemv_kernel<8>";
       }
       break;
@@ -264,10 +279,10 @@ int dnlp_oracle::launch(DevInstr &I) {
     case DNLP_SCALE: {
       int grid = grid_for((d.count + 1) / 2, 1);
       if (!d.pos && !d.accumulate && ((reinterpret_cast<uintptr_t>(d.coef) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0)
-        { scale_stream_kernel<4><<<sm_count * 16, 256, 0, stream>>>(V, d.s_slot, d.coef, dst, d.count);
+        { scale_stream_kernel<4><<<sm_count * 16, 256, 0, cur>>>(V, d.s_slot, d.coef, dst, d.count);
           if (I.kname.empty()) I.kname = "scale_stream_kernel<4>"; }
       else
-        scale_kernel<<<grid, 256, 0, stream>>>(V, d.s_slot, d.coef, dst, d.pos, d.count, d.accumulate);
+        scale_kernel<<<grid, 256, 0, cur>>>(V, d.s_slot, d.coef, dst, d.pos, d.count, d.accumulate);
       break;
     }
     default:
@@ -317,78 +332,163 @@ int dnlp_oracle::build_batches() {
   return 0;
 }
 
-int dnlp_oracle::run_program(int p, bool force) {
-  // 1. which launches does this call need?  (depends only on the validity flags)
-  ElemBatch &B = batch[p];
-  bool use_batch = false;
-  if (!B.members.empty()) {
-    use_batch = true;
-    if (cache_enabled && !force)
-      for (int32_t id : B.members) if (valid[id]) { use_batch = false; break; }
+// A node of a launch sequence: an instruction id (>= 0) or the fused elementwise batch of
+// program p, encoded as -(p + 1).
+int dnlp_oracle::launch_node(int32_t node) {
+  if (node >= 0) return launch(instrs[node]);
+  ElemBatch &B = batch[-node - 1];
+  if (cur == nullptr) { cur = stream; cur_lane = 0; }
+  int64_t cap = (int64_t)sm_count * 8;
+  int grid = (int)(B.total_tiles < cap ? B.total_tiles : cap);
+  dnlp::elem_batch_kernel<<<grid, 256, 0, cur>>>(V, B.descs, B.ndesc, B.total_tiles);
+  ++launches;
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) { err = std::string("kernel launch failed: ") + cudaGetErrorString(e); return 1; }
+  return 0;
+}
+
+int dnlp_oracle::issue_serial(const std::vector<int32_t> &nodes) {
+  cur = stream; cur_lane = 0;
+  for (int32_t nd : nodes) if (launch_node(nd)) return 1;
+  return 0;
+}
+
+cudaEvent_t dnlp_oracle::event_at(size_t i) {
+  while (ev_pool.size() <= i) {
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    ev_pool.push_back(e);
   }
-  std::vector<int32_t> plan;
+  return ev_pool[i];
+}
+
+// Capture-time issue: `stream` is capturing.  Every node is placed on a lane; a node waits (event
+// edges) for the nodes that produce the V ranges it reads and for the previous writer of the same
+// output array, nothing else.  All lanes are joined back into `stream` before returning, so whatever
+// follows in stream order (the D2H copy, the next program) sees every result.
+int dnlp_oracle::issue_parallel(const std::vector<int32_t> &nodes) {
+  const size_t N = nodes.size();
+  if (N < 2 || !parallel_enabled) return issue_serial(nodes);
+  std::unordered_map<int32_t, int> producer;      // instruction id -> node index within this sequence
+  for (size_t k = 0; k < N; ++k) {
+    if (nodes[k] >= 0) producer[nodes[k]] = (int)k;
+    else for (int32_t id : batch[-nodes[k] - 1].members) producer[id] = (int)k;
+  }
+  std::vector<int> lane_of(N, 0);
+  int last_on_lane[NLANE];
+  bool joined[NLANE];
+  for (int l = 0; l < NLANE; ++l) { last_on_lane[l] = -1; joined[l] = (l == 0); }
+  int last_writer[6] = {-1, -1, -1, -1, -1, -1};
+  int rr = 0;
+  cudaEvent_t fork = event_at(0);
+  if (!fork) { err = "cudaEventCreate failed"; return 1; }
+  CK(cudaEventRecord(fork, stream));
+  std::vector<int> deps;
+  for (size_t k = 0; k < N; ++k) {
+    deps.clear();
+    if (nodes[k] >= 0) {
+      const DevInstr &I = instrs[nodes[k]];
+      for (int32_t d : I.deps) {
+        auto it = producer.find(d);
+        if (it != producer.end() && it->second < (int)k) deps.push_back(it->second);
+      }
+      if (I.d.dst_space != DNLP_DST_V) {
+        if (last_writer[I.d.dst_space] >= 0) deps.push_back(last_writer[I.d.dst_space]);
+        last_writer[I.d.dst_space] = (int)k;
+      }
+    }
+    // lane choice: continue the chain of a dependency when it is still the tail of its lane,
+    // else an idle lane, else round robin
+    int L = -1;
+    for (int d : deps) if (last_on_lane[lane_of[d]] == d) { L = lane_of[d]; break; }
+    if (L < 0) for (int l = 0; l < NLANE; ++l) if (last_on_lane[l] < 0) { L = l; break; }
+    if (L < 0) { L = rr; rr = (rr + 1) % NLANE; }
+    if (!joined[L]) { CK(cudaStreamWaitEvent(lane[L], fork, 0)); joined[L] = true; }
+    for (int d : deps)
+      if (lane_of[d] != L) CK(cudaStreamWaitEvent(lane[L], event_at(1 + (size_t)d), 0));
+    cur = lane[L]; cur_lane = L;
+    const int rc = launch_node(nodes[k]);
+    cur = stream; cur_lane = 0;
+    if (rc) return 1;
+    cudaEvent_t done = event_at(1 + k);
+    if (!done) { err = "cudaEventCreate failed"; return 1; }
+    CK(cudaEventRecord(done, lane[L]));
+    lane_of[k] = L;
+    last_on_lane[L] = (int)k;
+  }
+  for (int l = 1; l < NLANE; ++l)
+    if (joined[l] && last_on_lane[l] >= 0) CK(cudaStreamWaitEvent(stream, event_at(1 + (size_t)last_on_lane[l]), 0));
+  return 0;
+}
+
+int dnlp_oracle::run_programs(const int *progs, int nprogs, bool force) {
+  // 1. which launches does this call need?  (depends only on the validity flags; several programs
+  //    are planned as one sequence so that their independent parts can overlap)
+  std::vector<int32_t> nodes;
+  std::vector<uint8_t> done(valid);
+  if (force || !cache_enabled) std::fill(done.begin(), done.end(), 0);
   uint64_t key = 1469598103934665603ull;
-  key = (key ^ (uint64_t)(p + 1)) * 1099511628211ull;
-  key = (key ^ (uint64_t)(use_batch ? 2 : 1)) * 1099511628211ull;
-  std::vector<uint8_t> covered;
-  if (use_batch) { covered.assign(instrs.size(), 0); for (int32_t id : B.members) covered[id] = 1; }
-  for (int32_t id : prog[p]) {
-    DevInstr &I = instrs[id];
-    const bool cacheable = !I.d.uses_lam && I.d.dst_space == DNLP_DST_V;
-    if (use_batch && covered[id]) continue;
-    if (cacheable && valid[id] && !force) continue;
-    plan.push_back(id);
-    key = (key ^ (uint64_t)(id + 1)) * 1099511628211ull;
+  for (int q = 0; q < nprogs; ++q) {
+    const int p = progs[q];
+    ElemBatch &B = batch[p];
+    bool use_batch = !B.members.empty();
+    if (use_batch) for (int32_t id : B.members) if (done[id]) { use_batch = false; break; }
+    if (use_batch) {
+      nodes.push_back(-(p + 1));
+      key = (key ^ (uint64_t)(0x10000 + p)) * 1099511628211ull;
+      for (int32_t id : B.members) done[id] = 2;      // 2: covered by a batch node of this sequence
+    }
+    for (int32_t id : prog[p]) {
+      const DevInstr &I = instrs[id];
+      const bool cacheable = !I.d.uses_lam && I.d.dst_space == DNLP_DST_V;
+      if (done[id] == 2) continue;
+      if (cacheable && done[id]) continue;
+      nodes.push_back(id);
+      key = (key ^ (uint64_t)(id + 1)) * 1099511628211ull;
+      if (cacheable) done[id] = 1;
+    }
+    // a later program of the same call must not skip what a batch of this one produced, nor treat
+    // it as still pending
+    for (auto &f : done) if (f == 2) f = 1;
   }
-  if (!use_batch && plan.empty()) return 0;
+  if (nodes.empty()) return 0;
 
   // 2. replay a captured graph, capture one, or launch directly
-  auto issue = [&]() -> int {
-    if (use_batch) {
-      int64_t cap = (int64_t)sm_count * 8;
-      int grid = (int)(B.total_tiles < cap ? B.total_tiles : cap);
-      dnlp::elem_batch_kernel<<<grid, 256, 0, stream>>>(V, B.descs, B.ndesc, B.total_tiles);
-      ++launches;
-      cudaError_t e = cudaPeekAtLastError();
-      if (e != cudaSuccess) { err = std::string("kernel launch failed: ") + cudaGetErrorString(e); return 1; }
-    }
-    for (int32_t id : plan) if (launch(instrs[id])) return 1;
-    return 0;
-  };
-  const int nl = (int)plan.size() + (use_batch ? 1 : 0);
-  if (graphs_enabled && !capturing && nl >= 2) {
+  if (capturing) {
+    if (issue_parallel(nodes)) return 1;              // an enclosing capture (dnlp_run_device)
+  } else if (graphs_enabled && nodes.size() >= 2) {
     auto it = graphs.find(key);
     if (it != graphs.end()) {
       const GraphEntry &ge = it->second;
-      if (ge.prog == p && ge.with_batch == use_batch && ge.plan == plan) {
+      if (ge.plan == nodes) {
         CK(cudaGraphLaunch(ge.exec, stream));
         launches += ge.nlaunch;
-      } else if (issue()) return 1;          // hash collision: launch directly
+      } else if (issue_serial(nodes)) return 1;       // hash collision: launch directly
     } else if (graphs.size() < 64) {
       const int64_t before = launches;
       capturing = true;
       CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-      const int rc = issue();
+      const int rc = issue_parallel(nodes);
       cudaGraph_t g = nullptr;
       cudaError_t ce = cudaStreamEndCapture(stream, &g);
       capturing = false;
-      if (rc) { if (g) cudaGraphDestroy(g); return 1; }
+      if (rc) { if (g) cudaGraphDestroy(g); cudaGetLastError(); return 1; }
       if (ce != cudaSuccess) { err = std::string("graph capture failed: ") + cudaGetErrorString(ce); return 1; }
       GraphEntry ge;
-      ge.prog = p; ge.with_batch = use_batch; ge.plan = plan;
+      ge.plan = nodes;
       ge.nlaunch = launches - before;
       CK(cudaGraphInstantiate(&ge.exec, g, 0));
       cudaGraphDestroy(g);
       graphs.emplace(key, ge);
       CK(cudaGraphLaunch(ge.exec, stream));
-    } else if (issue()) return 1;
-  } else if (issue()) return 1;
+    } else if (issue_serial(nodes)) return 1;
+  } else if (issue_serial(nodes)) return 1;
 
   // 3. bookkeeping: x-only results stay valid until x changes
-  if (use_batch) for (int32_t id : B.members) valid[id] = 1;
-  for (int32_t id : plan) {
-    const DevInstr &I = instrs[id];
-    if (!I.d.uses_lam && I.d.dst_space == DNLP_DST_V) valid[id] = 1;
+  for (int32_t nd : nodes) {
+    if (nd < 0) { for (int32_t id : batch[-nd - 1].members) valid[id] = 1; continue; }
+    const DevInstr &I = instrs[nd];
+    if (!I.d.uses_lam && I.d.dst_space == DNLP_DST_V) valid[nd] = 1;
   }
   return 0;
 }
@@ -482,6 +582,8 @@ void dnlp_destroy(dnlp_oracle *o) {
   if (o->hlam) cudaFreeHost(o->hlam);
   if (o->ev0) cudaEventDestroy(o->ev0);
   if (o->ev1) cudaEventDestroy(o->ev1);
+  for (cudaEvent_t e : o->ev_pool) cudaEventDestroy(e);
+  for (int l = 1; l < dnlp_oracle::NLANE; ++l) if (o->lane[l]) cudaStreamDestroy(o->lane[l]);
   if (o->stream) cudaStreamDestroy(o->stream);
   delete o;
 }
@@ -507,13 +609,16 @@ static int create_impl(dnlp_oracle *o, const dnlp_tape_desc *t) {
   o->hx = static_cast<double *>(p);
   CK(cudaMallocHost(&p, (size_t)(t->m + 2) * sizeof(double)));
   o->hlam = static_cast<double *>(p);
-  CK(cudaMalloc(&p, 4096 * sizeof(double)));
+  CK(cudaMalloc(&p, (size_t)dnlp_oracle::NLANE * 4096 * sizeof(double)));
   o->owned.push_back(p);
   o->scratch = static_cast<double *>(p);
-  CK(cudaMalloc(&p, 64));
+  CK(cudaMalloc(&p, (size_t)dnlp_oracle::NLANE * 16 * sizeof(unsigned int)));
   o->owned.push_back(p);
   o->ticket = static_cast<unsigned int *>(p);
-  CK(cudaMemset(o->ticket, 0, 64));
+  CK(cudaMemset(o->ticket, 0, (size_t)dnlp_oracle::NLANE * 16 * sizeof(unsigned int)));
+  o->lane[0] = o->stream;
+  for (int l = 1; l < dnlp_oracle::NLANE; ++l) CK(cudaStreamCreateWithFlags(&o->lane[l], cudaStreamNonBlocking));
+  o->cur = o->stream;
 
   const int64_t lens[6] = {0, 1, t->n, t->m, t->nnz_jac, t->nnz_hess};
   const double *consts[6] = {nullptr, &t->f_const, t->grad_const, t->g_const, t->jac_const, t->hess_const};
@@ -537,6 +642,11 @@ static int create_impl(dnlp_oracle *o, const dnlp_tape_desc *t) {
     DevInstr &D = o->instrs[i];
     D.d = h;
     D.d.ptr = nullptr; D.d.coef = nullptr; D.d.f1 = nullptr; D.d.f2 = nullptr; D.d.pos = nullptr; D.d.Q = nullptr;
+    D.d.deps = nullptr;
+    for (int64_t k = 0; k < h.n_deps; ++k) {
+      if (h.deps[k] < 0 || h.deps[k] >= i) { err = "instruction depends on a later or unknown instruction"; return 1; }
+      D.deps.push_back(h.deps[k]);
+    }
     if (h.kind == DNLP_POLY) {
       if (h.ptr) { if (o->upload(h.ptr, h.count + 1, const_cast<int64_t **>(&D.d.ptr))) return 1; }
       if (o->upload(h.coef, h.nterms, const_cast<double **>(&D.d.coef))) return 1;
@@ -714,12 +824,11 @@ int dnlp_run_device(dnlp_oracle *o, int32_t prog_mask, int32_t iters, float *ela
   ENTER(o);
   // one step = every cache invalidated, then the requested programs; the whole step is captured
   // once into a CUDA graph and replayed `iters` times
+  int progs[DNLP_NPROG], nprogs = 0;
+  for (int p = 0; p < DNLP_NPROG; ++p) if (prog_mask & (1 << p)) progs[nprogs++] = p;
   auto step = [&]() -> int {
     std::fill(o->valid.begin(), o->valid.end(), 0);   // a new point every step: nothing is reused
-    for (int p = 0; p < DNLP_NPROG; ++p)
-      if (prog_mask & (1 << p))
-        if (o->run_program(p, false)) return 1;
-    return 0;
+    return o->run_programs(progs, nprogs, false);     // one sequence: independent parts overlap
   };
   cudaGraphExec_t exec = nullptr;
   int64_t per_step = 0;
@@ -796,6 +905,15 @@ const char *dnlp_instr_kernel(dnlp_oracle *o, int32_t instr) {
 
 int dnlp_set_graphs(dnlp_oracle *o, int32_t enabled) {
   o->graphs_enabled = enabled != 0;
+  return 0;
+}
+
+int dnlp_set_parallel(dnlp_oracle *o, int32_t enabled) {
+  ENTER(o);
+  CK(cudaStreamSynchronize(o->stream));
+  o->parallel_enabled = enabled != 0;
+  for (auto &kv : o->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  o->graphs.clear();                                  // captured with the other setting
   return 0;
 }
 

@@ -230,5 +230,9 @@ class GpuOracles:
     def set_graphs(self, enabled):
         self.dev._L.dnlp_set_graphs(self.dev.h, int(bool(enabled)))
 
+    def set_parallel(self, enabled):
+        """Parallel graph branches for independent instructions (on by default)."""
+        self.dev.check(self.dev._L.dnlp_set_parallel(self.dev.h, int(bool(enabled))))
+
     def set_cache(self, enabled):
         self.dev._L.dnlp_set_cache(self.dev.h, int(bool(enabled)))

@@ -76,6 +76,10 @@ typedef struct {
   double alpha;
   /* SCALE: dst[pos?[k]] = V[s_slot] * coef[k] */
   int64_t s_slot;
+  /* data dependencies: ids of the instructions whose V ranges this one reads.  Independent
+   * instructions become parallel branches of the CUDA graph that replays a launch sequence. */
+  const int32_t *deps;
+  int64_t n_deps;
 } dnlp_instr_desc;
 
 typedef struct {
@@ -147,6 +151,7 @@ int64_t dnlp_kernel_launches(dnlp_oracle *o);                           /* launc
 const char *dnlp_instr_kernel(dnlp_oracle *o, int32_t instr);           /* kernel name of an executed instruction */
 int dnlp_set_cache(dnlp_oracle *o, int32_t enabled);                    /* x-keyed forward cache on/off */
 int dnlp_set_graphs(dnlp_oracle *o, int32_t enabled);                   /* CUDA-graph replay of launch sequences on/off */
+int dnlp_set_parallel(dnlp_oracle *o, int32_t enabled);                 /* parallel graph branches for independent instructions on/off */
 
 /* ---- batched multi-start evaluation (BASELINE config 4; the reference's serial `best_of` loop,
  *      cvxpy/problems/problem.py:1249-1275, evaluates one start at a time) ----

@@ -344,3 +344,40 @@ def test_gpu_cabi_error_paths():
             o.eval(np.zeros((4, g.problem.n)), want=("hess",))
     finally:
         o.close()
+
+
+@pytest.mark.parametrize("name", ["c1_readme_toy", "c2_eigen_qcqp_small", "c3_logistic_small",
+                                  "c5_microbench_small", "c5_lifted_small", "clnlbeam", "nmf_kl_graph_form"])
+def test_gpu_parallel_graph_branches_equal_serial(name, gpu_mod):
+    """Independent instructions are captured as parallel graph branches (data-dependency edges only).
+    Results must be bit-identical to the serial launch order, for single callbacks, for the fused
+    five-program sequence of the device loop, and with CUDA graphs switched off."""
+    g = Golden(name)
+    p = g.points[-1]
+    outs = {}
+    for mode in ("parallel", "serial", "nographs"):
+        o = gpu_mod(g.problem)
+        try:
+            if mode == "serial":
+                o.set_parallel(False)
+            if mode == "nographs":
+                o.set_graphs(False)
+            res = []
+            for _ in range(2):      # second round replays the captured graphs
+                o.set_cache(False)
+                o.set_cache(True)
+                r = o.eval_all(p["x"], p["lam"], float(p["sigma"]))
+                res.append({k: np.array(np.asarray(r[k]).reshape(-1), copy=True) for k in r})
+            o.upload_point(p["x"], p["lam"], float(p["sigma"]))
+            o.run_device(iters=3)
+            dev = {k: o.read_output(k) for k in ("f", "grad", "g", "jac", "hess")}
+            outs[mode] = (res, dev)
+        finally:
+            o.close()
+    for k in ("f", "grad", "g", "jac", "hess"):
+        assert_close(outs["parallel"][0][0][k], p[k], "parallel/" + k)
+        for mode in ("serial", "nographs"):
+            for rnd in range(2):
+                np.testing.assert_array_equal(outs["parallel"][0][rnd][k], outs[mode][0][rnd][k], err_msg=mode + "/" + k)
+            np.testing.assert_array_equal(outs["parallel"][1][k], outs[mode][1][k], err_msg=mode + "/device/" + k)
+        np.testing.assert_array_equal(outs["parallel"][1][k], outs["parallel"][0][0][k], err_msg="device vs host/" + k)
