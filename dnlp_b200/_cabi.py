@@ -50,7 +50,7 @@ EXPORTS = [
     "dnlp_device_count", "dnlp_version", "dnlp_create", "dnlp_destroy", "dnlp_last_error",
     "dnlp_eval_f", "dnlp_eval_grad", "dnlp_eval_g", "dnlp_eval_jac", "dnlp_eval_hess", "dnlp_eval_all",
     "dnlp_host_alloc", "dnlp_host_free", "dnlp_upload_point", "dnlp_run_device", "dnlp_profile_instrs",
-    "dnlp_read_output", "dnlp_kernel_launches", "dnlp_set_cache", "dnlp_set_graphs", "dnlp_set_parallel", "dnlp_set_dynamic", "dnlp_eval_dyn", "dnlp_instr_kernel", "dnlp_run", "dnlp_output_ptr",
+    "dnlp_read_output", "dnlp_kernel_launches", "dnlp_set_cache", "dnlp_set_graphs", "dnlp_set_parallel", "dnlp_set_windows", "dnlp_set_dynamic", "dnlp_eval_dyn", "dnlp_instr_kernel", "dnlp_run", "dnlp_output_ptr",
     "dnlp_batch_create", "dnlp_batch_destroy", "dnlp_batch_last_error", "dnlp_batch_eval", "dnlp_batch_upload",
     "dnlp_batch_run_device", "dnlp_batch_profile_instrs", "dnlp_batch_kernel_launches",
 ]
@@ -95,6 +95,7 @@ def lib():
     L.dnlp_set_cache.argtypes = [vp, C.c_int32]
     L.dnlp_set_graphs.argtypes = [vp, C.c_int32]
     L.dnlp_set_parallel.argtypes = [vp, C.c_int32]
+    L.dnlp_set_windows.argtypes = [vp, C.c_int32]
     L.dnlp_run.argtypes = [vp, C.c_int32, c_f64p, c_f64p, C.c_double]
     L.dnlp_output_ptr.argtypes = [vp, C.c_int32]
     L.dnlp_output_ptr.restype = vp

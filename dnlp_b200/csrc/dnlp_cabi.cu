@@ -7,6 +7,7 @@
 #include "../../include/dnlp_b200.h"
 #include "dnlp_kernels.cuh"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -42,6 +43,14 @@ struct DevInstr {
   bool const_coef = false;
   int64_t s0 = 0, s1 = 0;
   double c0 = 1.0;
+  // shared-memory gather window (poly_rows_win_kernel): slots [win0, win0 + winW) cover most gathers
+  int win0 = -1, winW = 0;
+  // flat term-streaming kernel (poly_flat_kernel): per-chunk first row, continuation partials
+  bool flat = false;
+  int32_t *chunk_row0 = nullptr;       // nchunks + 1: first row of every chunk
+  int64_t *chunk_term0 = nullptr;      // nchunks: first term of the chunk's window (even)
+  int64_t nchunks = 0;
+  int pad_shift = 31;
 };
 
 // All x-only elementwise instructions of one program, fused into a single launch.
@@ -101,6 +110,11 @@ struct dnlp_oracle {
   int cur_lane = 0;
   std::vector<cudaEvent_t> ev_pool;    // capture-time dependency markers
   bool parallel_enabled = true;
+  bool win_enabled = true;             // shared-memory gather windows (poly_rows_win_kernel)
+  bool fuse_enabled = true;            // family fusion of phi / phi' / phi'' in the elementwise batch
+  bool flat_enabled = true;            // flat term-streaming SpMV (poly_flat_kernel)
+  int64_t flat_min_terms = 1 << 18;
+  int64_t win_min_terms = 1 << 18;     // smaller instructions are launch-bound either way
 
   template <typename T>
   int upload(const T *host, int64_t count, T **dev) {
@@ -180,6 +194,69 @@ void launch_poly_g(const dnlp_oracle *o, const DevInstr &I, double *dst, int gri
 #undef LP
 }
 
+template <int G>
+void launch_poly_win_g(const dnlp_oracle *o, const DevInstr &I, double *dst, int grid, int threads, size_t smem) {
+  const dnlp_instr_desc &d = I.d;
+  const bool uni = d.ptr == nullptr;
+#define LW(H, Un)                                                                                        \
+  poly_rows_win_kernel<G, 2, H, Un><<<grid, threads, smem, o->cur>>>(o->V, dst, d.ptr, d.row_len, d.coef, \
+                                                                     d.f1, d.f2, d.pos, d.count,         \
+                                                                     d.accumulate, I.win0, I.winW)
+  if (I.has_f2) { if (uni) LW(true, true); else LW(true, false); }
+  else { if (uni) LW(false, true); else LW(false, false); }
+#undef LW
+}
+
+template <int G>
+cudaError_t set_win_attrs_g() {
+  cudaError_t e = cudaSuccess;
+#define SA(H, Un)                                                                                             \
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(poly_rows_win_kernel<G, 2, H, Un>,                           \
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);    \
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(poly_rows_win_kernel<G, 2, H, Un>,                           \
+                                                 cudaFuncAttributePreferredSharedMemoryCarveout, 100)
+  SA(true, true); SA(true, false); SA(false, true); SA(false, false);
+#undef SA
+  return e;
+}
+
+// Bucketed histogram of the gathered slots; the window is the narrowest of three widths that still
+// holds (almost) as many gathers as the widest one, provided that is at least half of them.
+void choose_window(const int32_t *f1, const int32_t *f2, int64_t nterms, int64_t nslots, int *w0, int *W) {
+  *w0 = -1; *W = 0;
+  constexpr int BK = 256;
+  const int64_t nb = nslots / BK + 1;
+  std::vector<int64_t> cnt((size_t)nb + 1, 0);
+  int64_t total = 0;
+  for (int64_t t = 0; t < nterms; ++t) {
+    if (f1[t] >= 0) { ++cnt[f1[t] / BK]; ++total; }
+    if (f2 && f2[t] >= 0) { ++cnt[f2[t] / BK]; ++total; }
+  }
+  if (total == 0) return;
+  const int widths[3] = {17, 33, 65};         // buckets: 34 KB, 68 KB, 133 KB of doubles
+  int64_t best[3], at[3];
+  for (int w = 0; w < 3; ++w) {
+    const int64_t Wb = widths[w] < nb ? widths[w] : nb;
+    int64_t run = 0;
+    for (int64_t b = 0; b < Wb; ++b) run += cnt[b];
+    best[w] = run; at[w] = 0;
+    for (int64_t b = Wb; b < nb; ++b) {
+      run += cnt[b] - cnt[b - Wb];
+      if (run > best[w]) { best[w] = run; at[w] = b - Wb + 1; }
+    }
+  }
+  if (2 * best[2] < total) return;
+  for (int w = 0; w < 3; ++w) {
+    if (10 * best[w] >= 9 * best[2]) {
+      const int64_t Wb = widths[w] < nb ? widths[w] : nb;
+      int64_t lo = at[w] * BK, hi = lo + Wb * BK;
+      if (hi > nslots) hi = nslots;
+      *w0 = (int)lo; *W = (int)(hi - lo);
+      return;
+    }
+  }
+}
+
 }  // namespace
 
 int dnlp_oracle::launch(DevInstr &I) {
@@ -238,11 +315,49 @@ int dnlp_oracle::launch(DevInstr &I) {
         if (I.kname.empty()) I.kname = std::string("poly1_stream_kernel<4, ") + (I.has_f2 ? "1" : "0") + ">";
         break;
       }
+      if (I.flat && flat_enabled) {
+        const bool win = I.winW > 0 && win_enabled && I.winW <= 33 * 256;
+        const size_t smem = win ? (size_t)I.winW * sizeof(double) : 0;
+        const int per_sm = smem > 36 * 1024 ? 2 : 4;
+        const int64_t nchunks = I.nchunks;
+        const int64_t need = (nchunks + dnlp::FLAT_WARPS - 1) / dnlp::FLAT_WARPS;
+        const int grid = (int)(need < (int64_t)sm_count * per_sm ? need : (int64_t)sm_count * per_sm);
+#define LF(H, Wn)                                                                                          \
+        poly_flat_kernel<H, Wn><<<grid, 256, smem, cur>>>(V, dst, d.ptr, d.row_len, d.coef, d.f1, d.f2, d.pos, \
+                                                          d.nterms, d.accumulate, I.chunk_row0, I.chunk_term0, \
+                                                          nchunks, I.win0, win ? I.winW : 0, I.pad_shift)
+        if (I.has_f2) { if (win) LF(true, true); else LF(true, false); }
+        else { if (win) LF(false, true); else LF(false, false); }
+#undef LF
+        if (I.kname.empty())
+          I.kname = std::string("poly_flat_kernel<") + (I.has_f2 ? "1" : "0") + ", " + (win ? "1" : "0") + ">";
+        break;
+      }
       // lanes per row: largest power of two <= 0.8 * mean row length (measured on B200 with
       // tools/kbench: L=5 -> 4, L=10 -> 8, L=16/17 -> 8; 16 lanes on 16-term rows lose 2x),
       // two rows in flight per lane group
       int G = 1;
       while (G < 32 && (double)(2 * G) <= 0.8 * I.mean_len) G <<= 1;
+      if (I.winW > 0 && win_enabled) {
+        // gathered window staged in shared memory: persistent CTAs, as many per SM as the window allows
+        const size_t smem = (size_t)I.winW * sizeof(double);
+        const int threads = smem > 72 * 1024 ? 1024 : 512;
+        const int per_sm = smem > 72 * 1024 ? 1 : (smem > 36 * 1024 ? 3 : 4);
+        int64_t need = ((d.count + 1) / 2 * G + threads - 1) / threads;
+        int grid = (int)(need < (int64_t)sm_count * per_sm ? (need < 1 ? 1 : need) : (int64_t)sm_count * per_sm);
+        switch (G) {
+          case 1: launch_poly_win_g<1>(this, I, dst, grid, threads, smem); break;
+          case 2: launch_poly_win_g<2>(this, I, dst, grid, threads, smem); break;
+          case 4: launch_poly_win_g<4>(this, I, dst, grid, threads, smem); break;
+          case 8: launch_poly_win_g<8>(this, I, dst, grid, threads, smem); break;
+          case 16: launch_poly_win_g<16>(this, I, dst, grid, threads, smem); break;
+          default: launch_poly_win_g<32>(this, I, dst, grid, threads, smem); break;
+        }
+        if (I.kname.empty())
+          I.kname = "poly_rows_win_kernel<" + std::to_string(G) + ", 2, " + (I.has_f2 ? "1" : "0") + ", " +
+                    (d.ptr == nullptr ? "1" : "0") + ">";
+        break;
+      }
       int grid = grid_for((d.count + 1) / 2, G);
       switch (G) {
         case 1: launch_poly_g<1>(this, I, dst, grid); break;
@@ -323,6 +438,14 @@ int dnlp_oracle::build_batches() {
       B.members.push_back(id);
     }
     if (B.members.size() < 2) { B.members.clear(); continue; }   // a single instruction gains nothing
+    for (auto &e : descs) {          // outputs of one family share their transcendental calls
+      e.group = dnlp::GRP_NONE;
+      if (e.nout < 2 || !fuse_enabled) continue;
+      const int fam = dnlp::elem_family(e.fcode[0]);
+      bool same = fam != dnlp::GRP_NONE;
+      for (int k = 1; k < e.nout; ++k) same = same && dnlp::elem_family(e.fcode[k]) == fam;
+      if (same) e.group = fam;
+    }
     int64_t tiles = 0;
     for (auto &e : descs) { e.tile0 = tiles; tiles += (e.count + dnlp::ELEM_TILE - 1) / dnlp::ELEM_TILE; }
     B.ndesc = (int)descs.size();
@@ -598,6 +721,11 @@ static int create_impl(dnlp_oracle *o, const dnlp_tape_desc *t) {
   CK(cudaEventCreate(&o->ev0));
   CK(cudaEventCreate(&o->ev1));
   o->n = t->n; o->m = t->m; o->nslots = t->nslots; o->nnz_jac = t->nnz_jac; o->nnz_hess = t->nnz_hess;
+  if (const char *e = getenv("DNLP_WIN_MIN_TERMS")) o->win_min_terms = atoll(e);   // tests: force the window path
+  if (const char *e = getenv("DNLP_FLAT_MIN_TERMS")) o->flat_min_terms = atoll(e);  // tests: force the flat kernel
+  if (const char *e = getenv("DNLP_NO_FLAT")) o->flat_enabled = atoi(e) == 0;
+  if (const char *e = getenv("DNLP_NO_WINDOWS")) o->win_enabled = atoi(e) == 0;
+  if (const char *e = getenv("DNLP_NO_ELEM_FUSION")) o->fuse_enabled = atoi(e) == 0;  // tests / A-B measurements
 
   void *p = nullptr;
   CK(cudaMalloc(&p, (size_t)(t->nslots + 2) * sizeof(double)));
@@ -669,6 +797,52 @@ static int create_impl(dnlp_oracle *o, const dnlp_tape_desc *t) {
         D.s1 = h.f2 ? h.f2[0] : 0;
         D.c0 = h.coef[0];
       }
+      // flat term streaming for SpMV-shaped instructions: rows are cut into chunks whose terms lie
+      // inside one window of FLAT_CHUNK terms that starts at an even term index
+      if (h.nterms >= o->flat_min_terms && h.count >= 2 && !(h.ptr == nullptr && h.row_len == 1) &&
+          D.mean_len <= 64.0 && h.count < ((int64_t)1 << 31) - 1) {
+        auto rb = [&](int64_t r) -> int64_t { return h.ptr ? h.ptr[r] : r * (int64_t)h.row_len; };
+        std::vector<int32_t> row0;
+        std::vector<int64_t> term0;
+        bool ok = true;
+        int64_t R = 0;
+        while (R < h.count) {
+          const int64_t a0 = rb(R) & ~(int64_t)1;
+          int64_t Rn = R;
+          while (Rn < h.count && rb(Rn + 1) <= a0 + dnlp::FLAT_CHUNK) ++Rn;
+          if (Rn == R) { ok = false; break; }            // a row longer than the window
+          row0.push_back((int32_t)R);
+          term0.push_back(a0);
+          R = Rn;
+        }
+        if (ok) {
+          row0.push_back((int32_t)h.count);
+          D.nchunks = (int64_t)term0.size();
+          if (o->upload(row0.data(), (int64_t)row0.size(), &D.chunk_row0)) return 1;
+          if (o->upload(term0.data(), (int64_t)term0.size(), &D.chunk_term0)) return 1;
+          // shared-memory padding for the row sums: thread j starts at j * L; pick the padding whose
+          // 16 consecutive row starts spread best over the 16 double-wide banks
+          const int64_t L = (int64_t)(D.mean_len + 0.5) > 0 ? (int64_t)(D.mean_len + 0.5) : 1;
+          int best_conf = 1 << 30;
+          const int shifts[3] = {31, 4, 5};
+          for (int si = 0; si < 3; ++si) {
+            int hits[16] = {0};
+            int conf = 0;
+            for (int j = 0; j < 16; ++j) {
+              const int64_t k = j * L;
+              const int64_t q = k + (shifts[si] >= 31 ? 0 : ((k >> shifts[si]) << 1));
+              conf = std::max(conf, ++hits[q & 15]);
+            }
+            if (conf < best_conf) { best_conf = conf; D.pad_shift = shifts[si]; }
+          }
+          D.flat = true;
+        }
+      }
+      // long multi-term row sets whose gathers concentrate on a short slot range (SpMV against a
+      // small x): stage that range in shared memory
+      const bool rows_path = !(h.count == 1 && h.nterms >= 2048 && !h.pos) && !(h.ptr == nullptr && h.row_len == 1);
+      if (rows_path && h.nterms >= o->win_min_terms && !D.contig)
+        choose_window(h.f1, h.f2, h.nterms, t->nslots, &D.win0, &D.winW);
     } else if (h.kind == DNLP_GEMV) {
       if (o->upload(h.Q, h.count * h.ncols, const_cast<double **>(&D.d.Q))) return 1;
     } else if (h.kind == DNLP_SCALE) {
@@ -687,6 +861,12 @@ static int create_impl(dnlp_oracle *o, const dnlp_tape_desc *t) {
   // opt in to > 48 KB dynamic shared memory for the GEMV x tile
   CK(cudaFuncSetAttribute(dnlp::gemv_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
   CK(cudaFuncSetAttribute(dnlp::gemv_cta_kernel<4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+  CK(set_win_attrs_g<1>()); CK(set_win_attrs_g<2>()); CK(set_win_attrs_g<4>());
+  CK(set_win_attrs_g<8>()); CK(set_win_attrs_g<16>()); CK(set_win_attrs_g<32>());
+  CK(cudaFuncSetAttribute(dnlp::poly_flat_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+  CK(cudaFuncSetAttribute(dnlp::poly_flat_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+  CK(cudaFuncSetAttribute(dnlp::poly_flat_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  CK(cudaFuncSetAttribute(dnlp::poly_flat_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   CK(cudaStreamSynchronize(o->stream));
   return 0;
 }
@@ -826,6 +1006,8 @@ int dnlp_run_device(dnlp_oracle *o, int32_t prog_mask, int32_t iters, float *ela
   // once into a CUDA graph and replayed `iters` times
   int progs[DNLP_NPROG], nprogs = 0;
   for (int p = 0; p < DNLP_NPROG; ++p) if (prog_mask & (1 << p)) progs[nprogs++] = p;
+  if ((prog_mask & 0x1F) == 0x1F) { progs[0] = DNLP_PROG_ALL; nprogs = 1; }   // the union: every instruction once,
+                                                                             // one elementwise batch for all five
   auto step = [&]() -> int {
     std::fill(o->valid.begin(), o->valid.end(), 0);   // a new point every step: nothing is reused
     return o->run_programs(progs, nprogs, false);     // one sequence: independent parts overlap
@@ -914,6 +1096,16 @@ int dnlp_set_parallel(dnlp_oracle *o, int32_t enabled) {
   o->parallel_enabled = enabled != 0;
   for (auto &kv : o->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   o->graphs.clear();                                  // captured with the other setting
+  return 0;
+}
+
+int dnlp_set_windows(dnlp_oracle *o, int32_t enabled) {
+  ENTER(o);
+  CK(cudaStreamSynchronize(o->stream));
+  o->win_enabled = enabled != 0;
+  for (auto &kv : o->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  o->graphs.clear();
+  for (auto &I : o->instrs) I.kname.clear();
   return 0;
 }
 

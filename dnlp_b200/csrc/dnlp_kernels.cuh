@@ -44,7 +44,19 @@ __device__ __forceinline__ double apply_fn(double a, double b, double p) {
   }
   else if constexpr (F == F_LOGISTIC_D1) { double e = exp(a); return e / (1.0 + e); }          // logistic.py:111-112
   else if constexpr (F == F_LOGISTIC_D2) { double e = exp(a); double d = e + 1.0; return e / (d * d); }  // logistic.py:101-102
-  else if constexpr (F == F_POW) return pow(a, p);                      // elementwise/power.py:188,420,448
+  else if constexpr (F == F_POW) {                                      // elementwise/power.py:188,420,448
+    // the exponents that dominate in practice (squares, cubes and their derivatives p-1, p-2) as
+    // exact products: same value as pow() to within 1 ulp, ~100x fewer fp64 instructions.  `p` is
+    // uniform over a launch, so these branches do not diverge.
+    if (p == 2.0) return a * a;
+    if (p == 1.0) return a;
+    if (p == 0.0) return 1.0;
+    if (p == 3.0) return a * a * a;
+    if (p == 4.0) { const double q = a * a; return q * q; }
+    if (p == -1.0) return 1.0 / a;
+    if (p == 0.5) return a == -INFINITY ? INFINITY : sqrt(a);
+    return pow(a, p);
+  }
   else if constexpr (F == F_SIN) return sin(a);                         // elementwise/trig.py:36
   else if constexpr (F == F_COS) return cos(a);                         // elementwise/trig.py:116,102
   else if constexpr (F == F_NEG_SIN) return -sin(a);                    // elementwise/trig.py:93,182
@@ -523,6 +535,198 @@ poly_rows_kernel(const double *__restrict__ V, double *__restrict__ dst, const i
   }
 }
 
+// ---- POLY v4: the gathered window lives in shared memory ------------------------------------------
+// SpMV against a SHORT vector (C3: A~ x with x in R^4096): every gather of poly_rows_kernel is a
+// 32-byte L2 sector for 8 useful bytes, which makes the kernel L2-bandwidth bound (34 M gathers =
+// 1.1 GB of L2->SM traffic next to 0.44 GB of streamed coefficients / indices).  Here each persistent
+// CTA first copies the window V[w0, w0 + W) - chosen on the host so that it covers most gathered
+// slots - into shared memory; gathers inside the window never leave the SM, the rest (one lifted
+// slot per row in C3) still go to L2.  Rows are dealt to lane groups exactly as in poly_rows_kernel,
+// so the summation order, and therefore every bit of the result, is the same.
+template <int G, int R, bool HAS_F2, bool UNIFORM>
+__global__ void __launch_bounds__(1024)
+poly_rows_win_kernel(const double *__restrict__ V, double *__restrict__ dst, const int64_t *__restrict__ ptr,
+                     int row_len, const double *__restrict__ coef, const int32_t *__restrict__ f1,
+                     const int32_t *__restrict__ f2, const int32_t *__restrict__ pos, int64_t count,
+                     int accumulate, int w0, int W) {
+  extern __shared__ __align__(16) double win[];
+  for (int j = threadIdx.x; j < W; j += blockDim.x) win[j] = V[w0 + j];
+  __syncthreads();
+  const uint64_t pf = l2_policy_evict_first(), pl = l2_policy_evict_last();
+  auto gather = [&](int idx) -> double {
+    if (idx < 0) return 1.0;
+    const unsigned rel = (unsigned)(idx - w0);
+    return rel < (unsigned)W ? win[rel] : ld_keep_f64(V + idx, pl);
+  };
+  const int lane = threadIdx.x & (G - 1);
+  const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+  const int64_t ngroups = ((int64_t)gridDim.x * blockDim.x) / G;
+  for (int64_t base = group; base < count; base += R * ngroups) {
+    int64_t t[R], t1[R];
+    double acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int64_t row = base + r * ngroups;
+      acc[r] = 0.0;
+      if (row < count) {
+        if (UNIFORM) { t[r] = row * (int64_t)row_len; t1[r] = t[r] + row_len; }
+        else { t[r] = __ldg(ptr + row); t1[r] = __ldg(ptr + row + 1); }
+        t[r] += lane;
+      } else { t[r] = 0; t1[r] = 0; }
+    }
+    bool more = true;
+    while (more) {
+      double c[R];
+      int a[R], b[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const bool ok = t[r] < t1[r];
+        c[r] = ok ? ld_stream_f64(coef + t[r], pf) : 0.0;
+        a[r] = ok ? ld_stream_s32(f1 + t[r], pf) : -1;
+        b[r] = (HAS_F2 && ok) ? ld_stream_s32(f2 + t[r], pf) : -1;
+      }
+      more = false;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        double v = c[r] * gather(a[r]);
+        if (HAS_F2) v *= gather(b[r]);
+        acc[r] += v;
+        t[r] += G;
+        more |= t[r] < t1[r];
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      double v = acc[r];
+#pragma unroll
+      for (int s = G >> 1; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s, G);
+      const int64_t row = base + r * ngroups;
+      if (lane == 0 && row < count) {
+        const int64_t d = pos ? (int64_t)__ldg(pos + row) : row;
+        dst[d] = accumulate ? dst[d] + v : v;
+      }
+    }
+  }
+}
+
+// ---- POLY v5: flat term streaming + in-warp segmented row sums --------------------------------------
+// poly_rows_kernel spends ~2 warp instructions per term (64-bit cursors, per-row predicates, shuffle
+// trees) and keeps only two 12-byte loads per lane in flight: on the C3 SpMV ncu shows 53 % issue
+// utilisation with every warp stalled on the scoreboard, DRAM at 61 %.  Here the host cuts the ROWS
+// into chunks whose terms fit a window of FLAT_CHUNK consecutive terms starting at an even term
+// index (chunk_row0 / chunk_term0), and each WARP handles one chunk at a time, on its own:
+//   1. every lane issues 128-bit coefficient loads and 64-bit index loads for 8 terms at once
+//      (perfectly coalesced, 96+ bytes in flight per lane),
+//   2. gathers the 8 (or 16) factors - from the shared-memory window when the host found one -
+//      and parks the products in the warp's slice of shared memory at their term position,
+//   3. one lane per row adds that row's products in term order (the CPU's own CSR order).
+// No row crosses a chunk, so there is no carry, no atomics and no second pass; empty rows are fine;
+// warps never wait for each other (only __syncwarp).  Requires: no row longer than FLAT_CHUNK - 1
+// terms (the host falls back to poly_rows_kernel).
+constexpr int FLAT_CHUNK = 256;                       // terms per warp-chunk: 32 lanes x 8
+constexpr int FLAT_PROD = FLAT_CHUNK + 2 * (FLAT_CHUNK / 16) + 2;
+constexpr int FLAT_WARPS = 8;
+
+__device__ __forceinline__ int2 ld_stream_s32x2(const int2 *p, uint64_t pol) {
+  int2 v;
+  asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.s32 {%0, %1}, [%2], %3;"
+      : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol));
+  return v;
+}
+
+template <bool HAS_F2, bool WIN>
+__global__ void __launch_bounds__(FLAT_WARPS * 32, 4)
+poly_flat_kernel(const double *__restrict__ V, double *dst, const int64_t *__restrict__ ptr, int row_len,
+                 const double *__restrict__ coef, const int32_t *__restrict__ f1,
+                 const int32_t *__restrict__ f2, const int32_t *__restrict__ pos, int64_t nterms,
+                 int accumulate, const int32_t *__restrict__ chunk_row0,
+                 const int64_t *__restrict__ chunk_term0, int64_t nchunks, int w0, int W, int pad_shift) {
+  __shared__ __align__(16) double prod_all[FLAT_WARPS][FLAT_PROD];
+  extern __shared__ __align__(16) double win[];
+  if (WIN) {
+    for (int j = threadIdx.x; j < W; j += FLAT_WARPS * 32) win[j] = V[w0 + j];
+    __syncthreads();
+  }
+  const uint64_t pf = l2_policy_evict_first(), pl = l2_policy_evict_last();
+  auto gather = [&](int idx) -> double {
+    if (idx < 0) return 1.0;
+    if (WIN) {
+      const unsigned rel = (unsigned)(idx - w0);
+      if (rel < (unsigned)W) return win[rel];
+    }
+    return ld_keep_f64(V + idx, pl);
+  };
+  auto padf = [&](int k) -> int { return k + ((k >> pad_shift) << 1); };   // even k stays even
+  auto row_begin = [&](int64_t r) -> int64_t { return ptr ? __ldg(ptr + r) : r * (int64_t)row_len; };
+  const int lane = threadIdx.x & 31;
+  double *prod = prod_all[threadIdx.x >> 5];
+  const int64_t nwarps = (int64_t)gridDim.x * FLAT_WARPS;
+  int64_t c = (int64_t)blockIdx.x * FLAT_WARPS + (threadIdx.x >> 5);
+  if (c >= nchunks) return;
+  int R0 = __ldg(chunk_row0 + c), R1 = __ldg(chunk_row0 + c + 1);
+  int64_t a0 = __ldg(chunk_term0 + c);
+  while (true) {
+    // descriptors of this warp's next chunk: requested now, needed after this one is done
+    const int64_t cn = c + nwarps;
+    int nR0 = 0, nR1 = 0;
+    int64_t na0 = 0;
+    if (cn < nchunks) { nR0 = __ldg(chunk_row0 + cn); nR1 = __ldg(chunk_row0 + cn + 1); na0 = __ldg(chunk_term0 + cn); }
+    // the row this lane sums first (its bounds travel together with the term streams)
+    int64_t s = 0, e = 0;
+    if (R0 + lane < R1) { s = row_begin(R0 + lane); e = row_begin(R0 + lane + 1); }
+    // ---- 1 + 2: stream the terms, gather, products to shared memory -----------------------------
+    if (a0 + FLAT_CHUNK <= nterms) {
+      const double2 *c2 = reinterpret_cast<const double2 *>(coef + a0);
+      const int2 *a2 = reinterpret_cast<const int2 *>(f1 + a0);
+      const int2 *b2 = reinterpret_cast<const int2 *>(f2 + a0);
+      double2 cv[4];
+      int2 av[4], bv[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        cv[j] = ld_stream_f64x2(c2 + j * 32 + lane, pf);
+        av[j] = ld_stream_s32x2(a2 + j * 32 + lane, pf);
+        if (HAS_F2) bv[j] = ld_stream_s32x2(b2 + j * 32 + lane, pf);
+      }
+      double gx[4], gy[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { gx[j] = gather(av[j].x); gy[j] = gather(av[j].y); }
+      if (HAS_F2) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { gx[j] *= gather(bv[j].x); gy[j] *= gather(bv[j].y); }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int q = padf(2 * (j * 32 + lane));
+        *reinterpret_cast<double2 *>(prod + q) = make_double2(cv[j].x * gx[j], cv[j].y * gy[j]);
+      }
+    } else {                                   // the window would run past the last term
+      for (int k = lane; k < (int)(nterms - a0); k += 32) {
+        double v = ld_stream_f64(coef + a0 + k, pf) * gather(ld_stream_s32(f1 + a0 + k, pf));
+        if (HAS_F2) v *= gather(ld_stream_s32(f2 + a0 + k, pf));
+        prod[padf(k)] = v;
+      }
+    }
+    __syncwarp();
+    // ---- 3: one lane per row, terms added in order --------------------------------------------------
+    for (int r = R0 + lane; r < R1; r += 32) {
+      if (r != R0 + lane) { s = row_begin(r); e = row_begin(r + 1); }
+      int k = (int)(s - a0);
+      const int ke = (int)(e - a0);
+      double acc = 0.0;
+      for (; k + 4 <= ke; k += 4) {            // four independent loads, one ordered chain of adds
+        const double p0 = prod[padf(k)], p1 = prod[padf(k + 1)], p2 = prod[padf(k + 2)], p3 = prod[padf(k + 3)];
+        acc = (((acc + p0) + p1) + p2) + p3;
+      }
+      for (; k < ke; ++k) acc += prod[padf(k)];
+      const int64_t d = pos ? (int64_t)__ldg(pos + r) : r;
+      dst[d] = accumulate ? dst[d] + acc : acc;
+    }
+    if (cn >= nchunks) break;
+    c = cn; R0 = nR0; R1 = nR1; a0 = na0;
+    __syncwarp();
+  }
+}
+
 // ---- K1 batched: every x-only elementwise segment of a program in ONE launch ----------------
 // A descriptor is one contiguous segment with up to three outputs that share the loads of the
 // source (phi, phi', phi'' of the same atom: x is read once).  Tiles of all descriptors are dealt
@@ -533,7 +737,79 @@ struct ElemDesc {
   double param[3];
   int32_t fcode[3];
   int32_t nout, a_stride, b_stride;
+  int32_t group;                           // GRP_*: outputs of one family share their transcendental calls
 };
+
+// Families whose value / first / second derivative share sub-expressions (phi, phi', phi'' of one atom
+// at the same argument).  The formulas stay the reference's; only the common calls are made once.
+enum : int { GRP_NONE = 0, GRP_TRIG = 1, GRP_LOGISTIC = 2, GRP_TANH = 3 };
+
+__host__ __device__ inline int elem_family(int f) {
+  if (f == F_SIN || f == F_COS || f == F_NEG_SIN || f == F_NEG_COS) return GRP_TRIG;
+  if (f == F_LOGISTIC || f == F_LOGISTIC_D1 || f == F_LOGISTIC_D2) return GRP_LOGISTIC;
+  if (f == F_TANH || f == F_TANH_D1 || f == F_TANH_D2) return GRP_TANH;
+  return GRP_NONE;
+}
+
+template <int GRP>
+__device__ __forceinline__ void fused_point(double a, const ElemDesc &d, bool want_val, double (&r)[3]) {
+  if constexpr (GRP == GRP_TRIG) {                      // trig.py:36,93,102,116,173,182
+    double sn, cs;
+    sincos(a, &sn, &cs);
+#pragma unroll
+    for (int o = 0; o < 3; ++o) {
+      const int f = d.fcode[o];
+      r[o] = f == F_SIN ? sn : (f == F_COS ? cs : (f == F_NEG_SIN ? -sn : -cs));
+    }
+  } else if constexpr (GRP == GRP_LOGISTIC) {           // logistic.py:39,101-102,111-112
+    const double e = exp(a);
+    const double dd = e + 1.0;
+    double val = 0.0;
+    if (want_val) val = isnan(a) ? a : fmax(a, 0.0) + log1p(a <= 0.0 ? e : 1.0 / e);   // exp(-|a|) from exp(a)
+#pragma unroll
+    for (int o = 0; o < 3; ++o) {
+      const int f = d.fcode[o];
+      r[o] = f == F_LOGISTIC ? val : (f == F_LOGISTIC_D1 ? e / dd : e / (dd * dd));
+    }
+  } else {                                              // hyperbolic.py:111,163,172
+    const double c = cosh(a);
+    const double t = want_val ? tanh(a) : 0.0;
+    const double c2 = c * c;
+#pragma unroll
+    for (int o = 0; o < 3; ++o) {
+      const int f = d.fcode[o];
+      r[o] = f == F_TANH ? t : (f == F_TANH_D1 ? 1.0 / c2 : -2.0 * (t / c2));
+    }
+  }
+}
+
+template <int GRP>
+__device__ __forceinline__ void fused_tile(double *__restrict__ V, const ElemDesc &d, int64_t e0, int64_t e1,
+                                           bool vec_ok) {
+  const double *__restrict__ A = V + d.a_off;
+  bool want_val = false;                  // does any output need the value-only call (log1p / tanh)?
+  for (int o = 0; o < d.nout; ++o)
+    want_val = want_val || d.fcode[o] == F_LOGISTIC || d.fcode[o] == F_TANH || d.fcode[o] == F_TANH_D2;
+  if (vec_ok) {
+    for (int64_t k = e0 + 2 * threadIdx.x; k < e1; k += 512) {
+      const double2 a = *reinterpret_cast<const double2 *>(A + k);
+      double rx[3], ry[3];
+      fused_point<GRP>(a.x, d, want_val, rx);
+      fused_point<GRP>(a.y, d, want_val, ry);
+#pragma unroll
+      for (int o = 0; o < 3; ++o)
+        if (o < d.nout) *reinterpret_cast<double2 *>(V + d.dst_off[o] + k) = make_double2(rx[o], ry[o]);
+    }
+  } else {
+    for (int64_t k = e0 + threadIdx.x; k < e1; k += 256) {
+      double r[3];
+      fused_point<GRP>(A[k * d.a_stride], d, want_val, r);
+#pragma unroll
+      for (int o = 0; o < 3; ++o)
+        if (o < d.nout) V[d.dst_off[o] + k] = r[o];
+    }
+  }
+}
 
 constexpr int ELEM_TILE = 2048;            // elements per tile: 256 threads x 4 x double2 (8192 measured no faster: fp64 math bound)
 
@@ -582,6 +858,9 @@ elem_batch_kernel(double *__restrict__ V, const ElemDesc *__restrict__ descs, in
     bool vec_ok = d.a_stride == 1 && (d.a_off & 1) == 0 && (d.b_stride == 0 || (d.b_off & 1) == 0) &&
                   ((e1 - e0) & 1) == 0;
     for (int o = 0; o < d.nout; ++o) vec_ok = vec_ok && (d.dst_off[o] & 1) == 0;
+    if (d.group == GRP_TRIG) { fused_tile<GRP_TRIG>(V, d, e0, e1, vec_ok); continue; }
+    if (d.group == GRP_LOGISTIC) { fused_tile<GRP_LOGISTIC>(V, d, e0, e1, vec_ok); continue; }
+    if (d.group == GRP_TANH) { fused_tile<GRP_TANH>(V, d, e0, e1, vec_ok); continue; }
     // outputs that share a source re-read the 16 KB tile from L1, not from HBM
     for (int o = 0; o < d.nout; ++o) {
       switch (d.fcode[o]) {

@@ -234,5 +234,9 @@ class GpuOracles:
         """Parallel graph branches for independent instructions (on by default)."""
         self.dev.check(self.dev._L.dnlp_set_parallel(self.dev.h, int(bool(enabled))))
 
+    def set_windows(self, enabled):
+        """Shared-memory gather windows for SpMV against a short vector (on by default)."""
+        self.dev.check(self.dev._L.dnlp_set_windows(self.dev.h, int(bool(enabled))))
+
     def set_cache(self, enabled):
         self.dev._L.dnlp_set_cache(self.dev.h, int(bool(enabled)))

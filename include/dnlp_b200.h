@@ -152,6 +152,7 @@ const char *dnlp_instr_kernel(dnlp_oracle *o, int32_t instr);           /* kerne
 int dnlp_set_cache(dnlp_oracle *o, int32_t enabled);                    /* x-keyed forward cache on/off */
 int dnlp_set_graphs(dnlp_oracle *o, int32_t enabled);                   /* CUDA-graph replay of launch sequences on/off */
 int dnlp_set_parallel(dnlp_oracle *o, int32_t enabled);                 /* parallel graph branches for independent instructions on/off */
+int dnlp_set_windows(dnlp_oracle *o, int32_t enabled);                  /* shared-memory gather windows (SpMV against a short vector) on/off */
 
 /* ---- batched multi-start evaluation (BASELINE config 4; the reference's serial `best_of` loop,
  *      cvxpy/problems/problem.py:1249-1275, evaluates one start at a time) ----

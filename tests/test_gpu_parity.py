@@ -381,3 +381,151 @@ def test_gpu_parallel_graph_branches_equal_serial(name, gpu_mod):
                 np.testing.assert_array_equal(outs["parallel"][0][rnd][k], outs[mode][0][rnd][k], err_msg=mode + "/" + k)
             np.testing.assert_array_equal(outs["parallel"][1][k], outs[mode][1][k], err_msg=mode + "/device/" + k)
         np.testing.assert_array_equal(outs["parallel"][1][k], outs["parallel"][0][0][k], err_msg="device vs host/" + k)
+
+
+@pytest.mark.parametrize("name", ["c3_logistic_small", "c5_microbench_small", "portfolio_socp", "matmul_const_sides",
+                                  "nmf_kl_graph_form", "clnlbeam"])
+def test_gpu_shared_memory_gather_window(name, gpu_mod, monkeypatch):
+    """SpMV-shaped instructions with the gathered slot window staged in shared memory
+    (poly_rows_win_kernel), forced on for small problems.  Same lane-group mapping as the plain
+    kernel, so the results must be bit-identical to it, and within 1e-10 of the reference."""
+    monkeypatch.setenv("DNLP_WIN_MIN_TERMS", "1")
+    g = Golden(name)
+    o = gpu_mod(g.problem)
+    try:
+        for i, p in enumerate(g.points):
+            res = {"f": o.objective(p["x"]), "grad": o.gradient(p["x"]).copy(), "g": o.constraints(p["x"]).copy(),
+                   "jac": np.array(o.jacobian(p["x"]), copy=True),
+                   "hess": np.array(o.hessian(p["x"], p["lam"], float(p["sigma"])), copy=True)}
+            for k, v in res.items():
+                assert_close(v, p[k], "%s[%d]" % (k, i))
+        used = [o.instr_kernel(i) for i in range(len(o.tape.instrs))]
+        o.set_windows(False)
+        o.set_cache(False)
+        o.set_cache(True)
+        p = g.points[-1]
+        plain = {"f": o.objective(p["x"]), "grad": o.gradient(p["x"]).copy(), "g": o.constraints(p["x"]).copy(),
+                 "jac": np.array(o.jacobian(p["x"]), copy=True),
+                 "hess": np.array(o.hessian(p["x"], p["lam"], float(p["sigma"])), copy=True)}
+        for k in plain:
+            np.testing.assert_array_equal(np.asarray(res[k]).reshape(-1), np.asarray(plain[k]).reshape(-1), err_msg=k)
+    finally:
+        o.close()
+    if name in ("c3_logistic_small", "c5_microbench_small"):
+        assert any(u.startswith("poly_rows_win_kernel") for u in used), used
+
+
+def test_gpu_medium_logistic_window(gpu_mod):
+    """C3 shape at a size where the window is chosen by the production rule (>= 2^18 terms)."""
+    from dnlp_b200 import workloads as W
+    At, x0 = W.logistic_data(40000, 512, 16)
+    prob = W.logistic_regression(At, x0)
+    _cmp_with_oracle(prob, gpu_mod)
+    o = gpu_mod(prob)
+    try:
+        o.constraints(prob.x0)
+        assert any(o.instr_kernel(i) == "poly_flat_kernel<0, 1>" for i in range(len(o.tape.instrs)))
+    finally:
+        o.close()
+
+
+def test_gpu_fused_elementwise_families(gpu_mod):
+    """phi / phi' / phi'' of sin, cos, logistic and tanh segments share their transcendental calls in
+    the one-launch elementwise sweep of eval_all; per-callback evaluation runs each formula on its
+    own.  Both must match the CPU oracle, also at arguments where exp overflows / underflows, and
+    integer powers (evaluated as products) must match pow()."""
+    from dnlp_b200 import ir
+    n = 4100                                     # two tiles + a ragged tail
+    rng = np.random.default_rng(5)
+    extreme = np.array([0.0, -0.0, 1e-300, -1e-300, 36.0, -36.0, 709.0, -709.0, 720.0, -745.0, 1e4, -1e4, 1e-8])
+    def point():
+        v = rng.uniform(-3, 3, n)
+        v[:extreme.size] = extreme
+        return v
+    a, b, c, d, e = (ir.Variable(n) for _ in range(5))
+    obj = (ir.sum(ir.logistic(a)) + ir.sum(ir.tanh(b)) + ir.sum(ir.sin(c)) + ir.sum(ir.cos(d))
+           + ir.sum(ir.power(e, 3)) + ir.sum(ir.power(e, 2)) + ir.sum(ir.power(e, 4)))
+    cons = [ir.sum(ir.logistic(a)) + ir.sum(ir.cos(c)) + (-1.0), ir.sum(ir.tanh(b)) + ir.sum(ir.power(e, 2.5)) + (-2.0)]
+    x0 = np.concatenate([point(), np.clip(point(), -30, 30), point(), point(), np.abs(point()) + 0.1])
+    prob = ir.ProblemIR(obj, cons, x0=x0)
+    ref = RefOracles(prob)
+    ref.jacobianstructure(), ref.hessianstructure()
+    o = gpu_mod(prob)
+    try:
+        lam = np.array([0.7, -1.3])
+        with np.errstate(all="ignore"):
+            want = {"f": ref.objective(x0), "grad": ref.gradient(x0).copy(), "g": ref.constraints(x0),
+                    "jac": np.asarray(ref.jacobian(x0)).ravel(), "hess": np.asarray(ref.hessian(x0, lam, 0.9)).ravel()}
+        fused = o.eval_all(x0, lam, 0.9)
+        for k in want:
+            assert_close(fused[k], want[k], "fused/" + k)
+        o.set_cache(False)
+        o.set_cache(True)
+        assert_close(o.gradient(x0), want["grad"], "separate/grad")
+        assert_close(o.jacobian(x0), want["jac"], "separate/jac")
+        assert_close(o.hessian(x0, lam, 0.9), want["hess"], "separate/hess")
+        assert_close(o.objective(x0), want["f"], "separate/f")
+    finally:
+        o.close()
+
+
+@pytest.mark.parametrize("name", ["c3_logistic_small", "c5_microbench_small", "c5_lifted_small", "portfolio_socp",
+                                  "matmul_const_sides", "nmf_kl_graph_form", "clnlbeam", "c4_qcqp_small"])
+@pytest.mark.parametrize("layered", [False, True])
+def test_gpu_flat_term_streaming_kernel(name, layered, gpu_mod, monkeypatch):
+    """poly_flat_kernel (chunked term streaming + in-CTA segmented row sums) forced on for every
+    multi-term instruction, with and without the shared-memory window, plain and through the
+    scatter-accumulate second layer of large outputs."""
+    monkeypatch.setenv("DNLP_FLAT_MIN_TERMS", "1")
+    monkeypatch.setenv("DNLP_WIN_MIN_TERMS", "1")
+    if layered:
+        from dnlp_b200.rules import Builder
+        monkeypatch.setattr(Builder, "LAYER_MIN", 2)
+    g = Golden(name)
+    o = gpu_mod(g.problem)
+    try:
+        for rnd in range(2):
+            for i, p in enumerate(g.points):
+                assert_close(o.objective(p["x"]), p["f"], "f[%d]" % i)
+                assert_close(o.gradient(p["x"]), p["grad"], "grad[%d]" % i)
+                assert_close(o.constraints(p["x"]), p["g"], "g[%d]" % i)
+                assert_close(o.jacobian(p["x"]), p["jac"], "jac[%d]" % i)
+                assert_close(o.hessian(p["x"], p["lam"], float(p["sigma"])), p["hess"], "hess[%d]" % i)
+            used = [o.instr_kernel(i) for i in range(len(o.tape.instrs))]
+            o.set_windows(False)          # second round: the variant without the window
+    finally:
+        o.close()
+    if name.startswith("c"):
+        assert any(u.startswith("poly_flat_kernel") for u in used), used
+
+
+def test_gpu_flat_kernel_long_short_and_empty_rows(gpu_mod, monkeypatch):
+    """Rows that fill almost a whole 256-term chunk mixed with many short ragged rows and empty rows,
+    odd chunk starts (windows are aligned down to an even term), a partial last window; rows longer
+    than a chunk make the instruction fall back to the row kernel."""
+    from dnlp_b200 import ir
+    import scipy.sparse as sp
+    monkeypatch.setenv("DNLP_FLAT_MIN_TERMS", "1")
+    rng = np.random.default_rng(11)
+    for n, expect_flat in ((240, True), (300, False)):
+        x = ir.Variable(n)
+        A = rng.standard_normal((6, n))
+        A[1, 100:] = 0.0                                   # one short dense row between the long ones
+        B = rng.standard_normal((300, n)) * (rng.random((300, n)) < 0.02)
+        cons = [ir.matmul(ir.Constant(A), x) + ir.Constant(-np.ones(6)),
+                ir.matmul(ir.Constant(sp.csr_matrix(B)), ir.exp(x)) + ir.Constant(-np.ones(300))]
+        prob = ir.ProblemIR(ir.sum(ir.power(x, 2)), cons, x0=rng.uniform(-1, 1, n))
+        _cmp_with_oracle(prob, gpu_mod, npoints=2)
+        o = gpu_mod(prob)
+        try:
+            a = np.array(o.constraints(prob.x0), copy=True)
+            o.hessian(prob.x0, np.ones(306), 1.0)
+            g_instr = [i.id for i in o.tape.instrs if i.dst_space == 3]
+            assert all(o.instr_kernel(i).startswith("poly_flat_kernel") == expect_flat for i in g_instr), \
+                [o.instr_kernel(i) for i in g_instr]
+            for _ in range(3):                             # identical bits on every run
+                o.set_cache(False)
+                o.set_cache(True)
+                np.testing.assert_array_equal(a, o.constraints(prob.x0))
+        finally:
+            o.close()
