@@ -29,7 +29,7 @@ class InstrDesc(C.Structure):
         ("param", C.c_double), ("a_off", C.c_int64), ("b_off", C.c_int64),
         ("ptr", c_i64p), ("coef", c_f64p), ("f1", c_i32p), ("f2", c_i32p), ("pos", c_i32p),
         ("nterms", C.c_int64), ("row_len", C.c_int32), ("uses_lam", C.c_int32),
-        ("level", C.c_int32), ("reserved", C.c_int32),
+        ("level", C.c_int32), ("dep_mask", C.c_int32),
         ("Q", c_f64p), ("ncols", C.c_int64), ("x_off", C.c_int64), ("alpha", C.c_double),
         ("s_slot", C.c_int64),
         ("deps", c_i32p), ("n_deps", C.c_int64),
@@ -178,6 +178,7 @@ def make_tape_desc(tape):
         d.param, d.a_off, d.b_off = float(ins.param), int(ins.a_off), int(ins.b_off)
         d.uses_lam = int(bool(ins.uses_lam))
         d.level = int(ins.level)
+        d.dep_mask = int(ins.dep_mask)
         d.alpha, d.ncols, d.x_off, d.s_slot = float(ins.alpha), int(ins.ncols), int(ins.x_off), int(ins.s_slot)
         if ins.kind == T.K_POLY:
             lens = np.diff(ins.ptr)

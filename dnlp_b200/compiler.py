@@ -22,7 +22,7 @@ import numpy as np
 
 from . import tape as T
 from .rules import Builder
-from .symvec import SymVec
+from .symvec import NONE, SymVec
 
 
 def _closure(tape, root_ids):
@@ -50,6 +50,13 @@ def _emit_output(b, sv, space):
     const = np.where(cmask, sv.const_values(), 0.0)
     dyn = np.where(~cmask)[0]
     b.tape.dynamic[space] = dyn.astype(np.int32)
+    # entries whose every factor is the objective factor: they change only when sigma does, so a
+    # caller that keeps its output array between calls can skip them while sigma is unchanged
+    sig = b.tape.sigma_slot
+    other = np.zeros(sv.K, dtype=bool)
+    if sv.row.size:
+        other[sv.row[((sv.f1 != NONE) & (sv.f1 != sig)) | ((sv.f2 != NONE) & (sv.f2 != sig))]] = True
+    b.tape.dynamic_sigma[space] = np.where(~cmask & ~other)[0].astype(np.int32)
     if dyn.size == 0:
         return const, []
     if dyn.size == sv.K:

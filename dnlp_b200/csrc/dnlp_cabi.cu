@@ -73,7 +73,8 @@ struct dnlp_oracle {
   int64_t out_len[6] = {0, 0, 0, 0, 0, 0};
   std::vector<DevInstr> instrs;
   std::vector<int32_t> prog[DNLP_NPROG];
-  ElemBatch batch[DNLP_NPROG];
+  ElemBatch batch[2 * DNLP_NPROG];     // per program: [2p] the long segments, [2p + 1] the short ones
+  int64_t batch_split = 1 << 16;       // a short segment must not wait behind a multi-million-element sweep
   std::vector<void *> owned;           // device allocations to free
   std::vector<uint8_t> valid;          // per instruction: result valid for the current x
   double *hx = nullptr;                // pinned host copy of the last uploaded point
@@ -141,6 +142,22 @@ struct dnlp_oracle {
 
   int launch(DevInstr &I);
   int build_batches();
+  // Results that stay valid between calls: V temporaries that depend on x only (until x changes) and
+  // output-array instructions that depend on sigma only (until sigma changes; e.g. the 2*sigma*Q first
+  // layer of a dense quad_form Hessian).  The latter requires that nothing accumulates into that
+  // output array: later writers overwrite, so re-running them alone is always correct.
+  bool space_has_acc[6] = {false, false, false, false, false, false};
+  bool sigma_cache_enabled = true;
+  bool cacheable(const DevInstr &I) const {
+    if (I.d.dst_space == DNLP_DST_V) return !I.d.uses_lam;
+    return sigma_cache_enabled && I.d.dep_mask == 2 && !I.d.accumulate && !space_has_acc[I.d.dst_space];
+  }
+  void invalidate(int bits) {            // bits: 1 = x changed, 2 = sigma changed, 4 = lambda changed
+    for (size_t i = 0; i < instrs.size(); ++i) {
+      const int mk = instrs[i].d.dep_mask;
+      if (mk == 0 || (mk & bits)) valid[i] = 0;
+    }
+  }
   int run_program(int p, bool force) { return run_programs(&p, 1, force); }
   int run_programs(const int *progs, int nprogs, bool force);
   int issue_serial(const std::vector<int32_t> &nodes);
@@ -322,15 +339,23 @@ int dnlp_oracle::launch(DevInstr &I) {
         const int64_t nchunks = I.nchunks;
         const int64_t need = (nchunks + dnlp::FLAT_WARPS - 1) / dnlp::FLAT_WARPS;
         const int grid = (int)(need < (int64_t)sm_count * per_sm ? need : (int64_t)sm_count * per_sm);
-#define LF(H, Wn)                                                                                          \
-        poly_flat_kernel<H, Wn><<<grid, 256, smem, cur>>>(V, dst, d.ptr, d.row_len, d.coef, d.f1, d.f2, d.pos, \
-                                                          d.nterms, d.accumulate, I.chunk_row0, I.chunk_term0, \
-                                                          nchunks, I.win0, win ? I.winW : 0, I.pad_shift)
-        if (I.has_f2) { if (win) LF(true, true); else LF(true, false); }
-        else { if (win) LF(false, true); else LF(false, false); }
+#define LF(H, Wn, Pd)                                                                                      \
+        poly_flat_kernel<H, Wn, Pd><<<grid, 256, smem, cur>>>(V, dst, d.ptr, d.row_len, d.coef, d.f1, d.f2,    \
+                                                              d.pos, d.nterms, d.accumulate, I.chunk_row0,    \
+                                                              I.chunk_term0, nchunks, I.win0,                 \
+                                                              win ? I.winW : 0, I.pad_shift)
+        const bool pad = I.pad_shift < 31;
+        if (I.has_f2) {
+          if (win) { if (pad) LF(true, true, true); else LF(true, true, false); }
+          else { if (pad) LF(true, false, true); else LF(true, false, false); }
+        } else {
+          if (win) { if (pad) LF(false, true, true); else LF(false, true, false); }
+          else { if (pad) LF(false, false, true); else LF(false, false, false); }
+        }
 #undef LF
         if (I.kname.empty())
-          I.kname = std::string("poly_flat_kernel<") + (I.has_f2 ? "1" : "0") + ", " + (win ? "1" : "0") + ">";
+          I.kname = std::string("poly_flat_kernel<") + (I.has_f2 ? "1" : "0") + ", " + (win ? "1" : "0") + ", " +
+                    (pad ? "1" : "0") + ">";
         break;
       }
       // lanes per row: largest power of two <= 0.8 * mean row length (measured on B200 with
@@ -414,12 +439,17 @@ int dnlp_oracle::launch(DevInstr &I) {
 }
 
 int dnlp_oracle::build_batches() {
-  for (int p = 0; p < DNLP_NPROG; ++p) {
-    ElemBatch &B = batch[p];
+  // Two batches per program: consumers of a 4096-element segment (the SpMV of C3 reads x^2) start as
+  // soon as the short batch is done instead of waiting for the 2 M-element sweeps next to it.
+  for (int bi = 0; bi < 2 * DNLP_NPROG; ++bi) {
+    const int p = bi >> 1;
+    const bool want_short = (bi & 1) != 0;
+    ElemBatch &B = batch[bi];
     std::vector<dnlp::ElemDesc> descs;
     for (int32_t id : prog[p]) {
       const dnlp_instr_desc &d = instrs[id].d;
       if (d.kind != DNLP_ELEM || d.level != 0 || d.uses_lam || d.dst_space != DNLP_DST_V || d.count <= 0) continue;
+      if ((d.count < batch_split) != want_short) continue;
       bool merged = false;
       for (auto &e : descs) {        // share the source loads: phi, phi', phi'' of one segment
         if (e.nout < 3 && e.a_off == d.a_off && e.b_off == d.b_off && e.count == d.count &&
@@ -455,8 +485,8 @@ int dnlp_oracle::build_batches() {
   return 0;
 }
 
-// A node of a launch sequence: an instruction id (>= 0) or the fused elementwise batch of
-// program p, encoded as -(p + 1).
+// A node of a launch sequence: an instruction id (>= 0) or fused elementwise batch b (long / short
+// segments of program b / 2), encoded as -(b + 1).
 int dnlp_oracle::launch_node(int32_t node) {
   if (node >= 0) return launch(instrs[node]);
   ElemBatch &B = batch[-node - 1];
@@ -553,22 +583,24 @@ int dnlp_oracle::run_programs(const int *progs, int nprogs, bool force) {
   uint64_t key = 1469598103934665603ull;
   for (int q = 0; q < nprogs; ++q) {
     const int p = progs[q];
-    ElemBatch &B = batch[p];
-    bool use_batch = !B.members.empty();
-    if (use_batch) for (int32_t id : B.members) if (done[id]) { use_batch = false; break; }
-    if (use_batch) {
-      nodes.push_back(-(p + 1));
-      key = (key ^ (uint64_t)(0x10000 + p)) * 1099511628211ull;
-      for (int32_t id : B.members) done[id] = 2;      // 2: covered by a batch node of this sequence
+    for (int bi = 2 * p + 1; bi >= 2 * p; --bi) {     // the short batch first: its consumers start early
+      ElemBatch &B = batch[bi];
+      bool use_batch = !B.members.empty();
+      if (use_batch) for (int32_t id : B.members) if (done[id]) { use_batch = false; break; }
+      if (use_batch) {
+        nodes.push_back(-(bi + 1));
+        key = (key ^ (uint64_t)(0x10000 + bi)) * 1099511628211ull;
+        for (int32_t id : B.members) done[id] = 2;    // 2: covered by a batch node of this sequence
+      }
     }
     for (int32_t id : prog[p]) {
       const DevInstr &I = instrs[id];
-      const bool cacheable = !I.d.uses_lam && I.d.dst_space == DNLP_DST_V;
+      const bool keep = cacheable(I);
       if (done[id] == 2) continue;
-      if (cacheable && done[id]) continue;
+      if (keep && done[id]) continue;
       nodes.push_back(id);
       key = (key ^ (uint64_t)(id + 1)) * 1099511628211ull;
-      if (cacheable) done[id] = 1;
+      if (keep) done[id] = 1;
     }
     // a later program of the same call must not skip what a batch of this one produced, nor treat
     // it as still pending
@@ -610,8 +642,7 @@ int dnlp_oracle::run_programs(const int *progs, int nprogs, bool force) {
   // 3. bookkeeping: x-only results stay valid until x changes
   for (int32_t nd : nodes) {
     if (nd < 0) { for (int32_t id : batch[-nd - 1].members) valid[id] = 1; continue; }
-    const DevInstr &I = instrs[nd];
-    if (!I.d.uses_lam && I.d.dst_space == DNLP_DST_V) valid[nd] = 1;
+    if (cacheable(instrs[nd])) valid[nd] = 1;
   }
   return 0;
 }
@@ -657,7 +688,7 @@ int dnlp_oracle::put_x(const double *x) {
   const bool changed = stage_point(hx, x, n, have_last_x && cache_enabled);
   if (!changed && have_last_x && cache_enabled) return 0;
   if (n > 0) CK(cudaMemcpyAsync(V, hx, bytes, cudaMemcpyHostToDevice, stream));
-  std::fill(valid.begin(), valid.end(), 0);
+  invalidate(1);
   have_last_x = true;
   return 0;
 }
@@ -666,8 +697,13 @@ int dnlp_oracle::put_lam(const double *lam, double sigma) {
   // sigma and lambda are adjacent in V: [n] = sigma, [n+1, n+1+m) = lambda; staged (multi-threaded
   // for large m) into one pinned buffer and uploaded with a single copy, skipped when unchanged
   bool changed = !have_last_lam || hlam[0] != sigma;
+  if (changed) invalidate(2);
   hlam[0] = sigma;
-  if (m > 0) changed = stage_point(hlam + 1, lam, m, have_last_lam) || changed;
+  if (m > 0) {
+    const bool lam_changed = stage_point(hlam + 1, lam, m, have_last_lam);
+    if (lam_changed) invalidate(4);
+    changed = lam_changed || changed;
+  }
   if (!changed) return 0;
   CK(cudaMemcpyAsync(V + n, hlam, (size_t)(m + 1) * sizeof(double), cudaMemcpyHostToDevice, stream));
   have_last_lam = true;
@@ -722,6 +758,8 @@ static int create_impl(dnlp_oracle *o, const dnlp_tape_desc *t) {
   CK(cudaEventCreate(&o->ev1));
   o->n = t->n; o->m = t->m; o->nslots = t->nslots; o->nnz_jac = t->nnz_jac; o->nnz_hess = t->nnz_hess;
   if (const char *e = getenv("DNLP_WIN_MIN_TERMS")) o->win_min_terms = atoll(e);   // tests: force the window path
+  if (const char *e = getenv("DNLP_NO_SIGMA_CACHE")) o->sigma_cache_enabled = atoi(e) == 0;
+  if (const char *e = getenv("DNLP_BATCH_SPLIT")) o->batch_split = atoll(e);        // tests: both batches on small problems
   if (const char *e = getenv("DNLP_FLAT_MIN_TERMS")) o->flat_min_terms = atoll(e);  // tests: force the flat kernel
   if (const char *e = getenv("DNLP_NO_FLAT")) o->flat_enabled = atoi(e) == 0;
   if (const char *e = getenv("DNLP_NO_WINDOWS")) o->win_enabled = atoi(e) == 0;
@@ -852,6 +890,8 @@ static int create_impl(dnlp_oracle *o, const dnlp_tape_desc *t) {
       if (o->upload(h.pos, h.count, const_cast<int32_t **>(&D.d.pos))) return 1;
     }
   }
+  for (const DevInstr &D : o->instrs)
+    if (D.d.accumulate && D.d.dst_space >= 1 && D.d.dst_space <= 5) o->space_has_acc[D.d.dst_space] = true;
   for (int q = 0; q < DNLP_NPROG; ++q) {
     o->prog[q].assign(t->prog[q], t->prog[q] + t->prog_len[q]);
     for (int32_t id : o->prog[q])
@@ -863,10 +903,11 @@ static int create_impl(dnlp_oracle *o, const dnlp_tape_desc *t) {
   CK(cudaFuncSetAttribute(dnlp::gemv_cta_kernel<4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
   CK(set_win_attrs_g<1>()); CK(set_win_attrs_g<2>()); CK(set_win_attrs_g<4>());
   CK(set_win_attrs_g<8>()); CK(set_win_attrs_g<16>()); CK(set_win_attrs_g<32>());
-  CK(cudaFuncSetAttribute(dnlp::poly_flat_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
-  CK(cudaFuncSetAttribute(dnlp::poly_flat_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
-  CK(cudaFuncSetAttribute(dnlp::poly_flat_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  CK(cudaFuncSetAttribute(dnlp::poly_flat_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+#define FA(H, Pd)                                                                                                       \
+  CK(cudaFuncSetAttribute(dnlp::poly_flat_kernel<H, true, Pd>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024)); \
+  CK(cudaFuncSetAttribute(dnlp::poly_flat_kernel<H, true, Pd>, cudaFuncAttributePreferredSharedMemoryCarveout, 100))
+  FA(true, true); FA(true, false); FA(false, true); FA(false, false);
+#undef FA
   CK(cudaStreamSynchronize(o->stream));
   return 0;
 }

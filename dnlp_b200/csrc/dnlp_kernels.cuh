@@ -627,6 +627,15 @@ constexpr int FLAT_CHUNK = 256;                       // terms per warp-chunk: 3
 constexpr int FLAT_PROD = FLAT_CHUNK + 2 * (FLAT_CHUNK / 16) + 2;
 constexpr int FLAT_WARPS = 8;
 
+// v = take ? V[...] : other, as ONE predicated load (no branch around the asm)
+__device__ __forceinline__ double ld_keep_f64_if(const double *p, bool take, double other, uint64_t pol) {
+  double v;
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %3, 0;\n\tmov.f64 %0, %4;\n\t"
+               "@p ld.global.L2::cache_hint.f64 %0, [%1], %2;\n\t}"
+               : "=d"(v) : "l"(p), "l"(pol), "r"((int)take), "d"(other) : "memory");
+  return v;
+}
+
 __device__ __forceinline__ int2 ld_stream_s32x2(const int2 *p, uint64_t pol) {
   int2 v;
   asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.s32 {%0, %1}, [%2], %3;"
@@ -634,7 +643,7 @@ __device__ __forceinline__ int2 ld_stream_s32x2(const int2 *p, uint64_t pol) {
   return v;
 }
 
-template <bool HAS_F2, bool WIN>
+template <bool HAS_F2, bool WIN, bool PAD>
 __global__ void __launch_bounds__(FLAT_WARPS * 32, 4)
 poly_flat_kernel(const double *__restrict__ V, double *dst, const int64_t *__restrict__ ptr, int row_len,
                  const double *__restrict__ coef, const int32_t *__restrict__ f1,
@@ -648,15 +657,19 @@ poly_flat_kernel(const double *__restrict__ V, double *dst, const int64_t *__res
     __syncthreads();
   }
   const uint64_t pf = l2_policy_evict_first(), pl = l2_policy_evict_last();
+  // branch-free gather: an unconditional shared-memory read at a clamped offset plus a predicated
+  // global read for the lanes whose slot lies outside the window (index -1 = factor 1.0)
   auto gather = [&](int idx) -> double {
-    if (idx < 0) return 1.0;
     if (WIN) {
       const unsigned rel = (unsigned)(idx - w0);
-      if (rel < (unsigned)W) return win[rel];
+      const bool in = rel < (unsigned)W;
+      const double wv = win[in ? rel : 0u];
+      const bool out = !in && idx >= 0;
+      return ld_keep_f64_if(V + (out ? idx : 0), out, idx < 0 ? 1.0 : wv, pl);
     }
-    return ld_keep_f64(V + idx, pl);
+    return ld_keep_f64_if(V + (idx >= 0 ? idx : 0), idx >= 0, 1.0, pl);
   };
-  auto padf = [&](int k) -> int { return k + ((k >> pad_shift) << 1); };   // even k stays even
+  auto padf = [&](int k) -> int { return PAD ? k + ((k >> pad_shift) << 1) : k; };   // even k stays even
   auto row_begin = [&](int64_t r) -> int64_t { return ptr ? __ldg(ptr + r) : r * (int64_t)row_len; };
   const int lane = threadIdx.x & 31;
   double *prod = prod_all[threadIdx.x >> 5];

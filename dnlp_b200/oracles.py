@@ -58,11 +58,23 @@ class GpuOracles:
         # (affine Jacobian rows, reference quirk Q5), only that part crosses PCIe per call; the
         # constants are written into the (reused) output array once, here.
         self._dyn = {}
+        self._hess_sigma_class = False     # part of the Hessian depends on sigma only (see hessian())
+        self._hess_sigma = None            # the sigma the sigma-only entries of self._hess were fetched for
         for name, space, buf, const in (("jac", 4, self._jac, self.tape.jac_const),
                                         ("hess", 5, self._hess, self.tape.hess_const),
                                         ("g", 3, self._g, self.tape.g_const),
                                         ("grad", 2, self.grad_obj, self.tape.grad_const)):
             pos = self.tape.dynamic.get(space)
+            sig = self.tape.dynamic_sigma.get(space)
+            if name == "hess" and pos is not None and sig is not None and sig.size and buf.size >= self.ELIDE_MIN:
+                # entries of the form c * sigma (dense quad_form objective: 2*sigma*Q) change only when
+                # the solver changes the objective factor, which IPOPT does not do between regular
+                # iterations: they are fetched in full when sigma differs from the last call and skipped
+                # otherwise, so a steady iteration moves only the x / lambda-dependent entries
+                general = np.setdiff1d(pos, sig, assume_unique=True)
+                if general.size <= self.ELIDE_MAX_FRACTION * buf.size:
+                    pos = general
+                    self._hess_sigma_class = True
             if pos is not None and buf.size >= self.ELIDE_MIN and pos.size <= self.ELIDE_MAX_FRACTION * buf.size:
                 buf[:] = const
                 pos = np.ascontiguousarray(pos, dtype=np.int32)
@@ -146,6 +158,12 @@ class GpuOracles:
         if not self.with_hessian:
             raise RuntimeError("this oracle was compiled without the Hessian program")
         lam = self._stage_lam(duals)
+        if "hess" in self._dyn and self._hess_sigma_class and float(obj_factor) != self._hess_sigma:
+            # sigma changed (or first call): every entry travels once, into the same reused array
+            self.dev.check(self.dev._L.dnlp_eval_hess(self.dev.h, self._stage_x(x), _ptr(lam),
+                                                     float(obj_factor), _ptr(self._hess)))
+            self._hess_sigma = float(obj_factor)
+            return self._hess
         if "hess" in self._dyn:
             pos, compact = self._eval_dyn("hess", 4, x, lam, obj_factor)
             self._hess[pos] = compact

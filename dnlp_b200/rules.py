@@ -61,6 +61,10 @@ class Builder:
         slots = np.asarray(slots, dtype=np.int64)
         slots = slots[slots >= 0]
         uses_lam = bool(np.any((slots >= self.tape.n) & (slots < self.tape.n + 1 + self.tape.m)))
+        self._last_mask = ((T.DEP_X if np.any(slots < self.tape.n) else 0)
+                           | (T.DEP_SIGMA if np.any(slots == self.tape.n) else 0)
+                           | (T.DEP_LAMBDA if np.any((slots > self.tape.n) & (slots < self.tape.n + 1 + self.tape.m))
+                              else 0))
         deps = set()
         if self._producers and slots.size:
             prod = sorted(self._producers)          # allocation order != emission order
@@ -81,6 +85,9 @@ class Builder:
             uses_lam = uses_lam or self.tape.instrs[d].uses_lam
         ins.deps = tuple(sorted(deps))
         ins.uses_lam = uses_lam
+        ins.dep_mask = self._last_mask
+        for d in deps:
+            ins.dep_mask |= self.tape.instrs[d].dep_mask
         ins.level = 1 + max([self.tape.instrs[d].level for d in deps], default=-1)
         self.tape.add(ins)
         if ins.dst_space == T.DST_V:
@@ -149,6 +156,9 @@ class Builder:
             d2, l2 = self._deps_of_slots(sv.f2)
             ins.deps = tuple(sorted(set(ins.deps) | d2))
             ins.uses_lam = ins.uses_lam or l2 or any(self.tape.instrs[d].uses_lam for d in d2)
+            ins.dep_mask |= self._last_mask
+            for d in d2:
+                ins.dep_mask |= self.tape.instrs[d].dep_mask
             ins.level = 1 + max([self.tape.instrs[d].level for d in ins.deps], default=-1)
         return ins
 
@@ -156,7 +166,9 @@ class Builder:
         """Write an output vector.  Large vectors whose rows are (almost all) a single term are
         split into a streaming first layer - a SCALE when that term is one shared slot times a
         constant (dense quad_form Hessian: 2*sigma*Q), else a one-term-per-row POLY (Jacobian fill)
-        - plus a small scatter-accumulate POLY for the few rows with more terms."""
+        - plus a small scatter POLY that OVERWRITES the few rows with more terms with their full sums
+        (overwrite, not accumulate: re-running it alone is then always correct, which lets the engine
+        keep a first layer that depends only on sigma cached across calls)."""
         K = sv.K
         lens = sv.term_counts()
         multi = lens > 1
@@ -171,12 +183,8 @@ class Builder:
             else:
                 roots.append(self.emit_poly(SymVec(K, np.arange(K), c0, a0, b0), space, 0, pos=pos))
             if multi.any():
-                rest = np.ones(sv.nterms, dtype=bool)
-                rest[first] = False
                 rows = np.where(multi)[0]
-                rv = SymVec(K, sv.row[rest], sv.coef[rest], sv.f1[rest], sv.f2[rest]).gather(rows)
-                roots.append(self.emit_poly(rv, space, 0, pos=rows if pos is None else pos[rows],
-                                            accumulate=True))
+                roots.append(self.emit_poly(sv.gather(rows), space, 0, pos=rows if pos is None else pos[rows]))
             return roots
         return [self.emit_poly(sv, space, 0, pos=pos)]
 

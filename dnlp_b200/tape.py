@@ -57,6 +57,9 @@ OUT_NAMES = {DST_F: "f", DST_GRAD: "grad", DST_G: "g", DST_JAC: "jac", DST_HESS:
 
 K_ELEM, K_POLY, K_GEMV, K_SCALE = 1, 2, 3, 4
 
+# what an instruction's result depends on (transitively): the point, the objective factor, the duals
+DEP_X, DEP_SIGMA, DEP_LAMBDA = 1, 2, 4
+
 
 class Instr:
     """One tape instruction.  ``reads`` / ``writes`` are slot ranges used for scheduling."""
@@ -64,7 +67,7 @@ class Instr:
                  "a_off", "a_stride", "b_off", "b_stride",
                  "ptr", "coef", "f1", "f2", "pos", "accumulate",
                  "Q", "x_off", "ncols", "alpha", "s_slot",
-                 "deps", "uses_lam", "id", "level")
+                 "deps", "uses_lam", "dep_mask", "id", "level")
 
     def __init__(self, kind, **kw):
         self.kind = kind
@@ -83,6 +86,7 @@ class Instr:
         self.s_slot = 0
         self.deps = ()
         self.uses_lam = False
+        self.dep_mask = 0           # DEP_X | DEP_SIGMA | DEP_LAMBDA, transitive over the instructions it reads
         self.id = -1
         self.level = 0
         for k, v in kw.items():
@@ -131,6 +135,7 @@ class Tape:
         self.f_const = 0.0
         self.jac_is_list = False    # reference returns a Python list when all constraints are affine
         self.dynamic = {}           # output space -> int32 positions of the x/lambda-dependent entries
+        self.dynamic_sigma = {}     # output space -> the subset of `dynamic` that depends on sigma ONLY
 
     @property
     def sigma_slot(self):

@@ -68,7 +68,7 @@ typedef struct {
   int32_t row_len;        /* uniform row length when ptr == NULL */
   int32_t uses_lam;       /* depends on (sigma, lambda): never cached across calls */
   int32_t level;          /* 0 = reads only x / lambda (no instruction feeds it) */
-  int32_t reserved;
+  int32_t dep_mask;       /* what the result depends on, transitively: 1 = x, 2 = sigma, 4 = lambda */
   /* GEMV: dst[i] = alpha * sum_j Q[i*ncols + j] * V[x_off + j] */
   const double *Q;
   int64_t ncols;
