@@ -1,0 +1,117 @@
+"""Compile-once reuse of the GPU oracle across solves of the same smooth problem.
+
+The reference's ``best_of=N`` loop (cvxpy/problems/problem.py:1249-1275, 1643-1693) re-samples the
+variables and re-applies the whole reduction chain for every start, so ``NLPsolver.apply`` builds a
+fresh ``Oracles`` object each time (nlp_solver.py:61-79).  For the GPU oracle that would mean
+re-running the DAG compiler and re-uploading the tape (10 s and 1 GB for the dense n = 8192
+eigen-QCQP) although only the initial point differs.  ``fingerprint`` identifies a smooth problem
+by everything the tape depends on - the expression DAG, every constant's bytes, the variable
+layout - and by nothing else (variable ids, names, values and bounds do not enter the tape), and
+``OracleCache`` hands back the already-compiled oracle when the fingerprint matches.
+"""
+import hashlib
+from collections import OrderedDict
+from fractions import Fraction
+
+import numpy as np
+import scipy.sparse as sp
+
+_VAR_ATTRS_IGNORED = ("id", "name", "value", "lb", "ub")
+
+
+def _feed_array(h, a):
+    a = np.ascontiguousarray(a)
+    h.update(str((a.dtype.str, a.shape)).encode())
+    h.update(memoryview(a).cast("B"))
+
+
+def _feed_value(h, v):
+    if sp.issparse(v):
+        c = sp.csc_array(v)
+        c.sum_duplicates()
+        h.update(b"sparse" + str(c.shape).encode())
+        _feed_array(h, c.indptr)
+        _feed_array(h, c.indices)
+        _feed_array(h, np.asarray(c.data, np.float64))
+    elif isinstance(v, np.ndarray):
+        _feed_array(h, v)
+    elif isinstance(v, Fraction):
+        h.update(("frac%d/%d" % (v.numerator, v.denominator)).encode())
+    elif isinstance(v, (list, tuple)):
+        h.update(b"seq%d" % len(v))
+        for e in v:
+            _feed_value(h, e)
+    elif isinstance(v, dict):
+        h.update(b"map%d" % len(v))
+        for k in sorted(v):
+            h.update(str(k).encode())
+            _feed_value(h, v[k])
+    elif isinstance(v, float):
+        h.update(np.float64(v).tobytes())
+    else:
+        h.update(repr(v).encode())
+
+
+def fingerprint(prob):
+    """Hex digest identifying the tape ``compile_problem(prob)`` would produce."""
+    h = hashlib.blake2b(digest_size=20)
+    var_index = {id(v): i for i, v in enumerate(prob.variables)}
+    memo = {}
+
+    def visit(n):
+        k = id(n)
+        if k in memo:
+            return memo[k]
+        kids = [visit(a) for a in n.args]
+        idx = len(memo)
+        h.update(("|%d:%s%s<%s>" % (idx, n.op, n.shape, ",".join(map(str, kids)))).encode())
+        if n.op == "var":
+            # a variable is its position in the flat layout; one that is not listed cannot be compiled
+            h.update(b"v%d" % var_index.get(k, -1))
+        else:
+            for name in sorted(n.attrs):
+                h.update(name.encode())
+                _feed_value(h, n.attrs[name])
+        memo[k] = idx
+        return idx
+
+    roots = [visit(prob.objective)] + [visit(c) for c in prob.constraints] + [visit(v) for v in prob.variables]
+    h.update(("roots%s n%d m%d" % (roots, prob.n, prob.m)).encode())
+    return h.hexdigest()
+
+
+class OracleCache:
+    """Small LRU of live oracles keyed by ``fingerprint``.  Evicted oracles are closed (their HBM is
+    released); ``clear`` closes everything."""
+
+    def __init__(self, capacity=2):
+        self.capacity = int(capacity)
+        self._items = OrderedDict()
+        self.hits = self.misses = 0
+
+    def get(self, prob, build):
+        """``build(prob)`` -> oracle is called on a miss.  Returns (oracle, hit)."""
+        if self.capacity <= 0:
+            self.misses += 1
+            return build(prob), False
+        key = fingerprint(prob)
+        if key in self._items:
+            self._items.move_to_end(key)
+            self.hits += 1
+            return self._items[key], True
+        self.misses += 1
+        o = build(prob)
+        self._items[key] = o
+        while len(self._items) > self.capacity:
+            _, old = self._items.popitem(last=False)
+            close = getattr(old, "close", None)
+            if close:
+                close()
+        return o, False
+
+    def clear(self):
+        while self._items:
+            _, old = self._items.popitem()
+            close = getattr(old, "close", None)
+            if close:
+                close()

@@ -11,17 +11,25 @@ else in the reference changes, and the user-facing API stays ``prob.solve(nlp=Tr
     gpu.install()                      # or: with gpu.gpu_oracle(): prob.solve(nlp=True)
     prob.solve(nlp=True, solver=cp.IPOPT)
 
+``best_of=N`` (cvxpy/problems/problem.py:1249-1275) re-applies the reduction chain for every
+start, which calls ``Oracles(...)`` again with a structurally identical smooth problem; the
+factory below recognises it (``compile_cache.fingerprint``) and hands back the oracle that is
+already compiled and resident in HBM, re-armed with the new initial point, so N starts cost one
+compile + one upload.  ``ORACLE_CACHE.capacity = 0`` switches that off.
+
 The reference is imported lazily so the rest of the package works without it.
 """
 import contextlib
 import importlib
 
+from .compile_cache import OracleCache
 from .frontend_cvxpy import problem_to_ir
 from .oracles import GpuOracles
 
 _REF_MODULE = "cvxpy.reductions.solvers.nlp_solvers.nlp_solver"
 _saved = {}
 DEVICE = 0
+ORACLE_CACHE = OracleCache(capacity=2)
 
 
 def gpu_oracles(problem, initial_point, num_constraints):
@@ -29,7 +37,10 @@ def gpu_oracles(problem, initial_point, num_constraints):
     pir = problem_to_ir(problem, x0=initial_point)
     if pir.m != num_constraints:
         raise ValueError("constraint count mismatch: IR has %d rows, caller says %d" % (pir.m, num_constraints))
-    return GpuOracles(pir, device=DEVICE)
+    oracle, hit = ORACLE_CACHE.get(pir, lambda p: GpuOracles(p, device=DEVICE))
+    if hit:
+        oracle.rearm(pir)
+    return oracle
 
 
 def install(device=0):
@@ -45,6 +56,7 @@ def install(device=0):
 def uninstall():
     if "Oracles" in _saved:
         importlib.import_module(_REF_MODULE).Oracles = _saved.pop("Oracles")
+    ORACLE_CACHE.clear()
 
 
 @contextlib.contextmanager

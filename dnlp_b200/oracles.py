@@ -82,6 +82,16 @@ class GpuOracles:
                                                            int(pos.size)))
                 self._dyn[name] = (pos, alloc(pos.size))
 
+    def rearm(self, problem_ir):
+        """Reuse this compiled oracle for another solve of the same smooth problem (next start of a
+        ``best_of`` loop): new initial point, iteration counter back to zero.  The tape, the device
+        buffers and the captured graphs stay."""
+        if problem_ir.n != self.n or problem_ir.m != self.m:
+            raise ValueError("rearm: problem size differs from the compiled one")
+        self.problem = problem_ir
+        self.initial_point = problem_ir.x0
+        self.iterations = 0
+
     def _pinned(self, count):
         arr, h = _cabi.pinned_empty(count)
         self._handles.append(h)

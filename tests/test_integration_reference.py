@@ -79,3 +79,43 @@ def test_install_swaps_the_oracle_and_structures_match(cp, monkeypatch):
     # after the context manager the reference's own class is back
     import cvxpy.reductions.solvers.nlp_solvers.nlp_solver as mod
     assert mod.Oracles is type(ref)
+
+
+def test_best_of_style_reapplied_chain_reuses_the_compiled_oracle(cp, monkeypatch):
+    """The reference's best_of loop re-applies the reduction chain per start (problem.py:1249-1275):
+    fresh auxiliary variables and ids every time, same smooth problem.  The factory must hand back
+    the oracle that is already compiled, re-armed with the new initial point."""
+    import dnlp_b200.nlp_solver as gpu
+    from dnlp_b200 import _cabi
+
+    class FakeDevice:
+        def __init__(self, tape, device=0):
+            self.tape = tape
+
+        def close(self):
+            pass
+    monkeypatch.setattr(_cabi, "DeviceTape", FakeDevice)
+    monkeypatch.setattr(_cabi, "pinned_empty", lambda k: (np.empty(k), types.SimpleNamespace(free=lambda: None)))
+
+    def build(start, rhs=1.0):
+        np.random.seed(0)
+        A = np.random.randn(5, 5)
+        x = cp.Variable(5)
+        x.value = start
+        return cp.Problem(cp.Minimize(cp.sum(cp.logistic(A @ x)) + cp.sum(cp.exp(-x))), [cp.sum_squares(x) == rhs])
+
+    with gpu.gpu_oracle():
+        gpu.ORACLE_CACHE.hits = gpu.ORACLE_CACHE.misses = 0
+        d1 = _chain(cp, build(np.ones(5)))
+        o1 = d1["oracles"]
+        x0_first = np.array(o1.initial_point, copy=True)
+        d2 = _chain(cp, build(np.full(5, 0.25)))
+        o2 = d2["oracles"]
+        assert o2 is o1 and (gpu.ORACLE_CACHE.hits, gpu.ORACLE_CACHE.misses) == (1, 1)
+        assert not np.array_equal(o2.initial_point, x0_first)            # re-armed with the new start
+        np.testing.assert_array_equal(o2.initial_point, d2["x0"])
+        o2.intermediate(0, 9, 0, 0, 0, 0, 0, 0, 0, 0, 0)
+        d3 = _chain(cp, build(np.ones(5)))
+        assert d3["oracles"] is o1 and d3["oracles"].iterations == 0
+        d4 = _chain(cp, build(np.ones(5), rhs=2.0))                      # another constant: another oracle
+        assert d4["oracles"] is not o1
