@@ -491,6 +491,19 @@ def main():
         for i in range(e2e_steps):
             o.eval_all(xs[i % npts], lams[i % npts], sigma)
         fused_s = time.perf_counter() - t0
+        # each callback on its own: device-side with nothing cached, and through the host API
+        cb_iters = max(3, min(args.steps, 10))
+        o.upload_point(x, lam, sigma)
+        cb_dev = {p: o.run_device((p,), cb_iters) / cb_iters for p in PROGS}
+        cb_e2e = {p: 0.0 for p in PROGS}
+        fns = {"f": lambda xi, li: o.objective(xi), "grad": lambda xi, li: o.gradient(xi),
+               "g": lambda xi, li: o.constraints(xi), "jac": lambda xi, li: o.jacobian(xi),
+               "hess": lambda xi, li: o.hessian(xi, li, sigma)}
+        for i in range(cb_iters):
+            for p in PROGS:
+                t0 = time.perf_counter()
+                fns[p](xs[i % npts], lams[i % npts])
+                cb_e2e[p] += (time.perf_counter() - t0) * 1e3 / cb_iters
     clocks = clk.summary()
 
     if dist is not None:
@@ -550,6 +563,9 @@ def main():
                     "d2h_bytes_per_step_without_elision": int(d2h_full),
                     "fused_eval_all_value": world * e2e_steps / (fused_ms * 1e-3)},
             "gpu_launches": int(launches),
+            "per_callback": {"device_ms_nothing_cached": cb_dev, "e2e_ms_in_ipopt_call_order": cb_e2e,
+                             "note": "device: each program alone at a fresh point (shared forward work is repeated); "
+                                     "e2e: objective first, so it carries the upload of x and the shared sweep"},
             "roofline": {"bound": "hbm", "kernel": "%s (instr %d, %d rows)" % (kname or kind, top, ins.count),
                          "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": traffic, "traffic_source": "profiles/r01_ncu_traffic.json (ncu --set full, dram read+write)"

@@ -43,7 +43,7 @@ struct DevInstr {
   bool const_coef = false;
   int64_t s0 = 0, s1 = 0;
   double c0 = 1.0;
-  // shared-memory gather window (poly_rows_win_kernel): slots [win0, win0 + winW) cover most gathers
+  // shared-memory gather window of the flat kernel: slots [win0, win0 + winW) cover most gathers
   int win0 = -1, winW = 0;
   // flat term-streaming kernel (poly_flat_kernel): per-chunk first row, continuation partials
   bool flat = false;
@@ -111,7 +111,7 @@ struct dnlp_oracle {
   int cur_lane = 0;
   std::vector<cudaEvent_t> ev_pool;    // capture-time dependency markers
   bool parallel_enabled = true;
-  bool win_enabled = true;             // shared-memory gather windows (poly_rows_win_kernel)
+  bool win_enabled = true;             // shared-memory gather window of the flat kernel
   bool fuse_enabled = true;            // family fusion of phi / phi' / phi'' in the elementwise batch
   bool flat_enabled = true;            // flat term-streaming SpMV (poly_flat_kernel)
   int64_t flat_min_terms = 1 << 18;
@@ -209,32 +209,6 @@ void launch_poly_g(const dnlp_oracle *o, const DevInstr &I, double *dst, int gri
   if (I.has_f2) { if (uni) LP(true, true); else LP(true, false); }
   else { if (uni) LP(false, true); else LP(false, false); }
 #undef LP
-}
-
-template <int G>
-void launch_poly_win_g(const dnlp_oracle *o, const DevInstr &I, double *dst, int grid, int threads, size_t smem) {
-  const dnlp_instr_desc &d = I.d;
-  const bool uni = d.ptr == nullptr;
-#define LW(H, Un)                                                                                        \
-  poly_rows_win_kernel<G, 2, H, Un><<<grid, threads, smem, o->cur>>>(o->V, dst, d.ptr, d.row_len, d.coef, \
-                                                                     d.f1, d.f2, d.pos, d.count,         \
-                                                                     d.accumulate, I.win0, I.winW)
-  if (I.has_f2) { if (uni) LW(true, true); else LW(true, false); }
-  else { if (uni) LW(false, true); else LW(false, false); }
-#undef LW
-}
-
-template <int G>
-cudaError_t set_win_attrs_g() {
-  cudaError_t e = cudaSuccess;
-#define SA(H, Un)                                                                                             \
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(poly_rows_win_kernel<G, 2, H, Un>,                           \
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);    \
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(poly_rows_win_kernel<G, 2, H, Un>,                           \
-                                                 cudaFuncAttributePreferredSharedMemoryCarveout, 100)
-  SA(true, true); SA(true, false); SA(false, true); SA(false, false);
-#undef SA
-  return e;
 }
 
 // Bucketed histogram of the gathered slots; the window is the narrowest of three widths that still
@@ -363,26 +337,6 @@ int dnlp_oracle::launch(DevInstr &I) {
       // two rows in flight per lane group
       int G = 1;
       while (G < 32 && (double)(2 * G) <= 0.8 * I.mean_len) G <<= 1;
-      if (I.winW > 0 && win_enabled) {
-        // gathered window staged in shared memory: persistent CTAs, as many per SM as the window allows
-        const size_t smem = (size_t)I.winW * sizeof(double);
-        const int threads = smem > 72 * 1024 ? 1024 : 512;
-        const int per_sm = smem > 72 * 1024 ? 1 : (smem > 36 * 1024 ? 3 : 4);
-        int64_t need = ((d.count + 1) / 2 * G + threads - 1) / threads;
-        int grid = (int)(need < (int64_t)sm_count * per_sm ? (need < 1 ? 1 : need) : (int64_t)sm_count * per_sm);
-        switch (G) {
-          case 1: launch_poly_win_g<1>(this, I, dst, grid, threads, smem); break;
-          case 2: launch_poly_win_g<2>(this, I, dst, grid, threads, smem); break;
-          case 4: launch_poly_win_g<4>(this, I, dst, grid, threads, smem); break;
-          case 8: launch_poly_win_g<8>(this, I, dst, grid, threads, smem); break;
-          case 16: launch_poly_win_g<16>(this, I, dst, grid, threads, smem); break;
-          default: launch_poly_win_g<32>(this, I, dst, grid, threads, smem); break;
-        }
-        if (I.kname.empty())
-          I.kname = "poly_rows_win_kernel<" + std::to_string(G) + ", 2, " + (I.has_f2 ? "1" : "0") + ", " +
-                    (d.ptr == nullptr ? "1" : "0") + ">";
-        break;
-      }
       int grid = grid_for((d.count + 1) / 2, G);
       switch (G) {
         case 1: launch_poly_g<1>(this, I, dst, grid); break;
@@ -876,10 +830,10 @@ static int create_impl(dnlp_oracle *o, const dnlp_tape_desc *t) {
           D.flat = true;
         }
       }
-      // long multi-term row sets whose gathers concentrate on a short slot range (SpMV against a
-      // small x): stage that range in shared memory
-      const bool rows_path = !(h.count == 1 && h.nterms >= 2048 && !h.pos) && !(h.ptr == nullptr && h.row_len == 1);
-      if (rows_path && h.nterms >= o->win_min_terms && !D.contig)
+      // gathers that concentrate on a short slot range (SpMV against a small x): the flat kernel
+      // stages that range in shared memory.  (The same window under poly_rows_kernel was measured
+      // slower than its L1-resident gathers - 0.167 vs 0.121 ms on the C3 SpMV - and was dropped.)
+      if (D.flat && h.nterms >= o->win_min_terms)
         choose_window(h.f1, h.f2, h.nterms, t->nslots, &D.win0, &D.winW);
     } else if (h.kind == DNLP_GEMV) {
       if (o->upload(h.Q, h.count * h.ncols, const_cast<double **>(&D.d.Q))) return 1;
@@ -901,8 +855,6 @@ static int create_impl(dnlp_oracle *o, const dnlp_tape_desc *t) {
   // opt in to > 48 KB dynamic shared memory for the GEMV x tile
   CK(cudaFuncSetAttribute(dnlp::gemv_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
   CK(cudaFuncSetAttribute(dnlp::gemv_cta_kernel<4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-  CK(set_win_attrs_g<1>()); CK(set_win_attrs_g<2>()); CK(set_win_attrs_g<4>());
-  CK(set_win_attrs_g<8>()); CK(set_win_attrs_g<16>()); CK(set_win_attrs_g<32>());
 #define FA(H, Pd)                                                                                                       \
   CK(cudaFuncSetAttribute(dnlp::poly_flat_kernel<H, true, Pd>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024)); \
   CK(cudaFuncSetAttribute(dnlp::poly_flat_kernel<H, true, Pd>, cudaFuncAttributePreferredSharedMemoryCarveout, 100))

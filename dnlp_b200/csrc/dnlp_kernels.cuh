@@ -535,80 +535,6 @@ poly_rows_kernel(const double *__restrict__ V, double *__restrict__ dst, const i
   }
 }
 
-// ---- POLY v4: the gathered window lives in shared memory ------------------------------------------
-// SpMV against a SHORT vector (C3: A~ x with x in R^4096): every gather of poly_rows_kernel is a
-// 32-byte L2 sector for 8 useful bytes, which makes the kernel L2-bandwidth bound (34 M gathers =
-// 1.1 GB of L2->SM traffic next to 0.44 GB of streamed coefficients / indices).  Here each persistent
-// CTA first copies the window V[w0, w0 + W) - chosen on the host so that it covers most gathered
-// slots - into shared memory; gathers inside the window never leave the SM, the rest (one lifted
-// slot per row in C3) still go to L2.  Rows are dealt to lane groups exactly as in poly_rows_kernel,
-// so the summation order, and therefore every bit of the result, is the same.
-template <int G, int R, bool HAS_F2, bool UNIFORM>
-__global__ void __launch_bounds__(1024)
-poly_rows_win_kernel(const double *__restrict__ V, double *__restrict__ dst, const int64_t *__restrict__ ptr,
-                     int row_len, const double *__restrict__ coef, const int32_t *__restrict__ f1,
-                     const int32_t *__restrict__ f2, const int32_t *__restrict__ pos, int64_t count,
-                     int accumulate, int w0, int W) {
-  extern __shared__ __align__(16) double win[];
-  for (int j = threadIdx.x; j < W; j += blockDim.x) win[j] = V[w0 + j];
-  __syncthreads();
-  const uint64_t pf = l2_policy_evict_first(), pl = l2_policy_evict_last();
-  auto gather = [&](int idx) -> double {
-    if (idx < 0) return 1.0;
-    const unsigned rel = (unsigned)(idx - w0);
-    return rel < (unsigned)W ? win[rel] : ld_keep_f64(V + idx, pl);
-  };
-  const int lane = threadIdx.x & (G - 1);
-  const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
-  const int64_t ngroups = ((int64_t)gridDim.x * blockDim.x) / G;
-  for (int64_t base = group; base < count; base += R * ngroups) {
-    int64_t t[R], t1[R];
-    double acc[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int64_t row = base + r * ngroups;
-      acc[r] = 0.0;
-      if (row < count) {
-        if (UNIFORM) { t[r] = row * (int64_t)row_len; t1[r] = t[r] + row_len; }
-        else { t[r] = __ldg(ptr + row); t1[r] = __ldg(ptr + row + 1); }
-        t[r] += lane;
-      } else { t[r] = 0; t1[r] = 0; }
-    }
-    bool more = true;
-    while (more) {
-      double c[R];
-      int a[R], b[R];
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const bool ok = t[r] < t1[r];
-        c[r] = ok ? ld_stream_f64(coef + t[r], pf) : 0.0;
-        a[r] = ok ? ld_stream_s32(f1 + t[r], pf) : -1;
-        b[r] = (HAS_F2 && ok) ? ld_stream_s32(f2 + t[r], pf) : -1;
-      }
-      more = false;
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        double v = c[r] * gather(a[r]);
-        if (HAS_F2) v *= gather(b[r]);
-        acc[r] += v;
-        t[r] += G;
-        more |= t[r] < t1[r];
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      double v = acc[r];
-#pragma unroll
-      for (int s = G >> 1; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s, G);
-      const int64_t row = base + r * ngroups;
-      if (lane == 0 && row < count) {
-        const int64_t d = pos ? (int64_t)__ldg(pos + row) : row;
-        dst[d] = accumulate ? dst[d] + v : v;
-      }
-    }
-  }
-}
-
 // ---- POLY v5: flat term streaming + in-warp segmented row sums --------------------------------------
 // poly_rows_kernel spends ~2 warp instructions per term (64-bit cursors, per-row predicates, shuffle
 // trees) and keeps only two 12-byte loads per lane in flight: on the C3 SpMV ncu shows 53 % issue

@@ -383,38 +383,6 @@ def test_gpu_parallel_graph_branches_equal_serial(name, gpu_mod):
         np.testing.assert_array_equal(outs["parallel"][1][k], outs["parallel"][0][0][k], err_msg="device vs host/" + k)
 
 
-@pytest.mark.parametrize("name", ["c3_logistic_small", "c5_microbench_small", "portfolio_socp", "matmul_const_sides",
-                                  "nmf_kl_graph_form", "clnlbeam"])
-def test_gpu_shared_memory_gather_window(name, gpu_mod, monkeypatch):
-    """SpMV-shaped instructions with the gathered slot window staged in shared memory
-    (poly_rows_win_kernel), forced on for small problems.  Same lane-group mapping as the plain
-    kernel, so the results must be bit-identical to it, and within 1e-10 of the reference."""
-    monkeypatch.setenv("DNLP_WIN_MIN_TERMS", "1")
-    g = Golden(name)
-    o = gpu_mod(g.problem)
-    try:
-        for i, p in enumerate(g.points):
-            res = {"f": o.objective(p["x"]), "grad": o.gradient(p["x"]).copy(), "g": o.constraints(p["x"]).copy(),
-                   "jac": np.array(o.jacobian(p["x"]), copy=True),
-                   "hess": np.array(o.hessian(p["x"], p["lam"], float(p["sigma"])), copy=True)}
-            for k, v in res.items():
-                assert_close(v, p[k], "%s[%d]" % (k, i))
-        used = [o.instr_kernel(i) for i in range(len(o.tape.instrs))]
-        o.set_windows(False)
-        o.set_cache(False)
-        o.set_cache(True)
-        p = g.points[-1]
-        plain = {"f": o.objective(p["x"]), "grad": o.gradient(p["x"]).copy(), "g": o.constraints(p["x"]).copy(),
-                 "jac": np.array(o.jacobian(p["x"]), copy=True),
-                 "hess": np.array(o.hessian(p["x"], p["lam"], float(p["sigma"])), copy=True)}
-        for k in plain:
-            np.testing.assert_array_equal(np.asarray(res[k]).reshape(-1), np.asarray(plain[k]).reshape(-1), err_msg=k)
-    finally:
-        o.close()
-    if name in ("c3_logistic_small", "c5_microbench_small"):
-        assert any(u.startswith("poly_rows_win_kernel") for u in used), used
-
-
 def test_gpu_medium_logistic_window(gpu_mod):
     """C3 shape at a size where the window is chosen by the production rule (>= 2^18 terms)."""
     from dnlp_b200 import workloads as W
