@@ -386,6 +386,9 @@ def main():
     ap.add_argument("--scale", type=float, default=float(os.environ.get("DNLP_BENCH_SCALE", "1.0")))
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--device-only", action="store_true",
+                    help="profiling aid: only the device-resident step loop and the per-instruction timing "
+                         "(the ncu launch list then holds the step's kernels and nothing else)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -432,8 +435,19 @@ def main():
     from dnlp_b200.oracles import GpuOracles
     prob, desc = build_workload(args.workload, args.scale)
     t0 = time.time()
-    o = GpuOracles(prob, device=local_rank)
+    tape, tape_file = None, None
+    if os.environ.get("DNLP_TAPE_CACHE"):
+        # profiling aid: repeated invocations on one box (bench, ncu launch list, ncu full capture) reuse
+        # the compiled tape instead of paying the DAG compiler again (55 s for c5)
+        import pickle
+        tape_file = os.path.join(os.environ["DNLP_TAPE_CACHE"], "tape_%s_%g.pkl" % (args.workload, args.scale))
+        if os.path.exists(tape_file):
+            tape = pickle.load(open(tape_file, "rb"))
+    o = GpuOracles(prob, device=local_rank, tape=tape)
     compile_s = time.time() - t0
+    if tape_file and tape is None:
+        import pickle
+        pickle.dump(o.tape, open(tape_file, "wb"), protocol=4)
     if rank == 0:
         import resource
         sys.stderr.write("[bench] %s: compiled in %.1f s, n=%d m=%d nnzJ=%d nnzH=%d, %d instructions, "
@@ -459,51 +473,55 @@ def main():
         if rank == 0:
             sys.stderr.write("[bench] device: %.4f ms/eval\n" % (ms / args.steps))
         barrier()
-        # ---- end to end through the public callbacks, host buffers --------------------------------
-        rng = np.random.default_rng(7 + rank)
-        npts = min(args.steps, 4)
-        xs = [x * (1.0 + 1e-3 * rng.standard_normal(prob.n)) for _ in range(npts)]
-        lams = [lam * (1.0 + 1e-3 * rng.standard_normal(prob.m)) for _ in range(npts)]
-
-        def five(i, sg):
-            xi, li = xs[i % npts], lams[i % npts]
-            o.objective(xi), o.gradient(xi), o.constraints(xi), o.jacobian(xi), o.hessian(xi, li, sg)
-        for i in range(2):
-            five(i, sigma)
-        barrier()
+        e2e_s = fused_s = sv_s = float("nan")
         e2e_steps = args.steps
-        # headline e2e: a new x and a new lambda every step, the objective factor held at 1.0 - the way
-        # IPOPT calls eval_h in every regular iteration (it passes 0 only in the restoration phase)
-        t0 = time.perf_counter()
-        for i in range(e2e_steps):
-            five(i, sigma)
-        e2e_s = time.perf_counter() - t0
-        barrier()
-        # worst case for the sigma-keyed Hessian entries: the objective factor changes every step too
-        sv_steps = max(2, min(e2e_steps, 6))
-        five(0, 0.5)
-        t0 = time.perf_counter()
-        for i in range(sv_steps):
-            five(i, 1.0 if i % 2 else 0.5)
-        sv_s = (time.perf_counter() - t0) * e2e_steps / sv_steps
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(e2e_steps):
-            o.eval_all(xs[i % npts], lams[i % npts], sigma)
-        fused_s = time.perf_counter() - t0
-        # each callback on its own: device-side with nothing cached, and through the host API
-        cb_iters = max(3, min(args.steps, 10))
-        o.upload_point(x, lam, sigma)
-        cb_dev = {p: o.run_device((p,), cb_iters) / cb_iters for p in PROGS}
-        cb_e2e = {p: 0.0 for p in PROGS}
-        fns = {"f": lambda xi, li: o.objective(xi), "grad": lambda xi, li: o.gradient(xi),
-               "g": lambda xi, li: o.constraints(xi), "jac": lambda xi, li: o.jacobian(xi),
-               "hess": lambda xi, li: o.hessian(xi, li, sigma)}
-        for i in range(cb_iters):
-            for p in PROGS:
-                t0 = time.perf_counter()
-                fns[p](xs[i % npts], lams[i % npts])
-                cb_e2e[p] += (time.perf_counter() - t0) * 1e3 / cb_iters
+        cb_dev, cb_e2e = {}, {}
+        if not args.device_only:
+            # ---- end to end through the public callbacks, host buffers --------------------------------
+            rng = np.random.default_rng(7 + rank)
+            npts = min(args.steps, 4)
+            xs = [x * (1.0 + 1e-3 * rng.standard_normal(prob.n)) for _ in range(npts)]
+            lams = [lam * (1.0 + 1e-3 * rng.standard_normal(prob.m)) for _ in range(npts)]
+
+            def five(i, sg):
+                xi, li = xs[i % npts], lams[i % npts]
+                o.objective(xi), o.gradient(xi), o.constraints(xi), o.jacobian(xi), o.hessian(xi, li, sg)
+            for i in range(2):
+                five(i, sigma)
+            barrier()
+            e2e_steps = args.steps
+            # headline e2e: a new x and a new lambda every step, the objective factor held at 1.0 - the way
+            # IPOPT calls eval_h in every regular iteration (it passes 0 only in the restoration phase)
+            t0 = time.perf_counter()
+            for i in range(e2e_steps):
+                five(i, sigma)
+            e2e_s = time.perf_counter() - t0
+            barrier()
+            # worst case for the sigma-keyed Hessian entries: the objective factor changes every step too
+            sv_steps = max(2, min(e2e_steps, 6))
+            five(0, 0.5)
+            t0 = time.perf_counter()
+            for i in range(sv_steps):
+                five(i, 1.0 if i % 2 else 0.5)
+            sv_s = (time.perf_counter() - t0) * e2e_steps / sv_steps
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(e2e_steps):
+                o.eval_all(xs[i % npts], lams[i % npts], sigma)
+            fused_s = time.perf_counter() - t0
+            # each callback on its own: device-side with nothing cached, and through the host API
+            cb_iters = max(3, min(args.steps, 10))
+            o.upload_point(x, lam, sigma)
+            cb_dev = {p: o.run_device((p,), cb_iters) / cb_iters for p in PROGS}
+            cb_e2e = {p: 0.0 for p in PROGS}
+            fns = {"f": lambda xi, li: o.objective(xi), "grad": lambda xi, li: o.gradient(xi),
+                   "g": lambda xi, li: o.constraints(xi), "jac": lambda xi, li: o.jacobian(xi),
+                   "hess": lambda xi, li: o.hessian(xi, li, sigma)}
+            for i in range(cb_iters):
+                for p in PROGS:
+                    t0 = time.perf_counter()
+                    fns[p](xs[i % npts], lams[i % npts])
+                    cb_e2e[p] += (time.perf_counter() - t0) * 1e3 / cb_iters
     clocks = clk.summary()
 
     if dist is not None:
@@ -550,7 +568,8 @@ def main():
                            "multi-start replicas: one start point per GPU, no collective",
                            l2="inputs larger than L2 (126 MB)" if total_alg > 2 * 126e6 else
                            "working set fits L2; no flush", nnz_jac=o.nnz_jac, nnz_hess=o.nnz_hess,
-                           compile_s=round(compile_s, 2), algorithmic_bytes_per_eval=int(total_alg)),
+                           compile_s=round(compile_s, 2), tape_from_cache=tape is not None,
+                           algorithmic_bytes_per_eval=int(total_alg)),
             "hbm_gbs_whole_eval": total_alg / (ms / args.steps * 1e-3) / 1e9,
             "clocks": clocks,
             "e2e": {"value": world * e2e_steps / (e2e_ms * 1e-3), "unit": "evals/s",
@@ -574,7 +593,10 @@ def main():
                          "peak_source": peak_src,
                          "share_of_step": float(per[top] / max(per.sum(), 1e-12))},
         }
-        if not args.no_cpu_baseline:
+        if args.device_only:
+            line["e2e"] = None
+            line["note"] = "--device-only profiling run: e2e legs skipped, not a bench line"
+        if not args.no_cpu_baseline and not args.device_only:
             v, d = cpu_port_evals_per_s(args.workload)
             line["cpu_baseline"] = {"value": v, "unit": "evals/s", "cores": 1, "kind": "port",
                                     "sample": d["sample"]}

@@ -32,11 +32,12 @@ class GpuOracles:
     ELIDE_MIN = 4096               # outputs shorter than this are always copied whole
     ELIDE_MAX_FRACTION = 0.5       # elide constants when at most this share of entries is dynamic
 
-    def __init__(self, problem_ir, device=0, pinned_outputs=True, with_hessian=True):
-        """``problem_ir``: a ``dnlp_b200.ir.ProblemIR`` (see frontend_cvxpy.data_to_ir)."""
+    def __init__(self, problem_ir, device=0, pinned_outputs=True, with_hessian=True, tape=None):
+        """``problem_ir``: a ``dnlp_b200.ir.ProblemIR`` (see frontend_cvxpy.data_to_ir).
+        ``tape``: an already compiled tape of this problem (skips the DAG compiler)."""
         self.problem = problem_ir
         self.with_hessian = with_hessian
-        self.tape = compile_problem(problem_ir, with_hessian=with_hessian)
+        self.tape = tape if tape is not None else compile_problem(problem_ir, with_hessian=with_hessian)
         self.dev = _cabi.DeviceTape(self.tape, device)
         self.n, self.m = self.tape.n, self.tape.m
         self.num_constraints = self.m

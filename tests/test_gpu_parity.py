@@ -552,5 +552,15 @@ def test_gpu_sigma_only_hessian_entries_are_kept_between_calls(name, layered, gp
                 assert got is o._hess
         if name in ("c2_eigen_qcqp_small", "portfolio_quadform"):
             assert o._hess_sigma_class and o._dyn["hess"][0].size < o.nnz_hess
+        if name == "c2_eigen_qcqp_small" and layered:
+            # the 2*sigma*Q layer is not re-launched while sigma stays the same: a new lambda costs the
+            # diagonal update and the compaction kernel only
+            o.hessian(xs[0], lams[0], 0.75)
+            k0 = o.kernel_launches()
+            o.hessian(xs[0], lams[1], 0.75)
+            k1 = o.kernel_launches()
+            o.hessian(xs[0], lams[1], 0.25)
+            k2 = o.kernel_launches()
+            assert k1 - k0 == 2 and k2 - k1 >= 2, (k0, k1, k2)
     finally:
         o.close()
