@@ -143,6 +143,11 @@ def _check(seed, make_evaluator):
     np.testing.assert_array_equal(tape.jac_cols, ref.jac_cols)
     np.testing.assert_array_equal(tape.hess_rows, ref.hess_rows)
     np.testing.assert_array_equal(tape.hess_cols, ref.hess_cols)
+    # scheduling metadata the CUDA engine relies on (parallel graph branches, validity flags)
+    from test_schedule_metadata import _derive
+    deps, masks = _derive(tape)
+    for ins in tape.instrs:
+        assert set(ins.deps) == deps[ins.id] and ins.dep_mask == masks[ins.id], "seed %d instr %d" % (seed, ins.id)
     ev = make_evaluator(prob, tape)
     with np.errstate(all="ignore"):
         for _ in range(2):
