@@ -15,7 +15,7 @@ import scipy.sparse as sp
 
 from . import ir
 from . import tape as T
-from .symvec import NONE, SymVec
+from .symvec import NONE, SymVec, stable_order
 
 
 def _flatF(v):
@@ -137,7 +137,7 @@ class Builder:
         owner = np.repeat(np.arange(sv.K, dtype=np.int64), nparts)
         keep = ~t_long
         row = np.concatenate([sv.row[keep], owner])
-        order = np.argsort(row, kind="stable")
+        order = stable_order(row, sv.K)
         none = np.full(P, NONE, dtype=np.int64)
         out = SymVec(sv.K, row[order],
                      np.concatenate([sv.coef[keep], np.ones(P)])[order],
@@ -478,7 +478,12 @@ class Builder:
         key = rows * (int(cols.max()) + 1) + cols
         if key.size < 2 or bool(np.all(key[1:] > key[:-1])):
             return rows, cols, sv
-        order = np.argsort(key, kind="stable")
+        nr, nc = int(rows.max()) + 1, int(cols.max()) + 1
+        if key.size >= (1 << 16) and max(nr, nc) <= 4 * key.size:
+            o1 = stable_order(cols, nc)                  # LSD radix: columns first, then rows
+            order = o1[stable_order(rows[o1], nr)]
+        else:
+            order = np.argsort(key, kind="stable")
         key = key[order]
         new = np.ones(key.size, dtype=bool)
         new[1:] = key[1:] != key[:-1]
@@ -649,7 +654,7 @@ class Builder:
             prow, pcol = P.coords[0].astype(np.int64), P.coords[1].astype(np.int64)
             # symbolic values
             br, bc, bv = self._coo_sum_duplicates(np.asarray(r, np.int64), np.asarray(c, np.int64), v)
-            order = np.argsort(br, kind="stable")
+            order = stable_order(br, A.shape[1])
             br, bc, bv = br[order], bc[order], bv.gather(order)
             bptr = np.zeros(A.shape[1] + 1, dtype=np.int64)
             np.cumsum(np.bincount(br, minlength=A.shape[1]), out=bptr[1:])

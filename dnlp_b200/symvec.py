@@ -18,6 +18,7 @@ tape instruction that evaluates it into fresh slots and continues with a SymVec 
 bare slots (``Builder.materialise``).
 """
 import numpy as np
+import scipy.sparse as sp
 
 NONE = -1
 
@@ -32,10 +33,21 @@ def _i32(a):
     return np.asarray(a, dtype=np.int32)
 
 
+def stable_order(key, K):
+    """``np.argsort(key, kind="stable")`` for integer keys in [0, K).  Large inputs go through SciPy's
+    COO -> CSR conversion, a C counting sort that keeps the input order inside a row (3-4x faster
+    than NumPy's merge sort on the 50 M-term vectors of config 5)."""
+    n = key.size
+    if n < (1 << 16) or K > 4 * n or n >= 2 ** 31 - 1 or K >= 2 ** 31 - 1:
+        return np.argsort(key, kind="stable")
+    m = sp.coo_matrix((np.ones(n, dtype=np.int8), (key, np.arange(n, dtype=np.int32))), shape=(int(K), n))
+    return m.tocsr().indices.astype(np.int64)      # column = original position, ascending inside a row
+
+
 def _sorted_by_row(K, row, coef, f1, f2):
     """SymVec with terms stably ordered by entry; skips the sort when already ordered."""
     if row.size > 1 and np.any(row[1:] < row[:-1]):
-        order = np.argsort(row, kind="stable")
+        order = stable_order(row, K)
         return SymVec(K, row[order], coef[order], f1[order], f2[order])
     return SymVec(K, row, coef, f1, f2)
 

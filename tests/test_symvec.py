@@ -78,3 +78,32 @@ def test_simplify_merges_like_terms_and_drops_zeros():
     assert s.nterms == 2                   # entry 0: 3*V0 ; entry 1: 0*V1 dropped, const 5 kept
     z = SymVec.slots([2, 3]).add(SymVec.const([0.0, 0.0])).drop_zero_constants()
     assert z.nterms == 2 and z.is_unit()
+
+
+def test_stable_order_counting_sort_equals_stable_argsort():
+    """Large inputs take the SciPy counting-sort path; it must be the same permutation."""
+    from dnlp_b200.symvec import stable_order
+    rng = np.random.default_rng(0)
+    for n, K in ((70_000, 10), (200_000, 50_000), (100_000, 399_999), (65_536, 1), (1000, 7)):
+        key = rng.integers(0, K, n)
+        np.testing.assert_array_equal(stable_order(key, K), np.argsort(key, kind="stable"))
+        np.testing.assert_array_equal(stable_order(key.astype(np.int32), K), np.argsort(key, kind="stable"))
+
+
+def test_coo_sum_duplicates_radix_path_equals_key_sort():
+    from dnlp_b200.rules import Builder
+    from dnlp_b200.symvec import SymVec
+    rng = np.random.default_rng(1)
+    n, nr, nc = 150_000, 3000, 2500
+    rows, cols = rng.integers(0, nr, n), rng.integers(0, nc, n)
+    sv = SymVec(n, np.arange(n), rng.standard_normal(n), rng.integers(0, 50, n), np.full(n, -1))
+    r, c, out = Builder._coo_sum_duplicates(rows, cols, sv)
+    key = rows * nc + cols
+    uniq = np.unique(key)
+    np.testing.assert_array_equal(r * nc + c, uniq)
+    # same sums, same order of the terms inside every merged entry (stable)
+    order = np.argsort(key, kind="stable")
+    grp = np.searchsorted(uniq, key[order])
+    np.testing.assert_array_equal(out.row, grp)
+    np.testing.assert_array_equal(out.coef, sv.coef[order])
+    np.testing.assert_array_equal(out.f1, sv.f1[order])
