@@ -111,7 +111,10 @@ struct dnlp_oracle {
   int cur_lane = 0;
   std::vector<cudaEvent_t> ev_pool;    // capture-time dependency markers
   bool parallel_enabled = true;
-  bool win_enabled = true;             // shared-memory gather window of the flat kernel
+  bool win_enabled = false;            // shared-memory gather window of the flat kernel.  OFF by default:
+                                       // on the C3 SpMV (x in R^4096) the window costs bank conflicts and
+                                       // MIO pressure while plain gathers hit L1 - 0.104 ms with, 0.086 ms
+                                       // (5.7 TB/s, 87 % of peak) without; kept for A/B (dnlp_set_windows)
   bool fuse_enabled = true;            // family fusion of phi / phi' / phi'' in the elementwise batch
   bool flat_enabled = true;            // flat term-streaming SpMV (poly_flat_kernel)
   int poly1_grid_mult = 8;             // CTAs per SM of the one-term-per-row streaming kernel (A/B on C5:
@@ -723,7 +726,8 @@ static int create_impl(dnlp_oracle *o, const dnlp_tape_desc *t) {
   if (const char *e = getenv("DNLP_FLAT_MIN_TERMS")) o->flat_min_terms = atoll(e);  // tests: force the flat kernel
   if (const char *e = getenv("DNLP_NO_FLAT")) o->flat_enabled = atoi(e) == 0;
   if (const char *e = getenv("DNLP_POLY1_GRID_MULT")) o->poly1_grid_mult = atoi(e) > 0 ? atoi(e) : 4;
-  if (const char *e = getenv("DNLP_NO_WINDOWS")) o->win_enabled = atoi(e) == 0;
+  if (const char *e = getenv("DNLP_WINDOWS")) o->win_enabled = atoi(e) != 0;
+  if (const char *e = getenv("DNLP_NO_WINDOWS")) o->win_enabled = atoi(e) == 0 && o->win_enabled;
   if (const char *e = getenv("DNLP_NO_ELEM_FUSION")) o->fuse_enabled = atoi(e) == 0;  // tests / A-B measurements
 
   void *p = nullptr;

@@ -392,6 +392,12 @@ def test_gpu_medium_logistic_window(gpu_mod):
     o = gpu_mod(prob)
     try:
         o.constraints(prob.x0)
+        assert any(o.instr_kernel(i).startswith("poly_flat_kernel<0, 0") for i in range(len(o.tape.instrs)))
+        plain = np.array(o.constraints(prob.x0), copy=True)
+        o.set_windows(True)                 # off by default (slower on B200); same bits when switched on
+        o.set_cache(False)
+        o.set_cache(True)
+        np.testing.assert_array_equal(plain, o.constraints(prob.x0))
         assert any(o.instr_kernel(i).startswith("poly_flat_kernel<0, 1") for i in range(len(o.tape.instrs)))
     finally:
         o.close()
@@ -451,6 +457,7 @@ def test_gpu_flat_term_streaming_kernel(name, layered, gpu_mod, monkeypatch):
         monkeypatch.setattr(Builder, "LAYER_MIN", 2)
     g = Golden(name)
     o = gpu_mod(g.problem)
+    o.set_windows(True)                   # first round with the window, second without
     try:
         for rnd in range(2):
             for i, p in enumerate(g.points):

@@ -107,11 +107,41 @@ int main(int argc, char **argv) {
     ms = time_it([&] { poly_uniform_tile_kernel<R, false><<<SM * G, R, sm>>>(V, d, L, c, f1, nullptr, nullptr, rows, 0); }); \
     printf("%s v2 tile rows/cta=%-4d grid=SMx%-2d %8.3f ms  %7.1f GB/s\n", name, R, G, ms, bytes / ms / 1e6); }
     ST(256, 8)
+    {  // flat term-streaming kernel: host-side chunking exactly as dnlp_cabi.cu does it
+      std::vector<int32_t> row0; std::vector<int64_t> term0;
+      for (int64_t R = 0; R < rows;) {
+        const int64_t a0 = (R * L) & ~(int64_t)1;
+        int64_t Rn = R;
+        while (Rn < rows && (Rn + 1) * L <= a0 + FLAT_CHUNK) ++Rn;
+        row0.push_back((int32_t)R); term0.push_back(a0); R = Rn;
+      }
+      row0.push_back((int32_t)rows);
+      const int64_t nchunks = (int64_t)term0.size();
+      int32_t *dr; int64_t *dt;
+      CHECK(cudaMalloc(&dr, row0.size() * 4)); CHECK(cudaMalloc(&dt, term0.size() * 8));
+      CHECK(cudaMemcpy(dr, row0.data(), row0.size() * 4, cudaMemcpyHostToDevice));
+      CHECK(cudaMemcpy(dt, term0.data(), term0.size() * 8, cudaMemcpyHostToDevice));
+      const int64_t need = (nchunks + FLAT_WARPS - 1) / FLAT_WARPS;
+      for (int per_sm : {2, 4}) {
+        const int grid = (int)(need < (int64_t)SM * per_sm ? need : (int64_t)SM * per_sm);
+        ms = time_it([&] { poly_flat_kernel<false, false, false><<<grid, 256>>>(V, d, nullptr, L, c, f1, nullptr, nullptr, nt, 0, dr, dt, nchunks, 0, 0, 31); });
+        printf("%s v5 flat          grid=SMx%-2d %8.3f ms  %7.1f GB/s\n", name, per_sm, ms, bytes / ms / 1e6);
+      }
+      if (ncols <= 33 * 256) {
+        CHECK(cudaFuncSetAttribute(poly_flat_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+        CHECK(cudaFuncSetAttribute(poly_flat_kernel<false, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        const int grid = (int)(need < (int64_t)SM * 4 ? need : (int64_t)SM * 4);
+        ms = time_it([&] { poly_flat_kernel<false, true, false><<<grid, 256, ncols * 8>>>(V, d, nullptr, L, c, f1, nullptr, nullptr, nt, 0, dr, dt, nchunks, 0, (int)ncols, 31); });
+        printf("%s v5 flat + window grid=SMx4  %8.3f ms  %7.1f GB/s\n", name, ms, bytes / ms / 1e6);
+      }
+      cudaFree(dr); cudaFree(dt);
+    }
     cudaFree(V); cudaFree(c); cudaFree(d); cudaFree(f1);
   };
   if (w == "all" || w == "spmv") {
     spmv("spmv5 ", 5000000, 10, 10000000);
     spmv("spmv3 ", 2000000, 16, 4096);
+    spmv("spmv3o", 2000000, 17, 4096);     // odd row length: chunk windows start at odd rows (C3 has 17 terms per row)
     spmv("spmvT ", 10000000, 5, 5000000);
   }
 
