@@ -39,6 +39,48 @@ __global__ void copy_kernel(const double2 *a, double2 *b, int64_t n2) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) b[i] = a[i];
 }
 
+// ---- experiments that are NOT in the library yet (candidates for the next round) -----------------
+// One term per row with the NEXT batch's streams requested before the CURRENT batch's gathers: the
+// Jacobian fill of config 5 is latency bound (ncu: 47 % DRAM throughput, gathers half L2 hits), so the
+// stream latency should hide behind the gather latency.
+template <int U>
+__global__ void __launch_bounds__(256)
+poly1_pipe_kernel(const double *__restrict__ V, double *__restrict__ dst, const double *__restrict__ coef,
+                  const int32_t *__restrict__ f1, int64_t count) {
+  const uint64_t pf = l2_policy_evict_first(), pl = l2_policy_evict_last();
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double c[U];
+  int a[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int64_t i = k + u * stride;
+    c[u] = i < count ? ld_stream_f64(coef + i, pf) : 0.0;
+    a[u] = i < count ? ld_stream_s32(f1 + i, pf) : -1;
+  }
+  for (; k < count; k += U * stride) {
+    double cn[U];
+    int an[U];
+    const int64_t kn = k + U * stride;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = kn + u * stride;
+      cn[u] = i < count ? ld_stream_f64(coef + i, pf) : 0.0;
+      an[u] = i < count ? ld_stream_s32(f1 + i, pf) : -1;
+    }
+    double v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = c[u] * gather_slot(V, a[u], pl);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = k + u * stride;
+      if (i < count) st_stream_f64(dst + i, v[u], pf);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) { c[u] = cn[u]; a[u] = an[u]; }
+  }
+}
+
 int main(int argc, char **argv) {
   const char *which = argc > 1 ? argv[1] : "all";
   std::string w(which);
@@ -127,6 +169,11 @@ int main(int argc, char **argv) {
         ms = time_it([&] { poly_flat_kernel<false, false, false><<<grid, 256>>>(V, d, nullptr, L, c, f1, nullptr, nullptr, nt, 0, dr, dt, nchunks, 0, 0, 31); });
         printf("%s v5 flat          grid=SMx%-2d %8.3f ms  %7.1f GB/s\n", name, per_sm, ms, bytes / ms / 1e6);
       }
+      if ((L & 1) == 0) {      // even rows: the library would pick a padding (one double pair per 16 terms)
+        const int grid = (int)(need < (int64_t)SM * 4 ? need : (int64_t)SM * 4);
+        ms = time_it([&] { poly_flat_kernel<false, false, true><<<grid, 256>>>(V, d, nullptr, L, c, f1, nullptr, nullptr, nt, 0, dr, dt, nchunks, 0, 0, 4); });
+        printf("%s v5 flat padded   grid=SMx4  %8.3f ms  %7.1f GB/s\n", name, ms, bytes / ms / 1e6);
+      }
       if (ncols <= 33 * 256) {
         CHECK(cudaFuncSetAttribute(poly_flat_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
         CHECK(cudaFuncSetAttribute(poly_flat_kernel<false, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
@@ -157,6 +204,9 @@ int main(int argc, char **argv) {
 #define P1(U, G) ms = time_it([&] { poly1_stream_kernel<U, false><<<SM * G, 256>>>(V, d, c, f1, nullptr, nullptr, n, 0); }); \
     printf("poly1  v2 U=%d grid=SMx%-2d         %8.3f ms  %7.1f GB/s\n", U, G, ms, bytes / ms / 1e6);
     P1(1, 8) P1(2, 8) P1(4, 8) P1(4, 4) P1(8, 4) P1(8, 8)
+#define PP(U, G) ms = time_it([&] { poly1_pipe_kernel<U><<<SM * G, 256>>>(V, d, c, f1, n); }); \
+    printf("poly1  pipelined U=%d grid=SMx%-2d  %8.3f ms  %7.1f GB/s\n", U, G, ms, bytes / ms / 1e6);
+    PP(2, 8) PP(4, 8) PP(4, 4) PP(8, 4)
     cudaFree(V); cudaFree(c); cudaFree(d); cudaFree(f1); cudaFree(f2);
   }
   return 0;
