@@ -159,9 +159,25 @@ def cpu_port_evals_per_s(name, budget_s=20.0):
     if name == "c2":
         n_s = desc["n"]
         full = (8192.0 / n_s) ** 2
+    # the extrapolation assumes linear cost: check it on a second, half-size sample (SURVEY 8d asks
+    # for the measured scaling next to extrapolated numbers)
+    linearity = ""
+    if name in ("c3", "c5"):
+        prob2, _ = build_workload(name, sample_scale / 2)
+        o2 = RefOracles(prob2)
+        o2.jacobianstructure(), o2.hessianstructure()
+        x2, lam2, _ = eval_point(prob2, 0)
+        t2, r2 = 0.0, 0
+        with np.errstate(all="ignore"):
+            while r2 < 3 or (t2 < budget_s / 4 and r2 < 25):
+                t0 = time.perf_counter()
+                o2.objective(x2), o2.gradient(x2), o2.constraints(x2), o2.jacobian(x2), o2.hessian(x2, lam2, sigma)
+                t2 += time.perf_counter() - t0
+                r2 += 1
+        linearity = "; half-size sample %.4f s/eval -> time ratio %.2f for a size ratio of 2" % (t2 / r2, per_eval / (t2 / r2))
     return 1.0 / (per_eval * full), {
         "sample": "%s; %d full evals in %.1f s (%.4f s/eval at sample size), scaled x%.1f by triplet count "
-                  "to the full workload" % (desc["workload"], reps, t_total, per_eval, full),
+                  "to the full workload%s" % (desc["workload"], reps, t_total, per_eval, full, linearity),
         "seconds_per_eval_at_sample": per_eval, "scale_factor": full}
 
 
