@@ -119,3 +119,47 @@ def test_best_of_style_reapplied_chain_reuses_the_compiled_oracle(cp, monkeypatc
         assert d3["oracles"] is o1 and d3["oracles"].iterations == 0
         d4 = _chain(cp, build(np.ones(5), rhs=2.0))                      # another constant: another oracle
         assert d4["oracles"] is not o1
+
+
+def test_reference_best_of_loop_compiles_once(cp, monkeypatch):
+    """The reference's own best_of problem (tests/NLP_tests/test_best_of.py:11-33) driven the way
+    Problem._solve drives it (problems/problem.py:1262-1266): a random initial point per run, the
+    chain re-applied every time.  One compile, best_of - 1 cache hits, the same structures throughout."""
+    import dnlp_b200.nlp_solver as gpu
+    from dnlp_b200 import _cabi
+
+    class FakeDevice:
+        def __init__(self, tape, device=0):
+            self.tape = tape
+
+        def close(self):
+            pass
+    monkeypatch.setattr(_cabi, "DeviceTape", FakeDevice)
+    monkeypatch.setattr(_cabi, "pinned_empty", lambda k: (np.empty(k), types.SimpleNamespace(free=lambda: None)))
+    rng = np.random.default_rng(5)
+    n = 5
+    radius = rng.uniform(1.0, 3.0, n)
+    centers = cp.Variable((n, 2), name="c")
+    constraints = []
+    for i in range(n - 1):
+        constraints += [cp.sum((centers[i, :] - centers[i + 1:, :]) ** 2, axis=1) >= (radius[i] + radius[i + 1:]) ** 2]
+    prob = cp.Problem(cp.Minimize(cp.max(cp.norm_inf(centers, axis=1) + radius)), constraints)
+    centers.sample_bounds = [-5.0, 5.0]
+    n_runs = 4
+    with gpu.gpu_oracle():
+        gpu.ORACLE_CACHE.hits = gpu.ORACLE_CACHE.misses = 0
+        seen, starts = [], []
+        for run in range(n_runs):
+            prob.set_random_NLP_initial_point(run)
+            data = _chain(cp, prob)
+            seen.append(data["oracles"])
+            starts.append(np.array(data["x0"], copy=True))
+            np.testing.assert_array_equal(data["oracles"].initial_point, data["x0"])
+        assert all(o is seen[0] for o in seen)
+        assert (gpu.ORACLE_CACHE.hits, gpu.ORACLE_CACHE.misses) == (n_runs - 1, 1)
+        assert not np.array_equal(starts[0], starts[1])
+    ref = _chain(cp, prob)["oracles"]                                   # the reference's own object again
+    for a, b in zip(seen[0].jacobianstructure(), ref.jacobianstructure()):
+        np.testing.assert_array_equal(a, b)
+    for a, b in zip(seen[0].hessianstructure(), ref.hessianstructure()):
+        np.testing.assert_array_equal(a, b)
