@@ -163,3 +163,42 @@ def test_reference_best_of_loop_compiles_once(cp, monkeypatch):
         np.testing.assert_array_equal(a, b)
     for a, b in zip(seen[0].hessianstructure(), ref.hessianstructure()):
         np.testing.assert_array_equal(a, b)
+
+
+def test_parameter_values_are_compile_time_constants(cp, monkeypatch):
+    """A cvxpy Parameter reaches the oracle as a constant (the reference evaluates `.value` inside its
+    rules): the same value reuses the compiled oracle, a new value is a new fingerprint and a recompile
+    whose constants follow the parameter (Parameter slots are not built yet)."""
+    import dnlp_b200.nlp_solver as gpu
+    from dnlp_b200 import _cabi
+    from tape_interp import TapeInterp
+
+    class FakeDevice:
+        def __init__(self, tape, device=0):
+            self.tape = tape
+
+        def close(self):
+            pass
+    monkeypatch.setattr(_cabi, "DeviceTape", FakeDevice)
+    monkeypatch.setattr(_cabi, "pinned_empty", lambda k: (np.empty(k), types.SimpleNamespace(free=lambda: None)))
+    gamma = cp.Parameter(nonneg=True)
+    b = cp.Parameter(3)
+    x = cp.Variable(3)
+    x.value = np.array([0.3, 0.5, 0.2])
+    prob = cp.Problem(cp.Minimize(cp.sum(cp.exp(x)) + gamma * cp.sum_squares(x - b)), [cp.sum(x) == 1])
+    with gpu.gpu_oracle():
+        gpu.ORACLE_CACHE.hits = gpu.ORACLE_CACHE.misses = 0
+        gamma.value, b.value = 0.5, np.array([1.0, 2.0, 3.0])
+        d1 = _chain(cp, prob)
+        o1 = d1["oracles"]
+        f1 = TapeInterp(o1.tape).eval("f", d1["x0"])
+        assert _chain(cp, prob)["oracles"] is o1                          # same values: reused
+        gamma.value = 2.0
+        d2 = _chain(cp, prob)
+        o2 = d2["oracles"]
+        assert o2 is not o1 and gpu.ORACLE_CACHE.misses == 2
+        f2 = TapeInterp(o2.tape).eval("f", d2["x0"])
+    xv = np.array([0.3, 0.5, 0.2])
+    want = lambda g: np.exp(xv).sum() + g * ((xv - np.array([1.0, 2.0, 3.0])) ** 2).sum()   # noqa: E731
+    np.testing.assert_allclose(f1, want(0.5), rtol=1e-12)
+    np.testing.assert_allclose(f2, want(2.0), rtol=1e-12)
