@@ -287,7 +287,7 @@ def bench_multistart(args, rank, local_rank, world, dist, metric, hbm_peak, peak
     from dnlp_b200 import workloads as W
     from dnlp_b200.multistart import BatchedOracles
     n, k = max(16, int(512 * args.scale)), 8
-    Btot = max(world, int(4096 * args.scale))
+    Btot = int(os.environ.get("DNLP_C4_BATCH", max(world, int(4096 * args.scale))))
     P, q, rng = W.qcqp_data(n, k)
     prob = W.qcqp(P, q)
     X = rng.uniform(-1, 1, (Btot, n))                       # the same rng stream as SURVEY 8(d) C4

@@ -169,6 +169,12 @@ def make_tape_desc(tape):
     until dnlp_create / dnlp_batch_create has copied them to the device."""
     keep = []
     n_instr = len(tape.instrs)
+    # slot indices, scatter positions and pattern indices are int32 on the device
+    i32max = int(np.iinfo(np.int32).max)
+    for what, v in (("value slots", tape.nslots), ("Jacobian entries", tape.jac_rows.size),
+                    ("Hessian entries", tape.hess_rows.size)):
+        if int(v) > i32max:
+            raise OverflowError("dnlp_b200: %d %s exceed the int32 index range of the device tape" % (int(v), what))
     arr = (InstrDesc * max(n_instr, 1))()
     for i, ins in enumerate(tape.instrs):
         d = arr[i]
@@ -246,12 +252,14 @@ class DeviceTape:
 
     def check(self, rc):
         if rc != 0:
+            if not self.h:
+                raise RuntimeError("dnlp_b200: oracle closed")
             raise RuntimeError("dnlp_b200: %s" % self._L.dnlp_last_error(self.h).decode())
 
     def close(self):
         if getattr(self, "h", None):
             self._L.dnlp_destroy(self.h)
-            self.h = None
+            self.h = None       # later calls pass NULL, which every entry point rejects (rc != 0)
 
     def __del__(self):
         try:
@@ -276,6 +284,8 @@ class DeviceBatch:
 
     def check(self, rc):
         if rc != 0:
+            if not self.h:
+                raise RuntimeError("dnlp_b200: oracle closed")
             raise RuntimeError("dnlp_b200: %s" % self._L.dnlp_batch_last_error(self.h).decode())
 
     def close(self):

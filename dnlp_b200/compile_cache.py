@@ -22,17 +22,28 @@ _VAR_ATTRS_IGNORED = ("id", "name", "value", "lb", "ub")
 def _feed_array(h, a):
     a = np.ascontiguousarray(a)
     h.update(str((a.dtype.str, a.shape)).encode())
-    h.update(memoryview(a).cast("B"))
+    if a.size:                                   # (memoryview.cast rejects shapes with a zero in them)
+        h.update(a.reshape(-1).view(np.uint8))
 
 
 def _feed_value(h, v):
     if sp.issparse(v):
-        c = sp.csc_array(v)
-        c.sum_duplicates()
-        h.update(b"sparse" + str(c.shape).encode())
-        _feed_array(h, c.indptr)
-        _feed_array(h, c.indices)
-        _feed_array(h, np.asarray(c.data, np.float64))
+        # the stored format and the raw index order enter the digest: the rules emit triplets in the
+        # constant's own COO order (rules.py `_tag_matrix`), so two constants with the same entries in a
+        # different storage order produce differently ordered patterns
+        h.update(("sparse:%s%s" % (v.format, v.shape)).encode())
+        if v.format in ("csr", "csc", "bsr"):
+            _feed_array(h, v.indptr)
+            _feed_array(h, v.indices)
+        elif v.format == "coo":
+            _feed_array(h, v.coords[0] if hasattr(v, "coords") else v.row)
+            _feed_array(h, v.coords[1] if hasattr(v, "coords") else v.col)
+        else:
+            c = sp.coo_array(v)
+            _feed_array(h, c.coords[0])
+            _feed_array(h, c.coords[1])
+            v = c
+        _feed_array(h, np.asarray(v.data, np.float64))
     elif isinstance(v, np.ndarray):
         _feed_array(h, v)
     elif isinstance(v, Fraction):
@@ -81,20 +92,22 @@ def fingerprint(prob):
 
 
 class OracleCache:
-    """Small LRU of live oracles keyed by ``fingerprint``.  Evicted oracles are closed (their HBM is
-    released); ``clear`` closes everything."""
+    """Small LRU of live oracles keyed by ``fingerprint`` (plus whatever the caller adds: device,
+    build options).  Evicted oracles are only DROPPED, never closed here: the caller may still hold
+    them (``data['oracles']`` and the bound callbacks of ``get_problem_data``), and an oracle frees its
+    HBM by itself when the last reference goes away (``GpuOracles.__del__``)."""
 
     def __init__(self, capacity=2):
         self.capacity = int(capacity)
         self._items = OrderedDict()
         self.hits = self.misses = 0
 
-    def get(self, prob, build):
+    def get(self, prob, build, extra_key=()):
         """``build(prob)`` -> oracle is called on a miss.  Returns (oracle, hit)."""
         if self.capacity <= 0:
             self.misses += 1
             return build(prob), False
-        key = fingerprint(prob)
+        key = (fingerprint(prob),) + tuple(extra_key)
         if key in self._items:
             self._items.move_to_end(key)
             self.hits += 1
@@ -103,15 +116,8 @@ class OracleCache:
         o = build(prob)
         self._items[key] = o
         while len(self._items) > self.capacity:
-            _, old = self._items.popitem(last=False)
-            close = getattr(old, "close", None)
-            if close:
-                close()
+            self._items.popitem(last=False)
         return o, False
 
     def clear(self):
-        while self._items:
-            _, old = self._items.popitem()
-            close = getattr(old, "close", None)
-            if close:
-                close()
+        self._items.clear()

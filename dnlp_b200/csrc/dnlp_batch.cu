@@ -232,6 +232,7 @@ void dnlp_batch_destroy(dnlp_batch *o) {
 }
 
 static int batch_create_impl(dnlp_batch *o, const dnlp_tape_desc *t) {
+  if (o == nullptr) { g_batch_create_error = "batch handle is NULL (closed or never created)"; return 1; }
   std::string &err = o->err;
   CKB(cudaSetDevice(o->device));
   cudaDeviceProp prop;
@@ -361,6 +362,7 @@ int dnlp_batch::reset_outputs() {
 extern "C" {
 
 int dnlp_batch_upload(dnlp_batch *o, const double *X, const double *LAM, const double *SIGMA) {
+  if (o == nullptr) { g_batch_create_error = "batch handle is NULL (closed or never created)"; return 1; }
   std::string &err = o->err;
   CKB(cudaSetDevice(o->device));
   if (o->put(X, o->V, o->n)) return 1;
@@ -372,6 +374,7 @@ int dnlp_batch_upload(dnlp_batch *o, const double *X, const double *LAM, const d
 
 int dnlp_batch_eval(dnlp_batch *o, const double *X, const double *LAM, const double *SIGMA,
                     double *F, double *GRAD, double *G, double *JAC, double *HESS) {
+  if (o == nullptr) { g_batch_create_error = "batch handle is NULL (closed or never created)"; return 1; }
   std::string &err = o->err;
   CKB(cudaSetDevice(o->device));
   if (o->put(X, o->V, o->n)) return 1;
@@ -396,6 +399,7 @@ int dnlp_batch_eval(dnlp_batch *o, const double *X, const double *LAM, const dou
 }
 
 int dnlp_batch_run_device(dnlp_batch *o, int32_t prog_mask, int32_t iters, float *elapsed_ms) {
+  if (o == nullptr) { g_batch_create_error = "batch handle is NULL (closed or never created)"; return 1; }
   std::string &err = o->err;
   CKB(cudaSetDevice(o->device));
   CKB(cudaEventRecord(o->ev0, o->stream));
@@ -410,6 +414,7 @@ int dnlp_batch_run_device(dnlp_batch *o, int32_t prog_mask, int32_t iters, float
 }
 
 int dnlp_batch_profile_instrs(dnlp_batch *o, int32_t p, int32_t iters, float *ms_per_instr) {
+  if (o == nullptr) { g_batch_create_error = "batch handle is NULL (closed or never created)"; return 1; }
   std::string &err = o->err;
   CKB(cudaSetDevice(o->device));
   for (size_t i = 0; i < o->instrs.size(); ++i) ms_per_instr[i] = 0.f;
@@ -428,6 +433,6 @@ int dnlp_batch_profile_instrs(dnlp_batch *o, int32_t p, int32_t iters, float *ms
   return 0;
 }
 
-int64_t dnlp_batch_kernel_launches(dnlp_batch *o) { return o->launches; }
+int64_t dnlp_batch_kernel_launches(dnlp_batch *o) { return o ? o->launches : -1; }
 
 }  // extern "C"

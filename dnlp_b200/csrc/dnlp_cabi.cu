@@ -372,8 +372,8 @@ int dnlp_oracle::launch(DevInstr &I) {
         int64_t blocks = (d.count + 7) / 8;
         int64_t cap = (int64_t)sm_count * (in_smem && smem > 48 * 1024 ? 2 : 4);
         int grid = (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
-        gemv_kernel<8><<<grid, 256, smem, cur>>>(d.Q, V, d.x_off, dst, d.count, d.ncols, d.alpha, in_smem);
-        if (I.kname.empty()) I.kname = "gemv_kernel<8>";
+        dnlp_gemv_rows_kernel<8><<<grid, 256, smem, cur>>>(d.Q, V, d.x_off, dst, d.count, d.ncols, d.alpha, in_smem);
+        if (I.kname.empty()) I.kname = "dnlp_gemv_rows_kernel<8>";
       }
       break;
     }
@@ -864,7 +864,7 @@ static int create_impl(dnlp_oracle *o, const dnlp_tape_desc *t) {
   }
   if (o->build_batches()) return 1;
   // opt in to > 48 KB dynamic shared memory for the GEMV x tile
-  CK(cudaFuncSetAttribute(dnlp::gemv_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+  CK(cudaFuncSetAttribute(dnlp::dnlp_gemv_rows_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
   CK(cudaFuncSetAttribute(dnlp::gemv_cta_kernel<4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
 #define FA(H, Pd)                                                                                                       \
   CK(cudaFuncSetAttribute(dnlp::poly_flat_kernel<H, true, Pd>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024)); \
@@ -888,7 +888,9 @@ int dnlp_create(const dnlp_tape_desc *t, int device, dnlp_oracle **out) {
   return 0;
 }
 
+// a NULL handle (an oracle that was closed, or never created) is an error, not a crash
 #define ENTER(o)                                   \
+  if ((o) == nullptr) { g_create_error = "oracle handle is NULL (closed or never created)"; return 1; } \
   std::string &err = (o)->err;                     \
   CK(cudaSetDevice((o)->device))
 
@@ -982,6 +984,7 @@ int dnlp_run(dnlp_oracle *o, int32_t prog, const double *x, const double *lam, d
 }
 
 void *dnlp_output_ptr(dnlp_oracle *o, int32_t space) {
+  if (!o) return nullptr;
   if (space < DNLP_DST_F || space > DNLP_DST_HESS) return nullptr;
   return o->out[space];
 }
@@ -1082,14 +1085,16 @@ int dnlp_read_output(dnlp_oracle *o, int32_t space, double *out) {
   return 0;
 }
 
-int64_t dnlp_kernel_launches(dnlp_oracle *o) { return o->launches; }
+int64_t dnlp_kernel_launches(dnlp_oracle *o) { return o ? o->launches : -1; }
 
 const char *dnlp_instr_kernel(dnlp_oracle *o, int32_t instr) {
+  if (!o) return "";
   if (instr < 0 || (size_t)instr >= o->instrs.size()) return "";
   return o->instrs[instr].kname.c_str();
 }
 
 int dnlp_set_graphs(dnlp_oracle *o, int32_t enabled) {
+  if (!o) return 1;
   o->graphs_enabled = enabled != 0;
   return 0;
 }
@@ -1114,6 +1119,7 @@ int dnlp_set_windows(dnlp_oracle *o, int32_t enabled) {
 }
 
 int dnlp_set_cache(dnlp_oracle *o, int32_t enabled) {
+  if (!o) return 1;
   o->cache_enabled = enabled != 0;
   o->have_last_x = false;
   std::fill(o->valid.begin(), o->valid.end(), 0);

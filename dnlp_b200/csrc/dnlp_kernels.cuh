@@ -132,7 +132,7 @@ elem_kernel(double *__restrict__ V, int64_t a_off, int a_stride, int64_t b_off, 
 }
 
 // ---- K2/K3/K4/K5: POLY - segmented sums of coef * V[f1] * V[f2] --------------------------
-// (poly_kernel / poly1_kernel / gemv_kernel / scale_kernel below are the first-cut versions; the
+// (poly_kernel / poly1_kernel / dnlp_gemv_rows_kernel / scale_kernel below are the first-cut versions; the
 //  library now launches the tuned variants further down and keeps these as the measured baselines
 //  of tools/kbench and as the general fallbacks for odd shapes.)
 // One kernel covers CSR SpMV (A@x, A^T lambda on the CSC copy), Jacobian value fill
@@ -193,7 +193,7 @@ poly1_kernel(const double *__restrict__ V, double *__restrict__ dst, const doubl
 // n = 8192), one warp per row, 8 independent 16-byte loads in flight per lane.
 template <int UNROLL>
 __global__ void __launch_bounds__(256)
-gemv_kernel(const double *__restrict__ Q, const double *__restrict__ V, int64_t x_off,
+dnlp_gemv_rows_kernel(const double *__restrict__ Q, const double *__restrict__ V, int64_t x_off,
             double *__restrict__ dst, int64_t nrows, int64_t ncols, double alpha, int x_in_smem) {
   extern __shared__ __align__(16) double xs[];
   const double *__restrict__ x = V + x_off;

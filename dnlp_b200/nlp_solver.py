@@ -37,7 +37,7 @@ def gpu_oracles(problem, initial_point, num_constraints):
     pir = problem_to_ir(problem, x0=initial_point)
     if pir.m != num_constraints:
         raise ValueError("constraint count mismatch: IR has %d rows, caller says %d" % (pir.m, num_constraints))
-    oracle, hit = ORACLE_CACHE.get(pir, lambda p: GpuOracles(p, device=DEVICE))
+    oracle, hit = ORACLE_CACHE.get(pir, lambda p: GpuOracles(p, device=DEVICE), extra_key=(("device", DEVICE),))
     if hit:
         oracle.rearm(pir)
     return oracle
@@ -45,6 +45,8 @@ def gpu_oracles(problem, initial_point, num_constraints):
 
 def install(device=0):
     global DEVICE
+    if device != DEVICE:
+        ORACLE_CACHE.clear()       # resident oracles live on the previous device
     DEVICE = device
     mod = importlib.import_module(_REF_MODULE)
     if "Oracles" not in _saved:

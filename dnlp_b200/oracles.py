@@ -118,9 +118,13 @@ class GpuOracles:
         return pos, compact
 
     def _stage_lam(self, duals):
-        lam = np.ascontiguousarray(duals, dtype=np.float64).reshape(-1)
-        if lam.size != self.m:
-            raise ValueError("duals has %d entries, expected %d" % (lam.size, self.m))
+        # the reference only slices duals[offset:offset + size] per constraint (nlp_solver.py:405-411), so
+        # a longer vector is accepted: Knitro hands over constraint AND variable-bound multipliers
+        # (evalRequest.lambda_, knitro_nlpif.py:284-291)
+        lam = np.asarray(duals, dtype=np.float64).reshape(-1)
+        if lam.size < self.m:
+            raise ValueError("duals has %d entries, expected at least %d" % (lam.size, self.m))
+        lam = np.ascontiguousarray(lam[:self.m])
         self._lam_ref = lam if self.m else self._lam      # m = 0: any valid pointer
         return self._lam_ref
 

@@ -62,13 +62,41 @@ def test_oracle_cache_lru_and_eviction():
     o1c, hit = c.get(_problem(), _FakeOracle)                            # refreshes o1
     assert hit and o1c is o1
     c.get(_problem(seed=2), _FakeOracle)                                 # evicts o2 (least recently used)
-    assert _FakeOracle.closed == 1
+    assert _FakeOracle.closed == 0        # evicted oracles are dropped, never closed: a caller may still hold them
     _, hit = c.get(_problem(seed=1), _FakeOracle)
     assert not hit
     assert (c.hits, c.misses) == (2, 4)
     c.clear()
-    assert _FakeOracle.closed == 4
+    assert _FakeOracle.closed == 0 and len(c._items) == 0
+    # the extra key separates devices / build options
+    d = OracleCache(capacity=4)
+    a0, _ = d.get(_problem(), _FakeOracle, extra_key=(("device", 0),))
+    a1, hit = d.get(_problem(), _FakeOracle, extra_key=(("device", 1),))
+    assert not hit and a1 is not a0
+    a0b, hit = d.get(_problem(), _FakeOracle, extra_key=(("device", 0),))
+    assert hit and a0b is a0
     off = OracleCache(capacity=0)
     a, _ = off.get(_problem(), _FakeOracle)
     b, hit = off.get(_problem(), _FakeOracle)
     assert a is not b and not hit
+
+
+def test_fingerprint_zero_size_and_sparse_order():
+    """a constant with an empty dimension must not crash the digest; two sparse constants
+    with the same entries in a different storage order are different tapes (the rules emit triplets in
+    the constant's own COO order)."""
+    import scipy.sparse as sp
+    from dnlp_b200.compile_cache import _feed_value
+    import hashlib
+
+    def dig(v):
+        h = hashlib.blake2b(digest_size=20)
+        _feed_value(h, v)
+        return h.hexdigest()
+    assert dig(np.zeros((0, 3))) != dig(np.zeros((3, 0)))
+    r, c, v = np.array([0, 1, 1]), np.array([1, 0, 2]), np.array([1.0, 2.0, 3.0])
+    a = sp.coo_array((v, (r, c)), shape=(2, 3))
+    b = sp.coo_array((v[::-1], (r[::-1], c[::-1])), shape=(2, 3))
+    assert dig(a) != dig(b)
+    assert dig(a) == dig(sp.coo_array((v.copy(), (r.copy(), c.copy())), shape=(2, 3)))
+    assert dig(a.tocsr()) != dig(a.tocsc())

@@ -190,6 +190,10 @@ def test_gpu_knitro_style_calls(gpu_mod):
         x, lam = list(p["x"]), list(p["lam"])
         assert_close(o.objective(x), ref.objective(np.array(x)), "f")
         assert_close(o.hessian(x, lam, 0.0), ref.hessian(np.array(x), np.array(lam), 0.0), "hess sigma=0")
+        # Knitro's lambda_ carries constraint AND variable-bound multipliers (length m + n); the reference
+        # only slices the first m (nlp_solver.py:405-411)
+        long_lam = lam + [9.0] * len(x)
+        assert_close(o.hessian(x, long_lam, 1.0), ref.hessian(np.array(x), np.array(long_lam), 1.0), "hess m+n duals")
         assert o.gradient(x) is o.gradient(x)        # same buffer object every call (nlp_solver.py:184,235)
         o.intermediate(0, 7, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0)
         assert o.iterations == 7
@@ -197,6 +201,11 @@ def test_gpu_knitro_style_calls(gpu_mod):
             o.objective(np.zeros(3))
     finally:
         o.close()
+    # a closed oracle raises instead of crashing the process (compile-cache eviction, uninstall())
+    with pytest.raises(RuntimeError, match="closed"):
+        o.objective(p["x"])
+    with pytest.raises(RuntimeError, match="closed"):
+        o.hessian(p["x"], p["lam"], 1.0)
 
 
 @pytest.mark.parametrize("name,B", [("c4_qcqp_small", 37), ("c2_eigen_qcqp_small", 64), ("c5_microbench_small", 5),

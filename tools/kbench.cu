@@ -120,8 +120,8 @@ int main(int argc, char **argv) {
     double *Q, *V, *y; CHECK(cudaMalloc(&Q, n * n * 8)); CHECK(cudaMalloc(&V, n * 8)); CHECK(cudaMalloc(&y, n * 8));
     fill_rand<<<SM * 8, 256>>>(Q, n * n, 4); fill_rand<<<SM, 256>>>(V, n, 5);
     double bytes = 8.0 * n * n + 16.0 * n;
-    CHECK(cudaFuncSetAttribute(gemv_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    float ms = time_it([&] { gemv_kernel<8><<<SM * 2, 256, n * 8>>>(Q, V, 0, y, n, n, 1.0, 1); });
+    CHECK(cudaFuncSetAttribute(dnlp_gemv_rows_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    float ms = time_it([&] { dnlp_gemv_rows_kernel<8><<<SM * 2, 256, n * 8>>>(Q, V, 0, y, n, n, 1.0, 1); });
     printf("gemv   v0 warp/row grid=SMx2     %8.3f ms  %7.1f GB/s\n", ms, bytes / ms / 1e6);
 #define GV(U, NW, G) { CHECK(cudaFuncSetAttribute(gemv_cta_kernel<U, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); \
     ms = time_it([&] { gemv_cta_kernel<U, NW><<<SM * G, NW * 32, n * 8>>>(Q, V, 0, y, n, n, 1.0); }); \
