@@ -53,6 +53,10 @@ EXPORTS = [
     "dnlp_read_output", "dnlp_kernel_launches", "dnlp_set_cache", "dnlp_set_graphs", "dnlp_set_parallel", "dnlp_set_windows", "dnlp_set_dynamic", "dnlp_eval_dyn", "dnlp_instr_kernel", "dnlp_run", "dnlp_output_ptr",
     "dnlp_batch_create", "dnlp_batch_destroy", "dnlp_batch_last_error", "dnlp_batch_eval", "dnlp_batch_upload",
     "dnlp_batch_run_device", "dnlp_batch_profile_instrs", "dnlp_batch_kernel_launches",
+    "dnlp_comm_unique_id", "dnlp_comm_create", "dnlp_comm_destroy", "dnlp_comm_last_error", "dnlp_comm_has_nccl",
+    "dnlp_comm_ipc_handle", "dnlp_comm_open_peers", "dnlp_comm_allreduce_host",
+    "dnlp_shard_create", "dnlp_shard_destroy", "dnlp_shard_last_error", "dnlp_shard_set_output",
+    "dnlp_shard_root_handles", "dnlp_shard_open_root", "dnlp_shard_eval", "dnlp_shard_run_device",
 ]
 
 _lib = None
@@ -114,6 +118,28 @@ def lib():
     L.dnlp_batch_profile_instrs.argtypes = [vp, C.c_int32, C.c_int32, c_f32p]
     L.dnlp_batch_kernel_launches.argtypes = [vp]
     L.dnlp_batch_kernel_launches.restype = C.c_int64
+    cp = C.c_char_p
+    L.dnlp_comm_unique_id.argtypes = [cp]
+    L.dnlp_comm_create.argtypes = [cp, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    L.dnlp_comm_destroy.argtypes = [vp]
+    L.dnlp_comm_destroy.restype = None
+    L.dnlp_comm_last_error.argtypes = [vp]
+    L.dnlp_comm_last_error.restype = C.c_char_p
+    L.dnlp_comm_has_nccl.argtypes = [vp]
+    L.dnlp_comm_ipc_handle.argtypes = [vp, cp]
+    L.dnlp_comm_open_peers.argtypes = [vp, cp]
+    L.dnlp_comm_allreduce_host.argtypes = [vp, c_f64p, C.c_int64]
+    L.dnlp_shard_create.argtypes = [vp, vp, C.c_int, C.POINTER(vp)]
+    L.dnlp_shard_destroy.argtypes = [vp]
+    L.dnlp_shard_destroy.restype = None
+    L.dnlp_shard_last_error.argtypes = [vp]
+    L.dnlp_shard_last_error.restype = C.c_char_p
+    L.dnlp_shard_set_output.argtypes = [vp, C.c_int32, C.c_int64, c_i32p, c_i32p, C.c_int64, c_i32p, c_i32p,
+                                        C.c_int64, c_f64p, C.c_int64, c_i32p]
+    L.dnlp_shard_root_handles.argtypes = [vp, cp]
+    L.dnlp_shard_open_root.argtypes = [vp, cp]
+    L.dnlp_shard_eval.argtypes = [vp, C.c_int32, c_f64p, c_f64p, C.c_double, c_f64p]
+    L.dnlp_shard_run_device.argtypes = [vp, C.c_int32, C.c_int32, c_f32p]
     _lib = L
     return L
 

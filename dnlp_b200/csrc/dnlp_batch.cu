@@ -4,6 +4,7 @@
 #include "dnlp_batch_kernels.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -66,9 +67,15 @@ struct dnlp_batch {
     int64_t need = (items + 255) / 256, cap = (int64_t)sm_count * 8;
     return (int)(need < 1 ? 1 : (need > cap ? cap : need));
   }
+  // the launch sequence of every program mask, captured once and replayed as one CUDA graph: a slice of
+  // 512 starts per GPU spends as long launching its ~25 short kernels as running them otherwise
+  struct MaskGraph { cudaGraphExec_t exec = nullptr; int64_t nlaunch = 0; };
+  MaskGraph graphs[64];
+  bool graphs_enabled = true;
   int launch(const BInstr &I);
   int run_program(int p);
   int run_union(int32_t prog_mask);
+  int issue_union(int32_t prog_mask);
   int reset_outputs();
   int put(const double *host, double *dev_batch_major, int64_t len);
   int get(int space, double *host);
@@ -111,28 +118,42 @@ int dnlp_batch::launch(const BInstr &I) {
     case DNLP_POLY: {
       if (I.smallk_slots) {
         const int threads = B >= 256 ? 256 : ((B + 31) / 32) * 32;
-        const int bchunks = (B + threads * 4 - 1) / (threads * 4);
+        // starts per thread: every register slot must carry a real start (a slice of 512 starts per GPU
+        // ran the 4-slot build half empty: 0.170 ms instead of the 0.09 ms its 0.54 GB of output needs)
+        const int nb = B > 2 * threads ? 4 : (B > threads ? 2 : 1);
+        const int bchunks = (B + threads * nb - 1) / (threads * nb);
         int64_t want_blocks = (int64_t)sm_count * 8;
         int64_t rblocks = want_blocks / bchunks > 0 ? want_blocks / bchunks : 1;
         int rows_per_block = (int)((d.count + rblocks - 1) / rblocks);
         if (rows_per_block < 1) rows_per_block = 1;
         const int64_t blocks = ((d.count + rows_per_block - 1) / rows_per_block) * bchunks;
-#define SK(Lc) case Lc: bsmallk_kernel<Lc, 4><<<(int)blocks, threads, 0, stream>>>(                    \
-            V, dst, d.coef, I.smallk_slots, d.pos, d.count, d.accumulate, B, rows_per_block); break;
+#define SKN(Lc, Nb) bsmallk_kernel<Lc, Nb><<<(int)blocks, threads, 0, stream>>>(                      \
+            V, dst, d.coef, I.smallk_slots, d.pos, d.count, d.accumulate, B, rows_per_block)
+#define SK(Lc) case Lc: if (nb == 4) SKN(Lc, 4); else if (nb == 2) SKN(Lc, 2); else SKN(Lc, 1); break;
         switch (d.row_len) {
           SK(2) SK(3) SK(4) SK(5) SK(6) SK(7) SK(8) SK(9) SK(10) SK(11) SK(12) SK(13) SK(14) SK(15) SK(16)
           default: err = "small-K kernel: unsupported row length"; return 1;
         }
 #undef SK
+#undef SKN
         break;
       }
       if (d.count > 0 && d.nterms / d.count >= 128) {
-        int64_t blocks = d.count * ((B + 31) / 32), cap = (int64_t)sm_count * 8;
-        int grid = (int)(blocks < cap ? blocks : cap);
-        if (I.has_f2)
-          bpoly_long_kernel<true><<<grid, 256, 0, stream>>>(V, dst, d.ptr, d.row_len, d.coef, d.f1, d.f2, d.pos, d.count, d.accumulate, B);
-        else
-          bpoly_long_kernel<false><<<grid, 256, 0, stream>>>(V, dst, d.ptr, d.row_len, d.coef, d.f1, d.f2, d.pos, d.count, d.accumulate, B);
+        const int64_t blocks = d.count * ((B + 31) / 32);
+        // few (row, start-chunk) pairs: 16 warps split the terms; enough of them to fill the machine: 8
+        if (blocks <= (int64_t)sm_count * 2) {
+          if (I.has_f2)
+            bpoly_long_kernel<true, 16><<<(int)blocks, 512, 0, stream>>>(V, dst, d.ptr, d.row_len, d.coef, d.f1, d.f2, d.pos, d.count, d.accumulate, B);
+          else
+            bpoly_long_kernel<false, 16><<<(int)blocks, 512, 0, stream>>>(V, dst, d.ptr, d.row_len, d.coef, d.f1, d.f2, d.pos, d.count, d.accumulate, B);
+        } else {
+          const int64_t cap = (int64_t)sm_count * 8;
+          const int grid = (int)(blocks < cap ? blocks : cap);
+          if (I.has_f2)
+            bpoly_long_kernel<true, 8><<<grid, 256, 0, stream>>>(V, dst, d.ptr, d.row_len, d.coef, d.f1, d.f2, d.pos, d.count, d.accumulate, B);
+          else
+            bpoly_long_kernel<false, 8><<<grid, 256, 0, stream>>>(V, dst, d.ptr, d.row_len, d.coef, d.f1, d.f2, d.pos, d.count, d.accumulate, B);
+        }
         break;
       }
       const int threads = B >= 256 ? 256 : ((B + 31) / 32) * 32;
@@ -171,6 +192,28 @@ int dnlp_batch::run_program(int p) {
 }
 
 int dnlp_batch::run_union(int32_t prog_mask) {
+  prog_mask &= 63;
+  if (!graphs_enabled) return issue_union(prog_mask);
+  MaskGraph &G = graphs[prog_mask];
+  if (!G.exec) {
+    const int64_t before = launches;
+    CKB(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = issue_union(prog_mask);
+    cudaGraph_t g = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(stream, &g);
+    if (rc) { if (g) cudaGraphDestroy(g); cudaGetLastError(); return 1; }
+    if (ce != cudaSuccess) { err = std::string("graph capture failed: ") + cudaGetErrorString(ce); return 1; }
+    G.nlaunch = launches - before;
+    launches = before;
+    CKB(cudaGraphInstantiate(&G.exec, g, 0));
+    cudaGraphDestroy(g);
+  }
+  CKB(cudaGraphLaunch(G.exec, stream));
+  launches += G.nlaunch;
+  return 0;
+}
+
+int dnlp_batch::issue_union(int32_t prog_mask) {
   // there is no per-x cache in batch mode: run every needed instruction exactly once
   std::vector<uint8_t> need(instrs.size(), 0);
   for (int p = 0; p < DNLP_NPROG; ++p)
@@ -224,6 +267,7 @@ void dnlp_batch_destroy(dnlp_batch *o) {
   if (!o) return;
   cudaSetDevice(o->device);
   if (o->stream) cudaStreamSynchronize(o->stream);
+  for (auto &g : o->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
   for (void *p : o->owned) cudaFree(p);
   if (o->ev0) cudaEventDestroy(o->ev0);
   if (o->ev1) cudaEventDestroy(o->ev1);
@@ -321,6 +365,7 @@ static int batch_create_impl(dnlp_batch *o, const dnlp_tape_desc *t) {
     }
     if (o->upload(hd.data(), (int64_t)hd.size(), &G.descs)) return 1;
   }
+  if (const char *e = getenv("DNLP_BATCH_NO_GRAPHS")) o->graphs_enabled = atoi(e) == 0;
   if (o->reset_outputs()) return 1;
   CKB(cudaFuncSetAttribute(dnlp::bgemm_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dnlp::BGEMM_SMEM));
   CKB(cudaStreamSynchronize(o->stream));

@@ -119,15 +119,18 @@ bsmallk_kernel(const double *__restrict__ V, double *__restrict__ dst, const dou
   }
 }
 
-// Rows with hundreds of terms but few (row, start) pairs (f = x'P0x + q'x of every start): the 8
+// Rows with hundreds of terms but few (row, start) pairs (f = x'P0x + q'x of every start): the NW
 // warps of a CTA split the terms of one row for 32 consecutive starts, then reduce in shared memory.
-template <bool HAS_F2>
-__global__ void __launch_bounds__(256)
+// Four terms are in flight per warp (index loads, then gathers, then the adds): a serial loop is bound
+// by two dependent memory latencies per term, which made this kernel the floor of small batches
+// (0.07 ms for 8 rows x 1025 terms at any B <= 1024 before the unrolling).
+template <bool HAS_F2, int NW>
+__global__ void __launch_bounds__(NW * 32)
 bpoly_long_kernel(const double *__restrict__ V, double *__restrict__ dst, const int64_t *__restrict__ ptr,
                   int row_len, const double *__restrict__ coef, const int32_t *__restrict__ f1,
                   const int32_t *__restrict__ f2, const int32_t *__restrict__ pos, int64_t count,
                   int accumulate, int B) {
-  __shared__ double part[8][33];
+  __shared__ double part[NW][33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int bchunks = (B + 31) / 32;
   for (int64_t blk = blockIdx.x; blk < count * bchunks; blk += gridDim.x) {
@@ -137,20 +140,34 @@ bpoly_long_kernel(const double *__restrict__ V, double *__restrict__ dst, const 
     if (ptr) { t0 = __ldg(ptr + row); t1 = __ldg(ptr + row + 1); }
     else { t0 = row * (int64_t)row_len; t1 = t0 + row_len; }
     double acc = 0.0;
-    if (b < B)
-      for (int64_t t = t0 + warp; t < t1; t += 8) {
-        const int i1 = __ldg(f1 + t);
-        double v = __ldg(coef + t);
-        if (i1 >= 0) v *= V[(int64_t)i1 * B + b];
-        if (HAS_F2) { const int i2 = __ldg(f2 + t); if (i2 >= 0) v *= V[(int64_t)i2 * B + b]; }
-        acc += v;
+    if (b < B) {
+      constexpr int U = 4;
+      for (int64_t t = t0 + warp; t < t1; t += (int64_t)U * NW) {
+        int i1[U], i2[U];
+        double c[U], v1[U], v2[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int64_t tt = t + (int64_t)u * NW;
+          const bool ok = tt < t1;
+          i1[u] = ok ? __ldg(f1 + tt) : -1;
+          i2[u] = (HAS_F2 && ok) ? __ldg(f2 + tt) : -1;
+          c[u] = ok ? __ldg(coef + tt) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          v1[u] = i1[u] >= 0 ? V[(int64_t)i1[u] * B + b] : 1.0;
+          v2[u] = (HAS_F2 && i2[u] >= 0) ? V[(int64_t)i2[u] * B + b] : 1.0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) acc += HAS_F2 ? c[u] * v1[u] * v2[u] : c[u] * v1[u];
       }
+    }
     part[warp][lane] = acc;
     __syncthreads();
     if (warp == 0 && b < B) {
       double t = 0.0;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) t += part[w][lane];
+      for (int w = 0; w < NW; ++w) t += part[w][lane];
       const int64_t d = (pos ? (int64_t)__ldg(pos + row) : row) * B + b;
       dst[d] = accumulate ? dst[d] + t : t;
     }

@@ -16,9 +16,11 @@ sum only ever adds real contributions for the replicated variables (gradient and
 that is the allreduce the north star names.  Entries that are constants of the global problem
 (affine Jacobian rows) never travel: only the x/lambda-dependent positions are reduced.
 
-The collective is one packed ``all_reduce(SUM, float64)`` per callback over
-``torch.distributed`` (NCCL between GPUs, gloo in the CPU tests) - plumbing only; every number in
-the packed buffer was produced by the CUDA tape of the local ``GpuOracles``.
+On GPUs the ranks meet in kernels (csrc/dnlp_shard.cu): a one-shot all-reduce over peer memory for the
+shared entries (ncclAllReduce for large payloads) and direct NVLink stores of owned entries into the
+root's global array; the host-side rendezvous (``dnlp_b200.comm``) only carries setup data.  With a
+host evaluator (CPU tests) the same assembly runs on the host through the store.  No third-party
+communication package is imported here.
 """
 import numpy as np
 
@@ -63,22 +65,12 @@ def _lookup(keys_global, keys_local, what):
     return order[pos]
 
 
-class _TorchComm:
-    """all_reduce(SUM) of a float64 NumPy vector through torch.distributed."""
+class _SoloStore:
+    """World of one (no communication)."""
+    rank, world = 0, 1
 
-    def __init__(self, group=None):
-        import torch
-        import torch.distributed as dist
-        self.torch, self.dist, self.group = torch, dist, group
-        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
-        self.cuda = dist.get_backend(group) == "nccl"
-
-    def allreduce(self, vec):
-        t = self.torch.from_numpy(vec)
-        if self.cuda:
-            t = t.cuda()
-        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
-        return t.cpu().numpy() if self.cuda else vec
+    def allgather(self, payload):
+        return [bytes(payload)]
 
 
 def _runs(idx):
@@ -101,106 +93,136 @@ def _take(src, runs, out):
     return out
 
 
-class _DeviceAssembler:
-    """NCCL path of ``RowShardedOracles``: local outputs stay in HBM, entries that several ranks
-    contribute to are all-reduced, entries owned by one rank are all-gathered, and the global
-    output is assembled on the device, so one contiguous D2H per callback reaches the host."""
+_SPACE = {"f": 1, "grad": 2, "g": 3, "jac": 4, "hess": 5}
+_PROG = {"f": 0, "grad": 1, "g": 2, "jac": 3, "hess": 4}
 
-    def __init__(self, owner, device):
-        import torch
-        import torch.distributed as dist
-        self.torch, self.dist, self.o = torch, dist, owner
-        self.dev = torch.device("cuda", device)
-        self.world = dist.get_world_size()
-        self.plan = {}
-        for name in ("grad", "g", "jac", "hess"):
-            self.plan[name] = self._plan(name)
-        self._f = torch.zeros(1, dtype=torch.float64, device=self.dev)
 
-    def _plan(self, name):
-        torch, dist, o = self.torch, self.dist, self.o
-        dyn = o.gs.dynamic[name].astype(np.int64)
-        nd = dyn.size
-        sel, cidx = o._sel[name], o._cidx[name]
-        cnt = torch.from_numpy(np.bincount(cidx, minlength=max(nd, 1)).astype(np.int64)).to(self.dev)
-        dist.all_reduce(cnt)
-        cnt = cnt.cpu().numpy()[:nd] if nd else np.zeros(0, np.int64)
-        shared_slots = np.where(cnt > 1)[0]
-        mine_shared = cnt[cidx] > 1 if nd else np.zeros(0, bool)
-        sel_sh, tgt_sh = sel[mine_shared], np.searchsorted(shared_slots, cidx[mine_shared])
-        sel_ow, slot_ow = sel[~mine_shared], cidx[~mine_shared]
-        n_ow = torch.tensor([sel_ow.size], dtype=torch.int64, device=self.dev)
-        sizes = [torch.zeros(1, dtype=torch.int64, device=self.dev) for _ in range(self.world)]
-        dist.all_gather(sizes, n_ow)
-        maxown = max(1, max(int(t.item()) for t in sizes))
-        pad = np.full(maxown, -1, dtype=np.int64)
-        pad[:slot_ow.size] = slot_ow
-        all_slots = torch.empty(self.world * maxown, dtype=torch.int64, device=self.dev)
-        dist.all_gather_into_tensor(all_slots, torch.from_numpy(pad).to(self.dev))
-        valid = torch.nonzero(all_slots >= 0).reshape(-1)
-        t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int64)).to(self.dev)  # noqa: E731
-        dense = nd > 0.5 * o._out[name].size
-        p = {"nd": nd, "maxown": maxown, "sel_ow": t(sel_ow), "n_ow": int(sel_ow.size),
-             "sel_sh": t(sel_sh), "tgt_sh": t(tgt_sh), "shared_slots": t(shared_slots), "n_sh": int(shared_slots.size),
-             "valid": valid, "valid_slots": all_slots[valid], "dense": dense,
-             "ow_buf": torch.zeros(maxown, dtype=torch.float64, device=self.dev),
-             "gbuf": torch.empty(self.world * maxown, dtype=torch.float64, device=self.dev),
-             "full": torch.zeros(max(nd, 1), dtype=torch.float64, device=self.dev)}
-        if dense:
-            p["out_dev"] = torch.from_numpy(np.ascontiguousarray(o.gs.const[name], dtype=np.float64)).to(self.dev)
-            p["dyn_pos"] = t(dyn)
-            p["host"] = torch.empty(o._out[name].size, dtype=torch.float64, pin_memory=True)   # pinned: D2H at PCIe rate
-            p["host"].copy_(torch.from_numpy(o._out[name]))
-            o._out[name] = p["host"].numpy()
-            if name == "grad":
-                o.grad_obj = o._out[name]
-        return p
+class _DeviceShard:
+    """GPU path of ``RowShardedOracles``: the ``dnlp_shard`` object of include/dnlp_b200.h.  Local outputs
+    stay in HBM; shared entries are summed by the one-shot peer-memory all-reduce (ncclAllReduce above
+    16384 doubles), owned entries are stored by their owner into the root's global array over NVLink,
+    and one D2H per callback leaves the root (csrc/dnlp_shard.cu)."""
 
-    def objective(self, f_loc):
-        self._f[0] = f_loc
-        self.dist.all_reduce(self._f)
-        return float(self._f.item())
+    DENSE_FRACTION = 0.5
 
-    def assemble(self, name):
-        """Local result of program ``name`` is in HBM; returns the assembled global host array."""
-        torch, dist, o, p = self.torch, self.dist, self.o, self.plan[name]
-        t = torch.as_tensor(o.local.output_device_array(name), device=self.dev)
-        full = p["full"]
-        full.zero_()
-        if p["n_ow"]:
-            p["ow_buf"][:p["n_ow"]] = t.index_select(0, p["sel_ow"])
-        dist.all_gather_into_tensor(p["gbuf"], p["ow_buf"])
-        full[p["valid_slots"]] = p["gbuf"][p["valid"]]
-        if p["n_sh"]:
-            sh = torch.zeros(p["n_sh"], dtype=torch.float64, device=self.dev)
-            if p["sel_sh"].numel():
-                sh.index_add_(0, p["tgt_sh"], t.index_select(0, p["sel_sh"]))
-            dist.all_reduce(sh)
-            full[p["shared_slots"]] = sh
-        out = o._out[name]
-        if o.root_only and dist.get_rank() != 0:
-            torch.cuda.current_stream().synchronize()
-            return out
-        if p["dense"]:
-            p["out_dev"][p["dyn_pos"]] = full[:p["nd"]]
-            p["host"].copy_(p["out_dev"])
-        elif p["nd"]:
-            out[o.gs.dynamic[name]] = full[:p["nd"]].cpu().numpy()
-        return out
+    def __init__(self, owner, store, device, root, nccl):
+        import ctypes as C
+
+        from . import _cabi
+        from .comm import Comm, allgather_array, barrier, bcast
+        self.C, self.o, self.store, self.root = C, owner, store, int(root)
+        self._L = L = _cabi.lib()
+        self.comm = Comm(store, device, nccl=nccl)
+        h = C.c_void_p()
+        if L.dnlp_shard_create(owner.local.dev.h, self.comm.h, self.root, C.byref(h)) != 0:
+            raise RuntimeError("dnlp_shard_create: %s" % L.dnlp_shard_last_error(None).decode())
+        self.h = h
+        self.is_root = store.rank == self.root
+        i32p = C.POINTER(C.c_int32)
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)          # noqa: E731
+        ptr = lambda a: a.ctypes.data_as(i32p) if a.size else None       # noqa: E731
+        self.compact, self.dense = {}, {}
+        gs = owner.gs
+        for name in ("f", "grad", "g", "jac", "hess"):
+            if name == "f":
+                glen, gconst, dyn = 1, np.zeros(1), np.zeros(1, np.int64)
+                sel, cidx = np.zeros(1, np.int64), np.zeros(1, np.int64)
+            else:
+                glen, gconst = owner._out[name].size, np.ascontiguousarray(gs.const[name], dtype=np.float64)
+                dyn = gs.dynamic[name].astype(np.int64)
+                sel, cidx = owner._sel[name], owner._cidx[name]
+            nd = dyn.size
+            allc = allgather_array(store, i32(cidx))
+            cnt = np.bincount(np.concatenate(allc), minlength=max(nd, 1))[:max(nd, 1)]
+            shared_slots = np.where(cnt > 1)[0] if store.world > 1 else np.zeros(0, np.int64)
+            if name == "f":
+                shared_slots = np.zeros(1, np.int64)                       # always summed (one double)
+            mine_shared = np.isin(cidx, shared_slots) if cidx.size else np.zeros(0, bool)
+            sh_src = np.full(shared_slots.size, -1, dtype=np.int64)
+            sh_src[np.searchsorted(shared_slots, cidx[mine_shared])] = sel[mine_shared]
+            sh_gpos = dyn[shared_slots] if nd else np.zeros(0, np.int64)
+            ow_pos, ow_gpos = sel[~mine_shared], (dyn[cidx[~mine_shared]] if nd else np.zeros(0, np.int64))
+            dense = name == "f" or nd > self.DENSE_FRACTION * glen
+            self.dense[name] = dense
+            a = [i32(sh_src), i32(sh_gpos), i32(ow_pos), i32(ow_gpos), i32(dyn)]
+            self.check(L.dnlp_shard_set_output(
+                self.h, _SPACE[name], int(shared_slots.size), ptr(a[0]), ptr(a[1]), int(ow_pos.size), ptr(a[2]), ptr(a[3]),
+                int(glen), gconst.ctypes.data_as(_cabi.c_f64p) if self.is_root and glen else None,
+                -1 if dense else int(nd), None if dense else ptr(a[4])))
+            if self.is_root:
+                if dense and name != "f":
+                    buf, hd = _cabi.pinned_empty(glen)               # the solver-facing array itself is pinned
+                    buf[:] = owner._out[name]
+                    owner._out[name], owner._keep = buf, getattr(owner, "_keep", []) + [hd]
+                    if name == "grad":
+                        owner.grad_obj = buf
+                elif not dense:
+                    self.compact[name] = _cabi.pinned_empty(max(nd, 1))
+        self._f, self._fh = _cabi.pinned_empty(1)
+        hb = C.create_string_buffer(384)
+        if self.is_root:
+            self.check(L.dnlp_shard_root_handles(self.h, hb))
+        table = bcast(store, hb.raw, self.root)
+        self.check(L.dnlp_shard_open_root(self.h, table))
+        barrier(store)
+
+    def check(self, rc):
+        if rc != 0:
+            raise RuntimeError("dnlp_b200 shard: %s" % self._L.dnlp_shard_last_error(self.h).decode())
+
+    def eval(self, name, xl, lam=None, sigma=1.0):
+        from . import _cabi
+        o = self.o
+        f64p = _cabi.c_f64p
+        out = None
+        if name == "f":
+            out = self._f
+        elif self.is_root:
+            out = o._out[name] if self.dense[name] else self.compact[name][0]
+        self.check(self._L.dnlp_shard_eval(
+            self.h, _PROG[name], xl.ctypes.data_as(f64p), None if lam is None else lam.ctypes.data_as(f64p),
+            float(sigma), None if out is None else out.ctypes.data_as(f64p)))
+        if name == "f":
+            return np.float64(self._f[0])
+        if self.is_root and not self.dense[name]:
+            dyn = o.gs.dynamic[name]
+            o._out[name][dyn] = self.compact[name][0][:dyn.size]
+        return o._out[name]
+
+    def run_device(self, programs, iters):
+        from . import _cabi
+        mask = 0
+        for p in programs:
+            mask |= 1 << _cabi.PROG_IDS[p]
+        ms = self.C.c_float(0)
+        self.check(self._L.dnlp_shard_run_device(self.h, mask, int(iters), self.C.byref(ms)))
+        return float(ms.value)
+
+    def close(self):
+        if getattr(self, "h", None):
+            from .comm import barrier
+            barrier(self.store)
+            self._L.dnlp_shard_destroy(self.h)
+            self.h = None
+            self.comm.close()
 
 
 class RowShardedOracles:
-    """Same seven callbacks as ``GpuOracles``; every call is collective over the group."""
+    """Same seven callbacks as ``GpuOracles``; every call is collective over the ranks of ``store``.
 
-    def __init__(self, local_problem, layout, global_structure, comm=None, oracle_factory=None, device=0,
-                 root_only=False):
-        """``root_only``: only rank 0 (where the solver runs) copies assembled outputs to the host;
-        the other ranks still take part in every collective but return their arrays un-refreshed."""
-        self.root_only = root_only
-        if oracle_factory is None:
+    ``store``: rendezvous object (``dnlp_b200.comm.SocketStore`` or anything with ``rank``, ``world``
+    and ``allgather(bytes)``).  ``oracle_factory``: evaluator of the LOCAL problem; the default is
+    ``GpuOracles`` with the device-side exchange of ``dnlp_shard``; a host evaluator (the CPU tests
+    pass the CPU oracle) makes the assembly run on the host through the store."""
+
+    def __init__(self, local_problem, layout, global_structure, store=None, oracle_factory=None, device=0,
+                 root=0, nccl=True):
+        self.store = store if store is not None else _SoloStore()
+        self.root = int(root)
+        gpu = oracle_factory is None
+        if gpu:
             from .oracles import GpuOracles
             oracle_factory = lambda p: GpuOracles(p, device=device)  # noqa: E731
-        self.comm = comm if comm is not None else _TorchComm()
         self.layout, self.gs = layout, global_structure
         self.local = oracle_factory(local_problem)
         self.n, self.m = global_structure.n, global_structure.m
@@ -227,21 +249,14 @@ class RowShardedOracles:
             c = slot[self._gpos[name]]
             sel = np.where(c >= 0)[0]
             self._sel[name], self._cidx[name] = sel, c[sel]
-            out = np.array(gs.const[name], dtype=np.float64, copy=True)
-            self._out[name] = out
+            self._out[name] = np.array(gs.const[name], dtype=np.float64, copy=True)
         self.grad_obj = self._out["grad"]
         self._var_runs, self._con_runs = None, None
-        try:
-            vr, cr = _runs(lay.var_map), _runs(lay.con_map)
-            if len(vr) <= 64 and len(cr) <= 64:
-                self._var_runs, self._con_runs = vr, cr
-                self._xl, self._ll = np.empty(lay.var_map.size), np.empty(max(lay.con_map.size, 1))
-        except Exception:
-            pass
-        # device-side assembly over NCCL when the local evaluator keeps its outputs in HBM
-        self._devasm = None
-        if getattr(self.comm, "cuda", False) and hasattr(self.local, "output_device_array"):
-            self._devasm = _DeviceAssembler(self, device)
+        vr, cr = _runs(lay.var_map), _runs(lay.con_map)
+        if len(vr) <= 64 and len(cr) <= 64:
+            self._var_runs, self._con_runs = vr, cr
+            self._xl, self._ll = np.empty(lay.var_map.size), np.empty(max(lay.con_map.size, 1))
+        self._dev = _DeviceShard(self, self.store, device, self.root, nccl) if gpu else None
 
     @staticmethod
     def _hess_lookup(gs, lay, lhr, lhc):
@@ -251,53 +266,58 @@ class RowShardedOracles:
         return _lookup(gs.hess_rows.astype(np.int64) * nG + gs.hess_cols, hi * nG + lo, "hessian")
 
     def close(self):
+        if self._dev is not None:
+            self._dev.close()
+            self._dev = None
         if hasattr(self.local, "close"):
             self.local.close()
 
     # ------------------------------------------------------------------------------------------
     def _local_x(self, x):
         x = np.asarray(x, dtype=np.float64).reshape(-1)
+        if x.size != self.n:
+            raise ValueError("x has %d entries, expected %d" % (x.size, self.n))
         if self._var_runs is not None:
             return _take(x, self._var_runs, self._xl)
         return np.ascontiguousarray(x[self.layout.var_map])
 
     def _local_lam(self, lam):
         lam = np.asarray(lam, dtype=np.float64).reshape(-1)
+        if lam.size < self.m:
+            raise ValueError("duals has %d entries, expected at least %d" % (lam.size, self.m))
         if self._con_runs is not None:
             return _take(lam, self._con_runs, self._ll)[:self.layout.con_map.size]
         return np.ascontiguousarray(lam[self.layout.con_map])
 
-    def _reduce_into(self, name, local_vals, extra=None):
-        """Scatter-add the local dynamic entries into the compact global vector, all-reduce it
-        (optionally with ``extra`` scalars appended), write the result into the global output."""
+    def _reduce_into(self, name, local_vals):
+        """Host path: scatter-add the local dynamic entries into the compact global vector, sum it over
+        the ranks, write the result into the global output."""
+        from .comm import allreduce_sum
         dyn = self.gs.dynamic[name]
-        n_extra = 0 if extra is None else len(extra)
-        buf = np.zeros(dyn.size + n_extra)
+        buf = np.zeros(dyn.size)
         vals = np.asarray(local_vals, dtype=np.float64).reshape(-1)[self._sel[name]]
         if dyn.size:
             buf[:dyn.size] = np.bincount(self._cidx[name], weights=vals, minlength=dyn.size)
-        if n_extra:
-            buf[dyn.size:] = extra
-        buf = self.comm.allreduce(buf)
+        buf = allreduce_sum(self.store, buf)
         out = self._out[name]
         out[dyn] = buf[:dyn.size]
-        return out, buf[dyn.size:]
+        return out
 
     def objective(self, x):
         # constants of the objective live in rank 0's local problem (it carries every non-row term)
-        f_loc = float(self.local.objective(self._local_x(x)))
-        if self._devasm is not None:
-            return np.float64(self._devasm.objective(f_loc))
-        return np.float64(self.comm.allreduce(np.array([f_loc]))[0])
+        xl = self._local_x(x)
+        if self._dev is not None:
+            return self._dev.eval("f", xl)
+        from .comm import allreduce_sum
+        return np.float64(allreduce_sum(self.store, np.array([float(self.local.objective(xl))]))[0])
 
     def _callback(self, name, x, lam=None, sigma=1.0):
         xl = self._local_x(x)
-        if self._devasm is not None:
-            self.local.run(name, xl, lam, sigma)
-            return self._devasm.assemble(name)
+        if self._dev is not None:
+            return self._dev.eval(name, xl, lam, sigma)
         fn = {"grad": self.local.gradient, "g": self.local.constraints, "jac": self.local.jacobian}
         vals = self.local.hessian(xl, lam, sigma) if name == "hess" else fn[name](xl)
-        return self._reduce_into(name, vals)[0]
+        return self._reduce_into(name, vals)
 
     def gradient(self, x):
         return self._callback("grad", x)
@@ -320,6 +340,11 @@ class RowShardedOracles:
     def intermediate(self, alg_mod, iter_count, obj_value, inf_pr, inf_du, mu,
                      d_norm, regularization_size, alpha_du, alpha_pr, ls_trials):
         self.iterations = iter_count
+
+    def run_device(self, programs=("f", "grad", "g", "jac", "hess"), iters=1):
+        """Device-resident sharded evaluation: local programs + the exchange of shared entries,
+        CUDA-event time of this rank in ms (take the max over ranks)."""
+        return self._dev.run_device(programs, iters)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -171,6 +171,38 @@ int dnlp_batch_run_device(dnlp_batch *b, int32_t prog_mask, int32_t iters, float
 int dnlp_batch_profile_instrs(dnlp_batch *b, int32_t prog, int32_t iters, float *ms_per_instr);
 int64_t dnlp_batch_kernel_launches(dnlp_batch *b);
 
+/* ---- row-sharded evaluation across the GPUs of one node (BASELINE config 3) ----
+ * One process per GPU.  The reference has no counterpart (it is single-process NumPy); the surface
+ * mirrors the callbacks above, evaluated collectively: every rank runs the local tape of its rows,
+ * entries several ranks contribute to are summed by a one-shot all-reduce over peer memory (NVLink
+ * P2P stores + flags; ncclAllReduce for payloads above 16384 doubles), entries owned by one rank are
+ * stored by their owner straight into the root's copy of the global output array.
+ * The caller brings its own rendezvous (any way to all-gather a few hundred bytes between the ranks). */
+typedef struct dnlp_comm dnlp_comm;
+typedef struct dnlp_shard dnlp_shard;
+int dnlp_comm_unique_id(char *out128);                    /* rank 0: ncclGetUniqueId (libnccl is dlopen'ed) */
+int dnlp_comm_create(const char *nccl_id /* 128 bytes or NULL: no NCCL */, int rank, int world, int device,
+                     dnlp_comm **out);
+void dnlp_comm_destroy(dnlp_comm *c);
+const char *dnlp_comm_last_error(dnlp_comm *c);
+int dnlp_comm_has_nccl(dnlp_comm *c);
+int dnlp_comm_ipc_handle(dnlp_comm *c, char *out64);      /* cudaIpcMemHandle_t of this rank's exchange area */
+int dnlp_comm_open_peers(dnlp_comm *c, const char *handles /* world x 64 bytes, rank order */);
+int dnlp_comm_allreduce_host(dnlp_comm *c, double *vec, int64_t count);   /* sum over ranks, in place */
+
+int dnlp_shard_create(dnlp_oracle *local, dnlp_comm *comm, int root, dnlp_shard **out);
+void dnlp_shard_destroy(dnlp_shard *s);
+const char *dnlp_shard_last_error(dnlp_shard *s);
+int dnlp_shard_set_output(dnlp_shard *s, int32_t dst_space, int64_t n_shared_total, const int32_t *shared_src,
+                          const int32_t *shared_global_pos, int64_t n_owned, const int32_t *owned_pos,
+                          const int32_t *owned_global_pos, int64_t global_len, const double *global_const,
+                          int64_t n_dyn, const int32_t *dyn_global_pos);
+int dnlp_shard_root_handles(dnlp_shard *s, char *out384);           /* root: IPC handles of its global arrays */
+int dnlp_shard_open_root(dnlp_shard *s, const char *handles384);    /* every rank: map them */
+int dnlp_shard_eval(dnlp_shard *s, int32_t prog, const double *x_local, const double *lam_local, double sigma,
+                    double *host_out /* root only */);
+int dnlp_shard_run_device(dnlp_shard *s, int32_t prog_mask, int32_t iters, float *elapsed_ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,5 +1,12 @@
-"""Row-sharded oracle over NCCL with device-side assembly (needs >= 2 GPUs; skipped otherwise).
-Every rank's assembled global outputs must equal the single-GPU oracle of the global problem."""
+"""Row-sharded oracle with the device-side exchange of csrc/dnlp_shard.cu (one process per rank).
+
+* 2 and 3 ranks SHARING one GPU: the peer-memory path alone (CUDA IPC exchange areas, one-shot
+  all-reduce kernels, direct stores into the root's global array) - runs on the 1-GPU test box;
+* 2 ranks on 2 GPUs with NCCL as well (the ncclAllReduce route forced for the shared entries) -
+  skipped when the box has one GPU.
+
+Every callback of the root must equal the single-GPU oracle of the GLOBAL problem (structures bit for
+bit, values rel 1e-10); the objective must be known on every rank."""
 import os
 import socket
 import sys
@@ -11,60 +18,77 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, q):
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q, same_gpu, kind, allreduce):
     try:
         sys.path.insert(0, ROOT)
         sys.path.insert(0, os.path.join(ROOT, "tests"))
-        import torch
-        import torch.distributed as dist
-        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
-        torch.cuda.set_device(rank)
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+        os.environ["DNLP_SHARD_ALLREDUCE"] = allreduce
         from dnlp_b200 import workloads as W
+        from dnlp_b200.comm import SocketStore, barrier
         from dnlp_b200.oracles import GpuOracles
-        from dnlp_b200.sharded import GlobalStructure, RowShardedOracles, shard_logistic_regression
+        from dnlp_b200.sharded import (GlobalStructure, RowShardedOracles, shard_logistic_regression,
+                                       shard_microbench)
         from golden_util import assert_close
-
-        At, x_init = W.logistic_data(20011, 48, 8, seed=5)
-        glob = W.logistic_regression(At, x_init)
-        ref = GpuOracles(glob, device=rank)
-        local, layout = shard_logistic_regression(At, x_init, rank, world)
-        o = RowShardedOracles(local, layout, GlobalStructure.from_problem(glob), device=rank)
-        assert o._devasm is not None, "device-side assembly not active"
+        dev = 0 if same_gpu else rank
+        store = SocketStore(rank, world, "127.0.0.1", port)
+        if kind == "c3":
+            At, x_init = W.logistic_data(20011, 48, 8, seed=5)
+            glob = W.logistic_regression(At, x_init)
+            local, layout = shard_logistic_regression(At, x_init, rank, world)
+        else:                       # C5-type: every variable replicated, Hessian contributions summed
+            A, x0 = W.microbench_data(4000, 1531, 6, seed=3)
+            glob = W.microbench(A, x0)
+            local, layout = shard_microbench(A, x0, rank, world)
+        ref = GpuOracles(glob, device=dev)
+        o = RowShardedOracles(local, layout, GlobalStructure.from_problem(glob), store=store, device=dev,
+                              nccl=not same_gpu)
+        assert o._dev is not None, "device-side exchange not active"
+        if allreduce == "nccl":
+            assert o._dev.comm.has_nccl
         np.testing.assert_array_equal(o.jacobianstructure()[0], ref.jacobianstructure()[0])
+        np.testing.assert_array_equal(o.jacobianstructure()[1], ref.jacobianstructure()[1])
+        np.testing.assert_array_equal(o.hessianstructure()[0], ref.hessianstructure()[0])
         np.testing.assert_array_equal(o.hessianstructure()[1], ref.hessianstructure()[1])
-        rng = np.random.default_rng(11)
-        for _ in range(3):
+        rng = np.random.default_rng(11)           # same stream on every rank: same global point
+        for it in range(3):
             x = glob.x0 * (1 + 0.05 * rng.standard_normal(glob.n))
             lam = rng.standard_normal(glob.m)
             sigma = float(rng.uniform(0.5, 1.5))
-            assert_close(o.objective(x), ref.objective(x), "f")
-            assert_close(o.gradient(x), ref.gradient(x), "grad")
-            assert_close(o.constraints(x), ref.constraints(x), "g", atol=1e-11)
-            assert_close(o.jacobian(x), ref.jacobian(x), "jac")
-            assert_close(o.hessian(x, lam, sigma), ref.hessian(x, lam, sigma), "hess")
-        dist.barrier()
+            f = o.objective(x)
+            assert_close(f, ref.objective(x), "f")                   # every rank knows the objective
+            got = [o.gradient(x), o.constraints(x), o.jacobian(x), o.hessian(x, lam, sigma)]
+            if it == 1:                                              # the same output twice in a row (line search)
+                got[1] = o.constraints(x)
+            if rank == 0:
+                assert_close(got[0], ref.gradient(x), "grad")
+                assert_close(got[1], ref.constraints(x), "g", atol=1e-11)
+                assert_close(got[2], ref.jacobian(x), "jac")
+                assert_close(got[3], ref.hessian(x, lam, sigma), "hess")
+        ms = o.run_device(iters=3)
+        assert ms > 0
+        barrier(store)
         o.close(), ref.close()
-        dist.destroy_process_group()
+        store.close()
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         import traceback
         q.put((rank, "FAIL: %s\n%s" % (e, traceback.format_exc())))
 
 
-def test_row_sharded_nccl_device_assembly():
-    from dnlp_b200 import _cabi
-    if _cabi.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
-    import torch.multiprocessing as mp
-    s = socket.socket()
-    s.bind(("127.0.0.1", 0))
-    port = s.getsockname()[1]
-    s.close()
+def _run(world, same_gpu, kind, allreduce="auto"):
+    import multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    world = 2
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, same_gpu, kind, allreduce)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=300) for _ in procs]
@@ -72,3 +96,16 @@ def test_row_sharded_nccl_device_assembly():
         p.join(timeout=60)
     for rank, msg in results:
         assert msg == "ok", "rank %d: %s" % (rank, msg)
+
+
+@pytest.mark.parametrize("world,kind", [(2, "c3"), (3, "c3"), (2, "c5")])
+def test_row_sharded_peer_memory_exchange_on_one_gpu(world, kind):
+    _run(world, True, kind)
+
+
+@pytest.mark.parametrize("kind,allreduce", [("c3", "auto"), ("c5", "auto"), ("c5", "nccl")])
+def test_row_sharded_two_gpus(kind, allreduce):
+    from dnlp_b200 import _cabi
+    if _cabi.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    _run(2, False, kind, allreduce)
