@@ -33,6 +33,7 @@ class InstrDesc(C.Structure):
         ("Q", c_f64p), ("ncols", C.c_int64), ("x_off", C.c_int64), ("alpha", C.c_double),
         ("s_slot", C.c_int64),
         ("deps", c_i32p), ("n_deps", C.c_int64),
+        ("dst_stride", C.c_int32), ("reserved0", C.c_int32), ("post_scale", C.c_double), ("qpos", c_i32p),
     ]
 
 
@@ -47,7 +48,7 @@ class TapeDesc(C.Structure):
 
 
 EXPORTS = [
-    "dnlp_device_count", "dnlp_version", "dnlp_create", "dnlp_destroy", "dnlp_last_error",
+    "dnlp_device_count", "dnlp_version", "dnlp_device_synchronize", "dnlp_create", "dnlp_destroy", "dnlp_last_error",
     "dnlp_eval_f", "dnlp_eval_grad", "dnlp_eval_g", "dnlp_eval_jac", "dnlp_eval_hess", "dnlp_eval_all",
     "dnlp_host_alloc", "dnlp_host_free", "dnlp_upload_point", "dnlp_run_device", "dnlp_profile_instrs",
     "dnlp_read_output", "dnlp_kernel_launches", "dnlp_set_cache", "dnlp_set_graphs", "dnlp_set_parallel", "dnlp_set_windows", "dnlp_set_dynamic", "dnlp_eval_dyn", "dnlp_instr_kernel", "dnlp_run", "dnlp_output_ptr",
@@ -75,6 +76,7 @@ def lib():
     vp = C.c_void_p
     L.dnlp_device_count.restype = C.c_int
     L.dnlp_version.restype = C.c_char_p
+    L.dnlp_device_synchronize.argtypes = [C.c_int]
     L.dnlp_create.argtypes = [C.POINTER(TapeDesc), C.c_int, C.POINTER(vp)]
     L.dnlp_destroy.argtypes = [vp]
     L.dnlp_destroy.restype = None
@@ -148,6 +150,11 @@ def device_count():
     return int(lib().dnlp_device_count())
 
 
+def device_synchronize(device=0):
+    if lib().dnlp_device_synchronize(int(device)) != 0:
+        raise RuntimeError("dnlp_b200: cudaDeviceSynchronize failed on device %d" % device)
+
+
 def _p(arr, typ):
     return None if arr is None else arr.ctypes.data_as(typ)
 
@@ -212,7 +219,12 @@ def make_tape_desc(tape):
         d.level = int(ins.level)
         d.dep_mask = int(ins.dep_mask)
         d.alpha, d.ncols, d.x_off, d.s_slot = float(ins.alpha), int(ins.ncols), int(ins.x_off), int(ins.s_slot)
-        if ins.kind == T.K_POLY:
+        d.dst_stride, d.post_scale = int(ins.dst_stride), float(ins.post_scale)
+        if ins.kind == T.K_SPMVJ:
+            qpos = np.ascontiguousarray(ins.qpos, dtype=np.int32)
+            keep.append(qpos)
+            d.qpos = _p(qpos, c_i32p)
+        if ins.kind in (T.K_POLY, T.K_SPMVJ):
             lens = np.diff(ins.ptr)
             uniform = lens.size > 0 and bool(np.all(lens == lens[0])) and lens[0] >= 1
             coef = f64(ins.coef)

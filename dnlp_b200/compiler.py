@@ -33,6 +33,8 @@ def _closure(tape, root_ids):
             continue
         need.add(i)
         stack.extend(tape.instrs[i].deps)
+        if tape.instrs[i].panel_prev is not None:
+            stack.append(tape.instrs[i].panel_prev)
     return sorted(need)
 
 
@@ -62,6 +64,67 @@ def _emit_output(b, sv, space):
     if dyn.size == sv.K:
         return const, b.emit_output(sv, space, pos=None)
     return const, b.emit_output(sv.gather(dyn), space, pos=dyn.astype(np.int64))
+
+
+def fuse_spmv_jacobian(b, g_ins, jac_ins):
+    """One pass over A for ``g = A @ phi(x)`` and ``J = A o phi'(x)`` (the two largest
+    kernels read the same (A_ij, j) and gather phi_j / phi'_j at the same random j).
+
+    Applies when the constraint values are ONE single-factor POLY whose slots are the even (value) slots of
+    interleaved pair regions, the Jacobian values are ONE one-term-per-row POLY on the odd (derivative)
+    slots, and every Jacobian entry is a term of g with the same coefficient, bit for bit.  The fused
+    instruction replaces both in the union program only: a lone ``constraints`` / ``jacobian`` callback
+    keeps its own kernel (no wasted Jacobian writes at rejected line-search points).
+    Returns the new instruction or None."""
+    tape = b.tape
+    if len(g_ins) != 1 or len(jac_ins) != 1 or not b.pairs:
+        return None
+    P, Q = g_ins[0], jac_ins[0]
+    if P.kind != T.K_POLY or Q.kind != T.K_POLY or P.accumulate or Q.accumulate:
+        return None
+    if np.any(P.f2 != NONE) or np.any(Q.f2 != NONE) or Q.coef.size != Q.count or P.coef.size < Builder.PAIR_MIN_NNZ:
+        return None
+    if not np.array_equal(Q.ptr, np.arange(Q.count + 1)):
+        return None
+    # slots must lie in pair regions: P on even (value) slots, Q on odd (derivative) slots
+    bases = np.array(sorted(b.pairs), dtype=np.int64)
+    ends = np.array([bs + 2 * b.pairs[bs][1] for bs in bases.tolist()], dtype=np.int64)
+
+    def in_pairs(slots, parity):
+        k = np.searchsorted(bases, slots, side="right") - 1
+        ok = (k >= 0) & (slots < ends[np.maximum(k, 0)])
+        return ok & (((slots - bases[np.maximum(k, 0)]) & 1) == parity)
+    real = P.f1 != NONE
+    if not np.all(in_pairs(P.f1[real], 0)) or not np.all(in_pairs(Q.f1, 1)):
+        return None
+    nsl = np.int64(tape.nslots + 2)
+    prow = np.repeat(np.arange(P.count, dtype=np.int64), np.diff(P.ptr))
+    if P.pos is not None:
+        prow = np.asarray(P.pos, dtype=np.int64)[prow]
+    qpos_of = np.arange(Q.count, dtype=np.int64) if Q.pos is None else np.asarray(Q.pos, dtype=np.int64)
+    key_p = np.where(real, prow * nsl + P.f1, -1 - np.arange(P.coef.size, dtype=np.int64))
+    key_q = tape.jac_rows[qpos_of].astype(np.int64) * nsl + (Q.f1 - 1)
+    order = np.argsort(key_p, kind="stable")
+    sk = key_p[order]
+    if sk.size > 1 and np.any(sk[1:] == sk[:-1]):
+        return None                                  # a repeated (row, column) in A: no one-to-one match
+    at = np.searchsorted(sk, key_q)
+    at = np.minimum(at, sk.size - 1)
+    if not np.all(sk[at] == key_q):
+        return None
+    term = order[at]                                 # the term of g behind every Jacobian entry
+    if not np.array_equal(P.coef[term].view(np.int64), Q.coef.view(np.int64)):
+        return None
+    qpos = np.full(P.coef.size, -1, dtype=np.int64)
+    qpos[term] = qpos_of
+    F = T.Instr(T.K_SPMVJ, dst_space=T.DST_G, dst_off=0, count=P.count, ptr=P.ptr, coef=P.coef, f1=P.f1,
+                f2=P.f2, pos=P.pos, qpos=qpos.astype(np.int32), fused_jac=(P.id, Q.id))
+    F.deps = tuple(sorted(set(P.deps) | set(Q.deps)))
+    F.uses_lam = False
+    F.dep_mask = P.dep_mask | Q.dep_mask
+    F.level = max(P.level, Q.level)
+    tape.add(F)
+    return F
 
 
 def compile_problem(prob, with_hessian=True):
@@ -167,5 +230,9 @@ def compile_problem(prob, with_hessian=True):
 
     for name, ins in (("f", f_ins), ("grad", grad_ins), ("g", g_ins), ("jac", jac_ins), ("hess", hess_ins)):
         tape.programs[name] = _closure(tape, [i.id for i in ins])
-    tape.programs["all"] = sorted(set().union(*[set(p) for p in tape.programs.values()]))
+    allp = set().union(*[set(p) for p in tape.programs.values()])
+    fused = fuse_spmv_jacobian(b, g_ins, jac_ins)
+    if fused is not None:
+        allp = (allp - {g_ins[0].id, jac_ins[0].id}) | {fused.id}
+    tape.programs["all"] = sorted(allp)
     return tape

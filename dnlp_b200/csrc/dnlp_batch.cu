@@ -87,7 +87,7 @@ using namespace dnlp;
 template <int F, bool Bn>
 void launch_belem_t(const dnlp_batch *o, const dnlp_instr_desc &d, int grid) {
   belem_kernel<F, Bn><<<grid, 256, 0, o->stream>>>(o->V, d.a_off, d.a_stride, d.b_off, d.b_stride, d.dst_off,
-                                                  d.count, d.param, o->B);
+                                                  d.count, d.param, o->B, d.dst_stride > 0 ? d.dst_stride : 1, d.post_scale);
 }
 bool launch_belem(const dnlp_batch *o, const dnlp_instr_desc &d, int grid) {
   switch (d.fcode) {
@@ -314,6 +314,7 @@ static int batch_create_impl(dnlp_batch *o, const dnlp_tape_desc *t) {
     BInstr &D = o->instrs[i];
     D.d = h;
     D.d.ptr = nullptr; D.d.coef = nullptr; D.d.f1 = nullptr; D.d.f2 = nullptr; D.d.pos = nullptr; D.d.Q = nullptr;
+    D.d.qpos = nullptr;                       // (SPMVJ only lives in the union program of the single-start engine)
     if (h.kind == DNLP_POLY) {
       if (h.ptr) { if (o->upload(h.ptr, h.count + 1, const_cast<int64_t **>(&D.d.ptr))) return 1; }
       if (o->upload(h.coef, h.nterms, const_cast<double **>(&D.d.coef))) return 1;

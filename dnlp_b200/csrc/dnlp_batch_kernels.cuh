@@ -13,14 +13,14 @@ namespace dnlp {
 template <int F, bool BINARY>
 __global__ void __launch_bounds__(256)
 belem_kernel(double *__restrict__ V, int64_t a_off, int a_stride, int64_t b_off, int b_stride,
-             int64_t dst_off, int64_t count, double p, int B) {
+             int64_t dst_off, int64_t count, double p, int B, int dst_stride, double post_scale) {
   const int64_t total = count * B;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int64_t k = e / B;
     const int b = (int)(e - k * B);
     const double a = V[(a_off + k * a_stride) * B + b];
     const double bb = BINARY ? V[(b_off + k * b_stride) * B + b] : 0.0;
-    V[dst_off * B + e] = apply_fn<F>(a, bb, p);
+    V[(dst_off + k * dst_stride) * B + b] = post_scale * apply_fn<F>(a, bb, p);
   }
 }
 

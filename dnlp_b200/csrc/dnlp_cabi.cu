@@ -29,7 +29,8 @@ using namespace dnlp;
 template <int F, bool B>
 void launch_elem_t(const dnlp_oracle *o, const dnlp_instr_desc &d, int grid) {
   elem_kernel<F, B><<<grid, 256, 0, o->cur>>>(o->V, d.a_off, d.a_stride, d.b_off, d.b_stride,
-                                                d.dst_off, d.count, d.param);
+                                                d.dst_off, d.count, d.param, d.dst_stride > 0 ? d.dst_stride : 1,
+                                                d.post_scale);
 }
 
 bool launch_elem(const dnlp_oracle *o, const dnlp_instr_desc &d, int grid) {
@@ -203,6 +204,24 @@ int dnlp_oracle::launch(DevInstr &I) {
                   (d.ptr == nullptr ? "1" : "0") + ">";
       break;
     }
+    case DNLP_SPMVJ: {
+      double *jac = out[DNLP_DST_JAC];
+      if (I.flat && flat_enabled) {
+        const int64_t need = (I.nchunks + dnlp::FLAT_WARPS - 1) / dnlp::FLAT_WARPS;
+        const int grid = (int)(need < (int64_t)sm_count * 3 ? need : (int64_t)sm_count * 3);
+        if (I.pad_shift < 31)
+          spmvj_flat_kernel<true><<<grid, 256, 0, cur>>>(V, dst, jac, d.ptr, d.row_len, d.coef, d.f1, I.jrank, I.jsorted, d.pos,
+                                                         d.nterms, I.chunk_row0, I.chunk_term0, I.nchunks, I.pad_shift);
+        else
+          spmvj_flat_kernel<false><<<grid, 256, 0, cur>>>(V, dst, jac, d.ptr, d.row_len, d.coef, d.f1, I.jrank, I.jsorted, d.pos,
+                                                          d.nterms, I.chunk_row0, I.chunk_term0, I.nchunks, I.pad_shift);
+        if (I.kname.empty()) I.kname = std::string("spmvj_flat_kernel<") + (I.pad_shift < 31 ? "1" : "0") + ">";
+      } else {
+        spmvj_rows_kernel<<<grid_for(d.count, 1), 256, 0, cur>>>(V, dst, jac, d.ptr, d.row_len, d.coef, d.f1, d.qpos, d.pos, d.count);
+        if (I.kname.empty()) I.kname = "spmvj_rows_kernel";
+      }
+      break;
+    }
     case DNLP_GEMV: {
       size_t smem = (size_t)d.ncols * sizeof(double);
       if ((d.ncols & 1) == 0 && smem <= 96 * 1024) {
@@ -260,7 +279,8 @@ int dnlp_oracle::build_batches() {
       for (auto &e : descs) {        // share the source loads: phi, phi', phi'' of one segment
         if (e.nout < 3 && e.a_off == d.a_off && e.b_off == d.b_off && e.count == d.count &&
             e.a_stride == d.a_stride && e.b_stride == d.b_stride) {
-          e.fcode[e.nout] = d.fcode; e.param[e.nout] = d.param; e.dst_off[e.nout] = d.dst_off; ++e.nout;
+          e.fcode[e.nout] = d.fcode; e.param[e.nout] = d.param; e.dst_off[e.nout] = d.dst_off;
+          e.dst_stride[e.nout] = d.dst_stride > 0 ? d.dst_stride : 1; e.scale[e.nout] = d.post_scale; ++e.nout;
           merged = true;
           break;
         }
@@ -269,6 +289,8 @@ int dnlp_oracle::build_batches() {
         dnlp::ElemDesc e{};
         e.a_off = d.a_off; e.b_off = d.b_off; e.count = d.count; e.a_stride = d.a_stride; e.b_stride = d.b_stride;
         e.nout = 1; e.fcode[0] = d.fcode; e.param[0] = d.param; e.dst_off[0] = d.dst_off;
+        e.dst_stride[0] = d.dst_stride > 0 ? d.dst_stride : 1; e.scale[0] = d.post_scale;
+        for (int k = 1; k < 3; ++k) { e.dst_stride[k] = 1; e.scale[k] = 1.0; }
         descs.push_back(e);
       }
       B.members.push_back(id);
@@ -355,13 +377,21 @@ int dnlp_oracle::issue_parallel(const std::vector<int32_t> &nodes) {
         if (last_writer[I.d.dst_space] >= 0) deps.push_back(last_writer[I.d.dst_space]);
         last_writer[I.d.dst_space] = (int)k;
       }
+      if (I.d.kind == DNLP_SPMVJ) {                   // the fused instruction also fills the Jacobian values
+        if (last_writer[DNLP_DST_JAC] >= 0) deps.push_back(last_writer[DNLP_DST_JAC]);
+        last_writer[DNLP_DST_JAC] = (int)k;
+      }
     }
     // lane choice: continue the chain of a dependency when it is still the tail of its lane,
-    // else an idle lane, else round robin
+    // else an idle lane, else round robin.  Instructions with millions of gathered terms all go to lane 0:
+    // two of them side by side evict each other's gathered vector from the L2 and both slow down (C5: the
+    // whole evaluation took LONGER than the sum of its kernels while they overlapped).
     int L = -1;
-    for (int d : deps) if (last_on_lane[lane_of[d]] == d) { L = lane_of[d]; break; }
-    if (L < 0) for (int l = 0; l < NLANE; ++l) if (last_on_lane[l] < 0) { L = l; break; }
-    if (L < 0) { L = rr; rr = (rr + 1) % NLANE; }
+    if (nodes[k] >= 0 && big_serial_terms > 0 && instrs[nodes[k]].d.kind != DNLP_ELEM &&
+        instrs[nodes[k]].d.nterms >= big_serial_terms) L = 0;
+    if (L < 0) for (int d : deps) if (last_on_lane[lane_of[d]] == d && !(big_serial_terms > 0 && lane_of[d] == 0)) { L = lane_of[d]; break; }
+    if (L < 0) for (int l = big_serial_terms > 0 ? 1 : 0; l < NLANE; ++l) if (last_on_lane[l] < 0) { L = l; break; }
+    if (L < 0) { L = big_serial_terms > 0 ? 1 + rr % (NLANE - 1) : rr; rr = (rr + 1) % NLANE; }
     if (!joined[L]) { CK(cudaStreamWaitEvent(lane[L], fork, 0)); joined[L] = true; }
     for (int d : deps)
       if (lane_of[d] != L) CK(cudaStreamWaitEvent(lane[L], event_at(1 + (size_t)d), 0));
@@ -535,7 +565,12 @@ int dnlp_device_count(void) {
   return c;
 }
 
-const char *dnlp_version(void) { return "dnlp_b200 0.1 (sm_100a)"; }
+const char *dnlp_version(void) { return "dnlp_b200 0.2 (sm_100a)"; }
+
+int dnlp_device_synchronize(int device) {
+  if (cudaSetDevice(device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) { cudaGetLastError(); return 1; }
+  return 0;
+}
 
 const char *dnlp_last_error(dnlp_oracle *o) { return o ? o->err.c_str() : g_create_error.c_str(); }
 
@@ -574,6 +609,8 @@ static int create_impl(dnlp_oracle *o, const dnlp_tape_desc *t) {
   if (const char *e = getenv("DNLP_WINDOWS")) o->win_enabled = atoi(e) != 0;
   if (const char *e = getenv("DNLP_NO_WINDOWS")) o->win_enabled = atoi(e) == 0 && o->win_enabled;
   if (const char *e = getenv("DNLP_NO_ELEM_FUSION")) o->fuse_enabled = atoi(e) == 0;  // tests / A-B measurements
+  if (const char *e = getenv("DNLP_NO_PARALLEL")) o->parallel_enabled = atoi(e) == 0;
+  if (const char *e = getenv("DNLP_BIG_SERIAL_TERMS")) o->big_serial_terms = atoll(e);
 
   void *p = nullptr;
   CK(cudaMalloc(&p, (size_t)(t->nslots + 2) * sizeof(double)));
@@ -619,19 +656,30 @@ static int create_impl(dnlp_oracle *o, const dnlp_tape_desc *t) {
     D.d = h;
     D.d.ptr = nullptr; D.d.coef = nullptr; D.d.f1 = nullptr; D.d.f2 = nullptr; D.d.pos = nullptr; D.d.Q = nullptr;
     D.d.deps = nullptr;
+    D.d.qpos = nullptr;
+    if (D.d.dst_stride <= 0) D.d.dst_stride = 1;
+    if (h.kind == DNLP_ELEM && D.d.post_scale == 0.0 && h.post_scale == 0.0) D.d.post_scale = 1.0;   // zero-initialised descriptor
     for (int64_t k = 0; k < h.n_deps; ++k) {
       if (h.deps[k] < 0 || h.deps[k] >= i) { err = "instruction depends on a later or unknown instruction"; return 1; }
       D.deps.push_back(h.deps[k]);
     }
-    if (h.kind == DNLP_POLY) {
+    if (h.kind == DNLP_POLY || h.kind == DNLP_SPMVJ) {
       if (h.ptr) { if (o->upload(h.ptr, h.count + 1, const_cast<int64_t **>(&D.d.ptr))) return 1; }
       if (o->upload(h.coef, h.nterms, const_cast<double **>(&D.d.coef))) return 1;
       if (o->upload(h.f1, h.nterms, const_cast<int32_t **>(&D.d.f1))) return 1;
       if (h.f2) { if (o->upload(h.f2, h.nterms, const_cast<int32_t **>(&D.d.f2))) return 1; }
+      if (h.kind == DNLP_SPMVJ) {
+        if (h.f2 || !h.qpos) { err = "SPMVJ needs single-factor terms and Jacobian positions"; return 1; }
+        for (int64_t t2 = 0; t2 < h.nterms; ++t2) {
+          if (h.f1[t2] >= 0 && ((h.f1[t2] & 1) || h.f1[t2] + 1 >= t->nslots)) { err = "SPMVJ: value slots must be even (pair layout)"; return 1; }
+          if (h.qpos[t2] >= t->nnz_jac) { err = "SPMVJ: Jacobian position out of range"; return 1; }
+        }
+        if (o->upload(h.qpos, h.nterms, const_cast<int32_t **>(&D.d.qpos))) return 1;
+      }
       D.has_f2 = h.f2 != nullptr;
       D.mean_len = h.count > 0 ? (double)h.nterms / (double)h.count : 1.0;
       // contiguous slots and (for reductions) one shared coefficient?  -> index-free kernels
-      if (h.nterms >= 2048 && (h.count == 1 || (!h.ptr && h.row_len == 1)) && h.f1[0] >= 0 &&
+      if (h.kind == DNLP_POLY && h.nterms >= 2048 && (h.count == 1 || (!h.ptr && h.row_len == 1)) && h.f1[0] >= 0 &&
           (!h.f2 || h.f2[0] >= 0)) {
         bool contig = true, cc = true;
         for (int64_t t2 = 1; t2 < h.nterms && contig; ++t2) {
@@ -684,6 +732,30 @@ static int create_impl(dnlp_oracle *o, const dnlp_tape_desc *t) {
             if (conf < best_conf) { best_conf = conf; D.pad_shift = shifts[si]; }
           }
           D.flat = true;
+          if (h.kind == DNLP_SPMVJ) {
+            // rank the terms each chunk owns by Jacobian position (terms without one go last)
+            std::vector<uint8_t> jrank((size_t)h.nterms + 2, 0);
+            std::vector<int32_t> jsorted((size_t)h.nterms + 2, -1);
+            const int64_t nch = D.nchunks;
+#pragma omp parallel for schedule(static)
+            for (int64_t ci = 0; ci < nch; ++ci) {
+              const int64_t t0c = rb(row0[ci]), t1c = rb(row0[ci + 1]);
+              const int nown = (int)(t1c - t0c);
+              int idx[dnlp::FLAT_CHUNK];
+              for (int i = 0; i < nown; ++i) idx[i] = i;
+              std::sort(idx, idx + nown, [&](int a, int b) {
+                const int32_t qa = h.qpos[t0c + a], qb = h.qpos[t0c + b];
+                const uint32_t ua = qa < 0 ? 0xFFFFFFFFu : (uint32_t)qa, ub = qb < 0 ? 0xFFFFFFFFu : (uint32_t)qb;
+                return ua != ub ? ua < ub : a < b;
+              });
+              for (int i = 0; i < nown; ++i) {
+                jrank[t0c + idx[i]] = (uint8_t)i;
+                jsorted[t0c + i] = h.qpos[t0c + idx[i]];
+              }
+            }
+            if (o->upload(jrank.data(), (int64_t)jrank.size(), &D.jrank)) return 1;
+            if (o->upload(jsorted.data(), (int64_t)jsorted.size(), &D.jsorted)) return 1;
+          }
         }
       }
       // gathers that concentrate on a short slot range (SpMV against a small x): the flat kernel
@@ -696,7 +768,7 @@ static int create_impl(dnlp_oracle *o, const dnlp_tape_desc *t) {
     } else if (h.kind == DNLP_SCALE) {
       if (o->upload(h.coef, h.count, const_cast<double **>(&D.d.coef))) return 1;
     }
-    if ((h.kind == DNLP_POLY || h.kind == DNLP_SCALE) && h.pos) {
+    if ((h.kind == DNLP_POLY || h.kind == DNLP_SCALE || h.kind == DNLP_SPMVJ) && h.pos) {
       if (o->upload(h.pos, h.count, const_cast<int32_t **>(&D.d.pos))) return 1;
     }
   }

@@ -44,6 +44,9 @@ struct DevInstr {
   int64_t *chunk_term0 = nullptr;      // nchunks: first term of the chunk's window (even)
   int64_t nchunks = 0;
   int pad_shift = 31;
+  // SPMVJ: rank of every term among the Jacobian positions of its chunk, and the positions in that order
+  uint8_t *jrank = nullptr;
+  int32_t *jsorted = nullptr;
 };
 
 // All x-only elementwise instructions of one program, fused into a single launch.
@@ -106,6 +109,8 @@ struct dnlp_oracle {
   int cur_lane = 0;
   std::vector<cudaEvent_t> ev_pool;    // capture-time dependency markers
   bool parallel_enabled = true;
+  int64_t big_serial_terms = 1 << 24;  // instructions with at least this many terms are serialised on lane 0 (0 = off):
+                                       // C5 1.173 ms with every branch parallel, 1.104 fully serial, 1.089 with this rule
   bool win_enabled = false;            // shared-memory gather window of the flat kernel.  OFF by default:
                                        // on the C3 SpMV (x in R^4096) the window costs bank conflicts and
                                        // MIO pressure while plain gathers hit L1 - 0.104 ms with, 0.086 ms

@@ -98,13 +98,13 @@ __device__ __forceinline__ double apply_fn(double a, double b, double p) {
 template <int F, bool BINARY>
 __global__ void __launch_bounds__(256)
 elem_kernel(double *__restrict__ V, int64_t a_off, int a_stride, int64_t b_off, int b_stride,
-            int64_t dst_off, int64_t count, double p) {
+            int64_t dst_off, int64_t count, double p, int dst_stride, double post_scale) {
   const double *__restrict__ A = V + a_off;
   const double *__restrict__ B = V + b_off;
   double *__restrict__ D = V + dst_off;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
-  const bool vec_ok = a_stride == 1 && ((a_off | dst_off) & 1) == 0 &&
+  const bool vec_ok = a_stride == 1 && ((a_off | dst_off) & 1) == 0 && dst_stride == 1 &&
                       (!BINARY || b_stride == 0 || (b_stride == 1 && (b_off & 1) == 0));
   if (vec_ok) {
     const int64_t n2 = count >> 1;
@@ -117,17 +117,18 @@ elem_kernel(double *__restrict__ V, int64_t a_off, int a_stride, int64_t b_off, 
       double2 b = make_double2(b0, b0);
       if (BINARY && b_stride == 1) b = B2[i];
       double2 r;
-      r.x = apply_fn<F>(a.x, b.x, p);
-      r.y = apply_fn<F>(a.y, b.y, p);
+      r.x = post_scale * apply_fn<F>(a.x, b.x, p);
+      r.y = post_scale * apply_fn<F>(a.y, b.y, p);
       D2[i] = r;
     }
     if ((count & 1) && tid == 0) {
       int64_t k = count - 1;
-      D[k] = apply_fn<F>(A[k], BINARY ? B[k * b_stride] : 0.0, p);
+      D[k] = post_scale * apply_fn<F>(A[k], BINARY ? B[k * b_stride] : 0.0, p);
     }
   } else {
+    // (dst_stride 2: the interleaved value / derivative pair layout the fused SpMV + Jacobian fill gathers)
     for (int64_t k = tid; k < count; k += nthr)
-      D[k] = apply_fn<F>(A[k * a_stride], BINARY ? B[k * b_stride] : 0.0, p);
+      D[k * dst_stride] = post_scale * apply_fn<F>(A[k * a_stride], BINARY ? B[k * b_stride] : 0.0, p);
   }
 }
 
@@ -666,6 +667,133 @@ poly_flat_kernel(const double *__restrict__ V, double *dst, const int64_t *__res
   }
 }
 
+// ---- SPMVJ: constraint value A @ phi(x) and Jacobian fill A o phi'(x) in one pass over A ------------------
+// Random gathers from a vector that does not fit L1 cost one 32-byte sector each and run at the sector rate
+// of the L2 -> SM path (measured with tools/kbench2: 50 M gathers take ~0.24 ms whatever the 8-byte
+// streams around them do, from 10 MB or from 50 MB).  g = A phi(x) and J = A o phi'(x) gather at the SAME
+// (i, j); with phi_j and phi'_j interleaved in one 16-byte pair (value at an even slot, derivative right
+// after it) a single 128-bit gather serves both, and A's (coef, index) stream is read once instead of twice.
+// Same chunked warp-per-window scheme as poly_flat_kernel; per term additionally a 4-byte Jacobian
+// position (qpos, -1 = none) and one streaming store of coef * phi'.
+__device__ __forceinline__ double2 ld_pair_if(const double *p, bool take, uint64_t pol) {
+  double2 v;
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %4, 0;\n\tmov.f64 %0, 0d3FF0000000000000;\n\tmov.f64 %1, 0d0000000000000000;\n\t"
+               "@p ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;\n\t}"
+               : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol), "r"((int)take) : "memory");
+  return v;
+}
+
+// Jacobian stores: the terms of a window belong to ~10 different column segments, i.e. to ~10 distant
+// regions of the Jacobian; stored straight from the term order every lane would write a lone 8 bytes of its
+// own sector (measured: 0.78 ms, slower than the two separate kernels).  The host therefore ranks the terms
+// of every chunk by Jacobian position once (jrank, one byte per term; jsorted = the positions in that
+// order): lanes drop their values into shared memory at their rank and the warp then writes the sorted
+// list, whose neighbours are neighbours in the Jacobian (runs of ~32 entries per segment).
+template <bool PAD>
+__global__ void __launch_bounds__(FLAT_WARPS * 32, 3)
+spmvj_flat_kernel(const double *__restrict__ V, double *g, double *__restrict__ jac, const int64_t *__restrict__ ptr,
+                  int row_len, const double *__restrict__ coef, const int32_t *__restrict__ f1,
+                  const uint8_t *__restrict__ jrank, const int32_t *__restrict__ jsorted,
+                  const int32_t *__restrict__ pos, int64_t nterms,
+                  const int32_t *__restrict__ chunk_row0, const int64_t *__restrict__ chunk_term0, int64_t nchunks,
+                  int pad_shift) {
+  __shared__ __align__(16) double prod_all[FLAT_WARPS][FLAT_PROD];
+  __shared__ __align__(16) double jbuf_all[FLAT_WARPS][FLAT_CHUNK];
+  const uint64_t pf = l2_policy_evict_first(), pl = l2_policy_evict_last();
+  auto padf = [&](int k) -> int { return PAD ? k + ((k >> pad_shift) << 1) : k; };
+  auto row_begin = [&](int64_t r) -> int64_t { return ptr ? __ldg(ptr + r) : r * (int64_t)row_len; };
+  auto pair = [&](int idx) -> double2 { return ld_pair_if(V + (idx >= 0 ? idx : 0), idx >= 0, pl); };
+  const int lane = threadIdx.x & 31;
+  double *prod = prod_all[threadIdx.x >> 5];
+  double *jbuf = jbuf_all[threadIdx.x >> 5];
+  const int64_t nwarps = (int64_t)gridDim.x * FLAT_WARPS;
+  int64_t c = (int64_t)blockIdx.x * FLAT_WARPS + (threadIdx.x >> 5);
+  if (c >= nchunks) return;
+  int R0 = __ldg(chunk_row0 + c), R1 = __ldg(chunk_row0 + c + 1);
+  int64_t a0 = __ldg(chunk_term0 + c);
+  while (true) {
+    const int64_t cn = c + nwarps;
+    int nR0 = 0, nR1 = 0;
+    int64_t na0 = 0;
+    if (cn < nchunks) { nR0 = __ldg(chunk_row0 + cn); nR1 = __ldg(chunk_row0 + cn + 1); na0 = __ldg(chunk_term0 + cn); }
+    int64_t s = 0, e = 0;
+    if (R0 + lane < R1) { s = row_begin(R0 + lane); e = row_begin(R0 + lane + 1); }
+    const int64_t own0 = row_begin(R0), own1 = row_begin(R1);     // the terms this chunk owns: [own0, own1)
+    const int ks = (int)(own0 - a0), ke = (int)(own1 - a0);
+    if (a0 + FLAT_CHUNK <= nterms) {
+      const double2 *c2 = reinterpret_cast<const double2 *>(coef + a0);
+      const int2 *a2 = reinterpret_cast<const int2 *>(f1 + a0);
+      const unsigned short *r2 = reinterpret_cast<const unsigned short *>(jrank + a0);
+      double2 cv[4];
+      int2 av[4];
+      unsigned rk[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        cv[j] = ld_stream_f64x2(c2 + j * 32 + lane, pf);
+        av[j] = ld_stream_s32x2(a2 + j * 32 + lane, pf);
+        rk[j] = __ldg(r2 + j * 32 + lane);
+      }
+      double2 px[4], py[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { px[j] = pair(av[j].x); py[j] = pair(av[j].y); }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = 2 * (j * 32 + lane);
+        *reinterpret_cast<double2 *>(prod + padf(k)) = make_double2(cv[j].x * px[j].x, cv[j].y * py[j].x);
+        if (k >= ks && k < ke) jbuf[rk[j] & 0xFF] = cv[j].x * px[j].y;
+        if (k + 1 >= ks && k + 1 < ke) jbuf[rk[j] >> 8] = cv[j].y * py[j].y;
+      }
+    } else {
+      for (int k = lane; k < (int)(nterms - a0); k += 32) {
+        const double cc = ld_stream_f64(coef + a0 + k, pf);
+        const double2 pv = pair(ld_stream_s32(f1 + a0 + k, pf));
+        prod[padf(k)] = cc * pv.x;
+        if (k >= ks && k < ke) jbuf[jrank[a0 + k]] = cc * pv.y;
+      }
+    }
+    __syncwarp();
+    for (int i = lane; i < ke - ks; i += 32) {
+      const int q = ld_stream_s32(jsorted + own0 + i, pf);
+      if (q >= 0) st_stream_f64(jac + q, jbuf[i], pf);
+    }
+    for (int r = R0 + lane; r < R1; r += 32) {
+      if (r != R0 + lane) { s = row_begin(r); e = row_begin(r + 1); }
+      int k = (int)(s - a0);
+      const int kend = (int)(e - a0);
+      double acc = 0.0;
+      for (; k + 4 <= kend; k += 4) {
+        const double p0 = prod[padf(k)], p1 = prod[padf(k + 1)], p2 = prod[padf(k + 2)], p3 = prod[padf(k + 3)];
+        acc = (((acc + p0) + p1) + p2) + p3;
+      }
+      for (; k < kend; ++k) acc += prod[padf(k)];
+      g[pos ? (int64_t)__ldg(pos + r) : r] = acc;
+    }
+    if (cn >= nchunks) break;
+    c = cn; R0 = nR0; R1 = nR1; a0 = na0;
+    __syncwarp();
+  }
+}
+
+// general fallback (rows longer than a window, small instructions): one thread per row
+static __global__ void __launch_bounds__(256)
+spmvj_rows_kernel(const double *__restrict__ V, double *__restrict__ g, double *__restrict__ jac,
+                  const int64_t *__restrict__ ptr, int row_len, const double *__restrict__ coef,
+                  const int32_t *__restrict__ f1, const int32_t *__restrict__ qpos, const int32_t *__restrict__ pos,
+                  int64_t count) {
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < count; r += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t0 = ptr ? ptr[r] : r * (int64_t)row_len, t1 = ptr ? ptr[r + 1] : t0 + row_len;
+    double acc = 0.0;
+    for (int64_t t = t0; t < t1; ++t) {
+      const double c = coef[t];
+      const int idx = f1[t], q = qpos[t];
+      const double v = idx >= 0 ? V[idx] : 1.0;
+      acc += c * v;
+      if (q >= 0) jac[q] = c * (idx >= 0 ? V[idx + 1] : 0.0);
+    }
+    g[pos ? (int64_t)pos[r] : r] = acc;
+  }
+}
+
 // ---- K1 batched: every x-only elementwise segment of a program in ONE launch ----------------
 // A descriptor is one contiguous segment with up to three outputs that share the loads of the
 // source (phi, phi', phi'' of the same atom: x is read once).  Tiles of all descriptors are dealt
@@ -674,7 +802,9 @@ struct ElemDesc {
   int64_t a_off, b_off, count, tile0;      // tile0: first global tile index of this descriptor
   int64_t dst_off[3];
   double param[3];
+  double scale[3];                         // result multiplier per output (p * x^(p-1) as one value)
   int32_t fcode[3];
+  int32_t dst_stride[3];                   // 1, or 2 for the interleaved (value, derivative) pair layout
   int32_t nout, a_stride, b_stride;
   int32_t group;                           // GRP_*: outputs of one family share their transcendental calls
 };
@@ -737,15 +867,24 @@ __device__ __forceinline__ void fused_tile(double *__restrict__ V, const ElemDes
       fused_point<GRP>(a.y, d, want_val, ry);
 #pragma unroll
       for (int o = 0; o < 3; ++o)
-        if (o < d.nout) *reinterpret_cast<double2 *>(V + d.dst_off[o] + k) = make_double2(rx[o], ry[o]);
+        if (o < d.nout)
+          *reinterpret_cast<double2 *>(V + d.dst_off[o] + k) = make_double2(d.scale[o] * rx[o], d.scale[o] * ry[o]);
     }
   } else {
+    // value and first derivative of a pair region land next to each other: one 16-byte store per element
+    const bool pair01 = d.nout >= 2 && d.dst_stride[0] == 2 && d.dst_stride[1] == 2 && d.dst_off[1] == d.dst_off[0] + 1 &&
+                        (d.dst_off[0] & 1) == 0;
     for (int64_t k = e0 + threadIdx.x; k < e1; k += 256) {
       double r[3];
       fused_point<GRP>(A[k * d.a_stride], d, want_val, r);
+      if (pair01) {
+        *reinterpret_cast<double2 *>(V + d.dst_off[0] + 2 * k) = make_double2(d.scale[0] * r[0], d.scale[1] * r[1]);
+        if (d.nout > 2) V[d.dst_off[2] + k * d.dst_stride[2]] = d.scale[2] * r[2];
+      } else {
 #pragma unroll
-      for (int o = 0; o < 3; ++o)
-        if (o < d.nout) V[d.dst_off[o] + k] = r[o];
+        for (int o = 0; o < 3; ++o)
+          if (o < d.nout) V[d.dst_off[o] + k * d.dst_stride[o]] = d.scale[o] * r[o];
+      }
     }
   }
 }
@@ -761,7 +900,8 @@ __device__ __forceinline__ void elem_tile(double *__restrict__ V, const ElemDesc
   const double *__restrict__ A = V + d.a_off;
   const double *__restrict__ B = V + d.b_off;
   double *__restrict__ D = V + d.dst_off[o];
-  const double p = d.param[o];
+  const double p = d.param[o], sc = d.scale[o];
+  const int ds = d.dst_stride[o];
   if (vec_ok) {
     for (int64_t k = e0 + 2 * threadIdx.x; k < e1; k += 512) {
       const double2 a = *reinterpret_cast<const double2 *>(A + k);
@@ -771,13 +911,13 @@ __device__ __forceinline__ void elem_tile(double *__restrict__ V, const ElemDesc
         else b = make_double2(B[0], B[0]);
       }
       double2 r;
-      r.x = apply_fn<F>(a.x, b.x, p);
-      r.y = apply_fn<F>(a.y, b.y, p);
+      r.x = sc * apply_fn<F>(a.x, b.x, p);
+      r.y = sc * apply_fn<F>(a.y, b.y, p);
       *reinterpret_cast<double2 *>(D + k) = r;
     }
   } else {
     for (int64_t k = e0 + threadIdx.x; k < e1; k += 256)
-      D[k] = apply_fn<F>(A[k * d.a_stride], F >= F_REL_ENTR ? B[k * d.b_stride] : 0.0, p);
+      D[k * ds] = sc * apply_fn<F>(A[k * d.a_stride], F >= F_REL_ENTR ? B[k * d.b_stride] : 0.0, p);
   }
 }
 
@@ -796,7 +936,7 @@ elem_batch_kernel(double *__restrict__ V, const ElemDesc *__restrict__ descs, in
     const int64_t e1 = (e0 + ELEM_TILE < d.count) ? e0 + ELEM_TILE : d.count;
     bool vec_ok = d.a_stride == 1 && (d.a_off & 1) == 0 && (d.b_stride == 0 || (d.b_off & 1) == 0) &&
                   ((e1 - e0) & 1) == 0;
-    for (int o = 0; o < d.nout; ++o) vec_ok = vec_ok && (d.dst_off[o] & 1) == 0;
+    for (int o = 0; o < d.nout; ++o) vec_ok = vec_ok && (d.dst_off[o] & 1) == 0 && d.dst_stride[o] == 1;
     if (d.group == GRP_TRIG) { fused_tile<GRP_TRIG>(V, d, e0, e1, vec_ok); continue; }
     if (d.group == GRP_LOGISTIC) { fused_tile<GRP_LOGISTIC>(V, d, e0, e1, vec_ok); continue; }
     if (d.group == GRP_TANH) { fused_tile<GRP_TANH>(V, d, e0, e1, vec_ok); continue; }

@@ -54,7 +54,12 @@ class Builder:
         self._elem_cache = {}
         self._value_cache = {}
         self._mat_cache = {}
-        self._producers = []        # (start, end, instr id) of V ranges written by instructions
+        self._producers = []        # [start, end, instr id, id of the odd-slot writer | -1] of V ranges
+        # (value, derivative) pairs stored interleaved so that the fused SpMV + Jacobian fill gathers both
+        # with one 16-byte load (compiler.fuse_spmv_jacobian); keys come from a scan of the constraints
+        self._pair_keys = self._scan_pair_candidates(prob) if self.PAIRING else set()
+        self._pair_base = {}
+        self.pairs = {}             # base slot -> (key, count): the interleaved regions
 
     # ---- emission ----------------------------------------------------------
     def _deps_of_slots(self, slots):
@@ -71,12 +76,21 @@ class Builder:
             starts = np.array([p[0] for p in prod], dtype=np.int64)
             ends = np.array([p[1] for p in prod], dtype=np.int64)
             ids = np.array([p[2] for p in prod], dtype=np.int64)
+            odd = np.array([p[3] for p in prod], dtype=np.int64)
             tmp = slots[slots >= self.tape.n + 1 + self.tape.m]
             if tmp.size:
                 k = np.searchsorted(starts, tmp, side="right") - 1
                 ok = (k >= 0) & (tmp < ends[np.maximum(k, 0)])
-                hit = np.bincount(k[ok], minlength=len(prod)) > 0
-                deps = set(ids[hit].tolist())
+                k, tmp = k[ok], tmp[ok]
+                paired = odd[k] != -2                # -2: a plain contiguous range
+                plain = np.bincount(k[~paired], minlength=len(prod)) > 0
+                deps = set(ids[plain].tolist())
+                if paired.any():                     # interleaved region: even slots / odd slots have different writers
+                    par = (tmp[paired] - starts[k[paired]]) & 1
+                    ev = np.bincount(k[paired][par == 0], minlength=len(prod)) > 0
+                    od = np.bincount(k[paired][par == 1], minlength=len(prod)) > 0
+                    deps |= set(int(i) for i in ids[ev].tolist() if i >= 0)
+                    deps |= set(int(i) for i in odd[od].tolist() if i >= 0)
         return deps, uses_lam
 
     def _finish(self, ins, read_slots):
@@ -91,7 +105,18 @@ class Builder:
         ins.level = 1 + max([self.tape.instrs[d].level for d in deps], default=-1)
         self.tape.add(ins)
         if ins.dst_space == T.DST_V:
-            self._producers.append((ins.dst_off, ins.dst_off + ins.count, ins.id))
+            if ins.dst_stride == 2:
+                base = ins.dst_off & ~1
+                for p in self._producers:
+                    if p[0] == base and p[3] != -2:
+                        p[2 + (ins.dst_off & 1)] = ins.id
+                        break
+                else:
+                    ent = [base, base + 2 * ins.count, -1, -1]
+                    ent[2 + (ins.dst_off & 1)] = ins.id
+                    self._producers.append(ent)
+            else:
+                self._producers.append([ins.dst_off, ins.dst_off + ins.count, ins.id, -2])
         return ins
 
     def materialise(self, sv):
@@ -145,8 +170,45 @@ class Builder:
                      np.concatenate([sv.f2[keep], none])[order])
         return self._split_long_rows(out)
 
+    # Column panels for SpMV-shaped instructions whose gathered slots span more than the L2 can keep: random
+    # 8-byte gathers from an 80 MB vector miss the L2 half of the time (each miss moves a 32-byte sector from
+    # HBM); cutting the columns into two panels of <= 48 MB, one pass each (the second pass adds to the first
+    # one's row sums), took the C5 SpMV from 0.343 to 0.272 ms in tools/kbench2; three or more panels lose
+    # again to the per-pass overhead (profiles/r02_kbench2.txt).
+    PANEL_MIN_TERMS = 1 << 22
+    PANEL_SPAN_BYTES = 48 << 20
+    PANEL_MAX = 2
+
+    def _column_panels(self, sv):
+        """[sv] or the list of per-panel SymVecs (same rows, terms partitioned by gathered slot)."""
+        if sv.nterms < self.PANEL_MIN_TERMS or sv.K < 2 or np.any(sv.f2 != NONE) or sv.nterms < 4 * sv.K:
+            return [sv]
+        real = sv.f1 != NONE
+        if not real.any():
+            return [sv]
+        lo, hi = int(sv.f1[real].min()), int(sv.f1[real].max()) + 1
+        P = min(self.PANEL_MAX, -(-(hi - lo) * 8 // self.PANEL_SPAN_BYTES))
+        if P < 2:
+            return [sv]
+        width = -(-(hi - lo) // P)
+        pan = np.where(real, (sv.f1 - lo) // width, 0)
+        return [SymVec(sv.K, sv.row[pan == p], sv.coef[pan == p], sv.f1[pan == p], sv.f2[pan == p]) for p in range(P)]
+
     def emit_poly(self, sv, dst_space, dst_off, pos=None, count=None, accumulate=False):
         sv = self._split_long_rows(sv)
+        if not accumulate and count is None and dst_space != T.DST_V:
+            # (output arrays only: the engine already runs the writers of one output array in program order)
+            panels = self._column_panels(sv)
+            if len(panels) > 1:
+                prev = self._emit_poly_raw(panels[0], dst_space, dst_off, pos, sv.K, False)
+                for pv in panels[1:]:
+                    ins = self._emit_poly_raw(pv, dst_space, dst_off, pos, sv.K, True)
+                    ins.panel_prev = prev.id       # the program closure keeps the earlier passes
+                    prev = ins
+                return prev
+        return self._emit_poly_raw(sv, dst_space, dst_off, pos, count, accumulate)
+
+    def _emit_poly_raw(self, sv, dst_space, dst_off, pos=None, count=None, accumulate=False):
         ins = T.Instr(T.K_POLY, dst_space=dst_space, dst_off=int(dst_off),
                       count=sv.K if count is None else count,
                       ptr=sv.ptr.copy(), coef=sv.coef, f1=sv.f1, f2=sv.f2, pos=pos,
@@ -188,8 +250,54 @@ class Builder:
             return roots
         return [self.emit_poly(sv, space, 0, pos=pos)]
 
-    def elem(self, fcode, a, b=None, param=0.0):
-        """dst = F(a, b); operands are broadcast when they have a single entry."""
+    DISTRIBUTE = True         # phi'' * (A' lambda) as rows of two-factor terms instead of a materialised A' lambda
+    DISTRIBUTE_MAX_MEAN = 32  # ... when the adjoint weights have at most this many terms per entry on average
+    # Interleaved (value, derivative) pairs + the fused SpMV / Jacobian-fill instruction: implemented, tested,
+    # and OFF - measured on B200 at the C5 size (profiles/r02_c5_fusion_ab.txt) the fused kernel needs 0.78 -
+    # 0.83 ms against 0.34 + 0.28 ms for the two separate kernels: the pair array is twice as large as phi
+    # alone (160 MB > L2), so the one gather per entry that fusion saves is paid back in DRAM sector misses,
+    # and the plain SpMV on the strided pair slots slows down from 0.34 to 0.73 ms for the same reason.
+    PAIRING = False           # interleave (value, derivative) of atoms feeding a large constant matmul
+    PAIR_MIN_NNZ = 1 << 18    # ... when the matrix has at least this many entries
+
+    def _scan_pair_candidates(self, prob):
+        """Keys (op, p, a_off, count) of the unary atoms phi(x_var) that appear as ``C @ phi(x)`` with a large
+        constant C inside a constraint: their value and first derivative are what the constraint value
+        and its Jacobian gather, entry by entry, with the same indices."""
+        keys = set()
+
+        def nnz_of(c):
+            v = c.attrs["value"]
+            return int(v.nnz) if sp.issparse(v) else int(np.count_nonzero(v))
+
+        def walk(n, seen):
+            if id(n) in seen:
+                return
+            seen.add(id(n))
+            if n.op == "matmul" and n.args[0].is_constant() and not n.args[1].is_constant():
+                y = n.args[1]
+                if (y.op in T.UNARY_TABLE or y.op == "power") and y.args[0].is_var() and len(y.shape) <= 1 \
+                        and nnz_of(n.args[0]) >= self.PAIR_MIN_NNZ:
+                    x = y.args[0]
+                    keys.add((y.op, float(y.attrs["p"]) if y.op == "power" else 0.0,
+                              self.var_off[x.attrs["id"]], x.size))
+            for a in n.args:
+                walk(a, seen)
+        seen = set()
+        for c in prob.constraints:
+            walk(c, seen)
+        return keys
+
+    def _pair_key(self, node):
+        x = node.args[0]
+        if not x.is_var():
+            return None
+        key = (node.op, float(node.attrs["p"]) if node.op == "power" else 0.0, self.var_off[x.attrs["id"]], x.size)
+        return key if key in self._pair_keys else None
+
+    def elem(self, fcode, a, b=None, param=0.0, post_scale=1.0, pair=None):
+        """dst = post_scale * F(a, b); operands are broadcast when they have a single entry.
+        ``pair`` = (key, role): role 0 (value) / 1 (first derivative) of an interleaved pair region."""
         count = max(a.K, b.K if b is not None else 1)
 
         def operand(sv):
@@ -198,17 +306,28 @@ class Builder:
 
         a_off, a_st = operand(a)
         b_off, b_st = operand(b) if b is not None else (0, 0)
-        key = (fcode, float(param), a_off, a_st, b_off, b_st, count)
+        key = (fcode, float(param), a_off, a_st, b_off, b_st, count, float(post_scale), pair)
         if key in self._elem_cache:
             return self._elem_cache[key]
-        dst = self.tape.alloc(count)
+        stride = 1
+        if pair is not None:
+            pkey, role = pair
+            if pkey not in self._pair_base:
+                if self.tape.nslots & 1:
+                    self.tape.alloc(1)               # pairs start at an even slot: one 16-byte gather per pair
+                self._pair_base[pkey] = self.tape.alloc(2 * count)
+                self.pairs[self._pair_base[pkey]] = (pkey, count)
+            dst, stride = self._pair_base[pkey] + role, 2
+        else:
+            dst = self.tape.alloc(count)
         ins = T.Instr(T.K_ELEM, dst_off=dst, count=count, fcode=fcode, param=float(param),
-                      a_off=a_off, a_stride=a_st, b_off=b_off, b_stride=b_st)
+                      a_off=a_off, a_stride=a_st, b_off=b_off, b_stride=b_st, dst_stride=stride,
+                      post_scale=float(post_scale))
         reads = [np.arange(a_off, a_off + (count if a_st else 1))]
         if b is not None:
             reads.append(np.arange(b_off, b_off + (count if b_st else 1)))
         self._finish(ins, np.concatenate(reads))
-        out = SymVec.slot_range(dst, count)
+        out = SymVec.slot_range(dst, count) if stride == 1 else SymVec.slots(dst + 2 * np.arange(count, dtype=np.int64))
         self._elem_cache[key] = out
         return out
 
@@ -226,6 +345,13 @@ class Builder:
 
         def simple(sv):
             return bool(np.all(sv.term_counts() <= 1)) and (sv.nterms == 0 or int(sv.arity().max()) <= 1)
+
+        def short_linear(sv):       # a few single-factor terms per entry: cheaper to distribute than to write out
+            return sv.nterms <= self.DISTRIBUTE_MAX_MEAN * max(sv.K, 1) and (sv.nterms == 0 or int(sv.arity().max()) <= 1)
+        if self.DISTRIBUTE and simple(a) and short_linear(b):
+            return a.distribute(b)
+        if self.DISTRIBUTE and simple(b) and short_linear(a):
+            return b.distribute(a)
         if not simple(a):
             a = self.materialise(a)
         if not a.can_multiply_directly(b) and not simple(b):
@@ -305,9 +431,11 @@ class Builder:
         if op == "matmul":                                 # affine/binary_operators.py:134-140
             return self._value_matmul(node)
         if op in T.UNARY_TABLE:
-            return self.elem(T.UNARY_TABLE[op][0], self.value(a[0]))
+            pk = self._pair_key(node)
+            return self.elem(T.UNARY_TABLE[op][0], self.value(a[0]), pair=None if pk is None else (pk, 0))
         if op == "power":                                  # elementwise/power.py:187-188 (exact p)
-            return self.elem(T.F_POW, self.value(a[0]), param=node.attrs["p"])
+            pk = self._pair_key(node)
+            return self.elem(T.F_POW, self.value(a[0]), param=node.attrs["p"], pair=None if pk is None else (pk, 0))
         if op == "rel_entr":                               # elementwise/rel_entr.py:36-40
             return self.elem(T.F_REL_ENTR, self.value(a[0]), self.value(a[1]))
         if op == "quad_over_lin":                          # quad_over_lin.py:39-45
@@ -711,7 +839,9 @@ class Builder:
     def _jac_unary(self, node):                            # e.g. elementwise/exp.py:112-121
         x = node.args[0]
         idxs = np.arange(x.size, dtype=np.int64)
-        return {x.attrs["id"]: (idxs, idxs, self.elem(T.UNARY_TABLE[node.op][1], self.var_slots(x)))}
+        pk = self._pair_key(node)
+        return {x.attrs["id"]: (idxs, idxs, self.elem(T.UNARY_TABLE[node.op][1], self.var_slots(x),
+                                                      pair=None if pk is None else (pk, 1)))}
 
     def _jac_power(self, node):                            # elementwise/power.py:433-449
         p = node.attrs["p_rational"] if node.attrs["p_rational"] is not None else node.attrs["p"]
@@ -719,7 +849,11 @@ class Builder:
             return {}
         x = node.args[0]
         idxs = np.arange(x.size, dtype=np.int64)
-        vals = self.elem(T.F_POW, self.var_slots(x), param=float(p) - 1).scale(float(p))
+        pk = self._pair_key(node)
+        if pk is not None:       # the pair's derivative slot holds p * x^(p-1) itself (what the fused fill gathers)
+            vals = self.elem(T.F_POW, self.var_slots(x), param=float(p) - 1, post_scale=float(p), pair=(pk, 1))
+        else:
+            vals = self.elem(T.F_POW, self.var_slots(x), param=float(p) - 1).scale(float(p))
         return {x.attrs["id"]: (idxs, idxs, vals)}
 
     def _jac_rel_entr(self, node):                         # elementwise/rel_entr.py:129-148

@@ -247,6 +247,22 @@ class SymVec:
         assert not F.size or np.all(F[:, 2] == NONE), "product exceeds two factors per term"
         return SymVec(self.K, rows, coef, F[:, 0], F[:, 1])
 
+    def distribute(self, other):
+        """Entrywise product of ``self`` (at most ONE term per entry, at most one factor) with ``other``
+        (any number of single-factor terms per entry): (c V[s]) * sum_t c_t V[f_t] = sum_t c c_t V[s] V[f_t].
+        The adjoint weights A' lambda of a second-derivative rule thus never have to be written out: the
+        Hessian entry phi''_j * sum_i A_ij lambda_i becomes one row of two-factor terms."""
+        assert self.K == other.K
+        ta = np.full(self.K, -1, dtype=np.int64)
+        ta[self.row] = np.arange(self.nterms)
+        ia = ta[other.row]
+        keep = ia >= 0
+        ia = ia[keep]
+        coef = self.coef[ia] * other.coef[keep]
+        F = -np.sort(-np.stack([self.f1[ia], self.f2[ia], other.f1[keep], other.f2[keep]], axis=1), axis=1)
+        assert not F.size or np.all(F[:, 2] == NONE), "product exceeds two factors per term"
+        return SymVec(self.K, other.row[keep], coef, F[:, 0], F[:, 1])
+
     # ---- clean-up -----------------------------------------------------------
     def drop_zero_constants(self):
         """Remove constant terms that are exactly zero (e.g. the `- 0` right-hand side that

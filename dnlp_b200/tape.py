@@ -16,6 +16,13 @@ Instruction kinds (the C-ABI mirrors these as plain structs, include/dnlp_b200.h
          scattered through ``pos``.
   GEMV   dst[i] = alpha * sum_j Q[i, j] * V[x0 + j]        dense constant Q (quad_form)
   SCALE  dst[pos[k]] = V[s] * coef[k]                      one slot times a constant vector
+  SPMVJ  g[pos?[k]] = sum_t coef[t] * V[f1[t]]   and   jac[qpos[t]] = coef[t] * V[f1[t] + 1]
+         the constraint value A @ phi(x) and its Jacobian fill A o phi'(x) in ONE pass over A:
+         phi and phi' live interleaved (value at an even slot, derivative right after it), so one
+         16-byte gather serves both (only in the union program; compiler.fuse_spmv_jacobian)
+
+ELEM may write with ``dst_stride`` 2 (the interleaved value / derivative pairs) and multiplies its
+result by ``post_scale`` (p * x^(p-1) as one derivative value).
 
 Each callback (f, grad, g, jac, hess) owns a *program*: the topologically ordered
 ids of the instructions it needs.  Instructions that depend only on x are cached
@@ -55,7 +62,7 @@ UNARY_TABLE = {
 DST_V, DST_F, DST_GRAD, DST_G, DST_JAC, DST_HESS = 0, 1, 2, 3, 4, 5
 OUT_NAMES = {DST_F: "f", DST_GRAD: "grad", DST_G: "g", DST_JAC: "jac", DST_HESS: "hess"}
 
-K_ELEM, K_POLY, K_GEMV, K_SCALE = 1, 2, 3, 4
+K_ELEM, K_POLY, K_GEMV, K_SCALE, K_SPMVJ = 1, 2, 3, 4, 5
 
 # what an instruction's result depends on (transitively): the point, the objective factor, the duals
 DEP_X, DEP_SIGMA, DEP_LAMBDA = 1, 2, 4
@@ -67,7 +74,8 @@ class Instr:
                  "a_off", "a_stride", "b_off", "b_stride",
                  "ptr", "coef", "f1", "f2", "pos", "accumulate",
                  "Q", "x_off", "ncols", "alpha", "s_slot",
-                 "deps", "uses_lam", "dep_mask", "id", "level")
+                 "deps", "uses_lam", "dep_mask", "id", "level",
+                 "dst_stride", "post_scale", "qpos", "fused_jac", "panel_prev")
 
     def __init__(self, kind, **kw):
         self.kind = kind
@@ -89,6 +97,11 @@ class Instr:
         self.dep_mask = 0           # DEP_X | DEP_SIGMA | DEP_LAMBDA, transitive over the instructions it reads
         self.id = -1
         self.level = 0
+        self.dst_stride = 1         # ELEM: distance between consecutive outputs (2 = interleaved pair layout)
+        self.post_scale = 1.0       # ELEM: result multiplier
+        self.qpos = None            # SPMVJ: Jacobian position of every term (-1 = none)
+        self.fused_jac = None       # SPMVJ: (id of the POLY it replaces for g, id of the Jacobian fill)
+        self.panel_prev = None      # POLY: id of the previous column-panel pass over the same rows (this one accumulates)
         for k, v in kw.items():
             setattr(self, k, v)
 
@@ -98,6 +111,13 @@ class Instr:
             n_in = (self.count if self.a_stride else 1) + \
                 ((self.count if self.b_stride else 1) if self.fcode in BINARY_CODES else 0)
             return 8 * (n_in + self.count)
+        if self.kind == K_SPMVJ:
+            nt = int(self.coef.size)
+            span = int(self.f1.max()) - int(self.f1[self.f1 >= 0].min()) + 2 if nt else 0
+            lens = np.diff(self.ptr)
+            uniform = lens.size > 0 and bool(np.all(lens == lens[0]))
+            return (16 * nt + 8 * nt + 8 * min(2 * nt, span) + (0 if uniform else 8 * (self.count + 1))
+                    + 8 * self.count)
         if self.kind == K_POLY:
             nt = int(self.coef.size)
             has_f2 = bool(np.any(self.f2 >= 0))

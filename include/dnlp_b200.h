@@ -37,7 +37,7 @@ extern "C" {
 typedef struct dnlp_oracle dnlp_oracle;
 
 /* instruction kinds */
-enum { DNLP_ELEM = 1, DNLP_POLY = 2, DNLP_GEMV = 3, DNLP_SCALE = 4 };
+enum { DNLP_ELEM = 1, DNLP_POLY = 2, DNLP_GEMV = 3, DNLP_SCALE = 4, DNLP_SPMVJ = 5 };
 /* destinations: the value buffer V or one of the five outputs */
 enum { DNLP_DST_V = 0, DNLP_DST_F = 1, DNLP_DST_GRAD = 2, DNLP_DST_G = 3, DNLP_DST_JAC = 4, DNLP_DST_HESS = 5 };
 /* programs */
@@ -80,6 +80,14 @@ typedef struct {
    * instructions become parallel branches of the CUDA graph that replays a launch sequence. */
   const int32_t *deps;
   int64_t n_deps;
+  /* ELEM: dst[k * dst_stride] = post_scale * F(...).  dst_stride 2 = the interleaved (value, derivative)
+   * pair layout that SPMVJ gathers with one 16-byte load. */
+  int32_t dst_stride;
+  int32_t reserved0;
+  double post_scale;
+  /* SPMVJ (fused constraint value + Jacobian fill; ptr / coef / f1 / pos as for POLY, f1 even slots):
+   *   G[pos?[k]] = sum_t coef[t] * V[f1[t]],   JAC[qpos[t]] = coef[t] * V[f1[t] + 1]   (qpos -1 = skip) */
+  const int32_t *qpos;    /* nterms */
 } dnlp_instr_desc;
 
 typedef struct {
@@ -102,6 +110,7 @@ typedef struct {
 
 int dnlp_device_count(void);
 const char *dnlp_version(void);
+int dnlp_device_synchronize(int device);       /* cudaDeviceSynchronize on `device` (timing brackets of callers) */
 
 int dnlp_create(const dnlp_tape_desc *tape, int device, dnlp_oracle **out);
 void dnlp_destroy(dnlp_oracle *o);

@@ -69,6 +69,21 @@ class TapeInterp:
                 a = V[ins.a_off + k * ins.a_stride]
                 bb = V[ins.b_off + k * ins.b_stride]
                 res = _f(ins.fcode, a, bb, ins.param)
+                if ins.post_scale != 1.0:
+                    res = ins.post_scale * res
+                if ins.dst_stride != 1:
+                    assert ins.dst_space == T.DST_V
+                    V[ins.dst_off + ins.dst_stride * k] = res
+                    continue
+            elif ins.kind == T.K_SPMVJ:
+                m1 = ins.f1 >= 0
+                term = ins.coef.copy()
+                term[m1] = term[m1] * V[ins.f1[m1]]
+                rows = np.repeat(np.arange(ins.count), np.diff(ins.ptr))
+                res = np.zeros(ins.count)
+                np.add.at(res, rows, term)
+                q = ins.qpos >= 0
+                outs[T.DST_JAC][ins.qpos[q]] = ins.coef[q] * V[ins.f1[q] + 1]
             elif ins.kind == T.K_POLY:
                 with np.errstate(all="ignore"):
                     term = ins.coef.copy()

@@ -580,3 +580,45 @@ def test_gpu_sigma_only_hessian_entries_are_kept_between_calls(name, layered, gp
             assert k1 - k0 == 2 and k2 - k1 >= 2, (k0, k1, k2)
     finally:
         o.close()
+
+
+@pytest.mark.parametrize("flat", [True, False])
+def test_gpu_fused_spmv_jacobian(flat, gpu_mod, monkeypatch):
+    """SPMVJ: g = A phi(x) and J = A o phi'(x) in one pass over A with 16-byte pair gathers (the union
+    program), against the CPU oracle; per-callback programs (plain SpMV / Jacobian fill on the strided pair
+    slots) too.  Both the chunked warp kernel and the row fallback."""
+    from dnlp_b200 import tape as T
+    from dnlp_b200 import workloads as W
+    from dnlp_b200.rules import Builder
+    monkeypatch.setattr(Builder, "PAIRING", True)        # off by default (measured slower at the C5 size)
+    monkeypatch.setattr(Builder, "PAIR_MIN_NNZ", 1)
+    monkeypatch.setenv("DNLP_FLAT_MIN_TERMS", "1" if flat else str(1 << 40))
+    monkeypatch.setenv("DNLP_BATCH_SPLIT", "3000")
+    A, x0 = W.microbench_data(40000, 15313, 7, seed=3)
+    prob = W.microbench(A, x0)
+    ref = RefOracles(prob)
+    ref.jacobianstructure(), ref.hessianstructure()
+    o = gpu_mod(prob)
+    try:
+        fused = [i for i in o.tape.instrs if i.kind == T.K_SPMVJ]
+        assert len(fused) == 1
+        rng = np.random.default_rng(2)
+        for it in range(2):
+            x = prob.x0 * (1 + 0.01 * rng.standard_normal(prob.n))
+            lam = rng.standard_normal(prob.m)
+            res = o.eval_all(x, lam, 0.8)                       # union program: the fused instruction
+            assert_close(res["f"], ref.objective(x), "f")
+            assert_close(res["grad"], ref.gradient(x), "grad")
+            assert_close(res["g"], ref.constraints(x), "g", atol=1e-11)
+            assert_close(res["jac"], ref.jacobian(x), "jac")
+            assert_close(res["hess"], ref.hessian(x, lam, 0.8), "hess")
+            assert_close(o.constraints(x), ref.constraints(x), "g alone", atol=1e-11)
+            assert_close(o.jacobian(x), ref.jacobian(x), "jac alone")
+        assert o.instr_kernel(fused[0].id) == ("spmvj_flat_kernel<0>" if flat else "spmvj_rows_kernel") or \
+            o.instr_kernel(fused[0].id).startswith("spmvj_flat_kernel")
+        o.upload_point(x, lam, 0.8)
+        assert o.run_device(iters=2) > 0
+        assert_close(o.read_output("jac"), ref.jacobian(x), "jac after device loop")
+        assert_close(o.read_output("g"), ref.constraints(x), "g after device loop", atol=1e-11)
+    finally:
+        o.close()

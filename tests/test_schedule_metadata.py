@@ -28,6 +28,9 @@ def _read_slots(ins):
     if ins.kind == T.K_POLY:
         s = np.concatenate([ins.f1, ins.f2])
         return np.unique(s[s >= 0])
+    if ins.kind == T.K_SPMVJ:
+        s = np.concatenate([ins.f1, ins.f1[ins.qpos >= 0] + 1])
+        return np.unique(s[s >= 0])
     if ins.kind == T.K_GEMV:
         return np.arange(ins.x_off, ins.x_off + ins.ncols)
     if ins.kind == T.K_SCALE:
@@ -50,8 +53,10 @@ def _derive(tape):
         deps.append(d)
         masks.append(mk)
         if ins.dst_space == T.DST_V:
-            assert np.all(producer[ins.dst_off:ins.dst_off + ins.count] == -1), "a V range is written twice"
-            producer[ins.dst_off:ins.dst_off + ins.count] = ins.id
+            st = getattr(ins, "dst_stride", 1) if ins.kind == T.K_ELEM else 1
+            w = ins.dst_off + st * np.arange(ins.count)
+            assert np.all(producer[w] == -1), "a V slot is written twice"
+            producer[w] = ins.id
     # nothing reads a temporary before it is produced
     for ins in tape.instrs:
         slots = _read_slots(ins)
@@ -187,3 +192,17 @@ def test_sigma_only_hessian_entries(name):
     np.testing.assert_array_equal(b[const], a[const])
     np.testing.assert_array_equal(a[sig], b[sig])
     np.testing.assert_allclose(c[sig], 2.0 * b[sig], rtol=1e-15, atol=0)
+
+
+@pytest.mark.parametrize("name", ["c5_microbench_small", "matmul_with_atom_operand", "matmul_const_sides", "c5_lifted_small"])
+def test_metadata_with_interleaved_pairs_and_fused_instruction(name, monkeypatch):
+    """Pair regions have two writers (even slots: value, odd slots: derivative) and the fused SPMVJ
+    instruction reads both: deps / dep_mask must still be exactly what the operands say."""
+    from dnlp_b200.rules import Builder
+    monkeypatch.setattr(Builder, "PAIRING", True)        # off by default (measured slower at the C5 size)
+    monkeypatch.setattr(Builder, "PAIR_MIN_NNZ", 1)
+    tape = compile_problem(Golden(name).problem)
+    deps, masks = _derive(tape)
+    for ins in tape.instrs:
+        assert set(ins.deps) == deps[ins.id], "instr %d: deps %s, operands say %s" % (ins.id, ins.deps, deps[ins.id])
+        assert ins.dep_mask == masks[ins.id]

@@ -72,3 +72,99 @@ def test_distinct_columns_are_distinct():
     cols = W.distinct_columns(np.random.default_rng(3), 500, 40, 16)
     assert cols.shape == (500, 16)
     assert all(len(set(r)) == 16 for r in cols)
+
+
+# ---- fused constraint value + Jacobian fill (SPMVJ) and the interleaved pair layout ---------------------
+def _union(tape, x, lam, sigma):
+    """Run the union program with the NumPy interpreter; returns the five outputs."""
+    from dnlp_b200 import tape as T
+    it = TapeInterp(tape)
+    it.V[:tape.n] = x
+    it.V[tape.n] = sigma
+    it.V[tape.n + 1:tape.n + 1 + tape.m] = lam
+    outs = {T.DST_F: np.array([tape.f_const]), T.DST_GRAD: tape.grad_const.copy(), T.DST_G: tape.g_const.copy(),
+            T.DST_JAC: tape.jac_const.copy(), T.DST_HESS: tape.hess_const.copy()}
+    it._run(tape.programs["all"], outs)
+    return outs
+
+
+def test_spmv_jacobian_fusion_on_c5(monkeypatch):
+    """With the pairing threshold lowered the C5 fixture compiles to ONE fused instruction in the union
+    program (value slots even, derivative right after), the per-callback programs keep their own kernels,
+    and every program still reproduces the live reference."""
+    from dnlp_b200 import tape as T
+    from dnlp_b200.rules import Builder
+    monkeypatch.setattr(Builder, "PAIRING", True)        # off by default (measured slower at the C5 size)
+    monkeypatch.setattr(Builder, "PAIR_MIN_NNZ", 1)
+    g = Golden("c5_microbench_small")
+    tape = compile_problem(g.problem)
+    fused = [i for i in tape.instrs if i.kind == T.K_SPMVJ]
+    assert len(fused) == 1
+    F = fused[0]
+    assert F.id in tape.programs["all"] and F.id not in tape.programs["g"] and F.id not in tape.programs["jac"]
+    assert F.fused_jac[0] in tape.programs["g"] and F.fused_jac[1] in tape.programs["jac"]
+    assert F.fused_jac[0] not in tape.programs["all"] and F.fused_jac[1] not in tape.programs["all"]
+    assert np.all(F.f1[F.f1 >= 0] % 2 == 0)
+    assert np.array_equal(np.sort(F.qpos[F.qpos >= 0]), np.arange(tape.jac_rows.size))     # every entry exactly once
+    strided = [i for i in tape.instrs if i.kind == T.K_ELEM and i.dst_stride == 2]
+    assert len(strided) == 16 and any(i.post_scale != 1.0 for i in strided)                  # 8 atoms x (value, derivative)
+    np.testing.assert_array_equal(tape.jac_rows, g.jac_rows)
+    np.testing.assert_array_equal(tape.hess_cols, g.hess_cols)
+    it = TapeInterp(tape)
+    for p in g.points:
+        for name in ("f", "grad", "g", "jac"):
+            assert_close(it.eval(name, p["x"]), p[name], name)
+        assert_close(it.eval("hess", p["x"], p["lam"], float(p["sigma"])), p["hess"], "hess")
+        outs = _union(tape, p["x"], p["lam"], float(p["sigma"]))
+        for space, name in ((T.DST_F, "f"), (T.DST_GRAD, "grad"), (T.DST_G, "g"), (T.DST_JAC, "jac"), (T.DST_HESS, "hess")):
+            assert_close(outs[space], p[name], "union/" + name)
+
+
+def test_fusion_is_refused_when_it_would_be_wrong(monkeypatch):
+    """No pair candidates (atoms under a matmul with a NON-constant left operand, lifted forms, small
+    matrices) -> no fused instruction and no strided ELEM; problems with other constraint shapes keep
+    compiling exactly as before."""
+    from dnlp_b200 import tape as T
+    from dnlp_b200.rules import Builder
+    monkeypatch.setattr(Builder, "PAIRING", True)        # off by default (measured slower at the C5 size)
+    monkeypatch.setattr(Builder, "PAIR_MIN_NNZ", 1)
+    for name in ("c3_logistic_small", "c5_lifted_small", "matmul_with_atom_operand", "hs071", "clnlbeam"):
+        g = Golden(name)
+        tape = compile_problem(g.problem)
+        assert not any(i.kind == T.K_SPMVJ for i in tape.instrs) or name == "matmul_with_atom_operand"
+        it = TapeInterp(tape)
+        p = g.points[0]
+        outs = _union(tape, p["x"], p["lam"], float(p["sigma"]))
+        assert_close(outs[T.DST_JAC], p["jac"], name + " union/jac")
+        assert_close(outs[T.DST_G], p["g"], name + " union/g")
+        assert_close(it.eval("jac", p["x"]), p["jac"], name + " jac")
+
+
+def test_column_panels_split_and_accumulate(monkeypatch):
+    """SpMV-shaped outputs whose gathered slots span more than the L2 keeps are cut into column panels:
+    pass 1 writes the row sums, pass 2 adds its own (same rows, disjoint terms, every term exactly once)."""
+    from dnlp_b200 import tape as T
+    from dnlp_b200.rules import Builder
+    monkeypatch.setattr(Builder, "PANEL_MIN_TERMS", 8)
+    monkeypatch.setattr(Builder, "PANEL_SPAN_BYTES", 64)
+    for name in ("c5_microbench_small", "c3_logistic_small", "matmul_const_sides"):
+        g = Golden(name)
+        tape = compile_problem(g.problem)
+        acc = [i for i in tape.instrs if i.kind == T.K_POLY and i.accumulate]
+        if name == "c5_microbench_small":
+            assert acc, "no panel pass emitted"
+        for i in acc:
+            first = tape.instrs[i.panel_prev]
+            assert first.dst_space == i.dst_space != T.DST_V and first.count == i.count and not first.accumulate
+            assert first.id < i.id
+            for prog in tape.programs.values():
+                assert (i.id in prog) == (first.id in prog)
+            lo = i.f1[i.f1 >= 0].min()
+            assert first.f1.max() < lo                       # disjoint slot ranges
+        it = TapeInterp(tape)
+        for p in g.points:
+            assert_close(it.eval("g", p["x"]), p["g"], name + " g")
+            assert_close(it.eval("jac", p["x"]), p["jac"], name + " jac")
+            assert_close(it.eval("hess", p["x"], p["lam"], float(p["sigma"])), p["hess"], name + " hess")
+            outs = _union(tape, p["x"], p["lam"], float(p["sigma"]))
+            assert_close(outs[T.DST_G], p["g"], name + " union/g")
