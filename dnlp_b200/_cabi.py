@@ -51,13 +51,13 @@ EXPORTS = [
     "dnlp_device_count", "dnlp_version", "dnlp_device_synchronize", "dnlp_create", "dnlp_destroy", "dnlp_last_error",
     "dnlp_eval_f", "dnlp_eval_grad", "dnlp_eval_g", "dnlp_eval_jac", "dnlp_eval_hess", "dnlp_eval_all",
     "dnlp_host_alloc", "dnlp_host_free", "dnlp_upload_point", "dnlp_run_device", "dnlp_profile_instrs",
-    "dnlp_read_output", "dnlp_kernel_launches", "dnlp_set_cache", "dnlp_set_graphs", "dnlp_set_parallel", "dnlp_set_windows", "dnlp_set_dynamic", "dnlp_eval_dyn", "dnlp_instr_kernel", "dnlp_run", "dnlp_output_ptr",
+    "dnlp_read_output", "dnlp_kernel_launches", "dnlp_set_cache", "dnlp_set_graphs", "dnlp_set_parallel", "dnlp_set_windows", "dnlp_set_dynamic", "dnlp_eval_dyn", "dnlp_bind_outputs", "dnlp_instr_kernel", "dnlp_run", "dnlp_output_ptr",
     "dnlp_batch_create", "dnlp_batch_destroy", "dnlp_batch_last_error", "dnlp_batch_eval", "dnlp_batch_upload",
     "dnlp_batch_run_device", "dnlp_batch_profile_instrs", "dnlp_batch_kernel_launches",
     "dnlp_comm_unique_id", "dnlp_comm_create", "dnlp_comm_destroy", "dnlp_comm_last_error", "dnlp_comm_has_nccl",
     "dnlp_comm_ipc_handle", "dnlp_comm_open_peers", "dnlp_comm_allreduce_host",
     "dnlp_shard_create", "dnlp_shard_destroy", "dnlp_shard_last_error", "dnlp_shard_set_output",
-    "dnlp_shard_root_handles", "dnlp_shard_open_root", "dnlp_shard_eval", "dnlp_shard_run_device",
+    "dnlp_shard_root_handles", "dnlp_shard_open_root", "dnlp_shard_eval", "dnlp_shard_run_device", "dnlp_shard_set_layout",
 ]
 
 _lib = None
@@ -72,6 +72,9 @@ def lib():
         raise RuntimeError(
             "dnlp_b200: %s is missing - build it with `python -m dnlp_b200.build` "
             "(there is no CPU fallback for the oracle)" % LIB_PATH)
+    if int(os.environ.get("LOCAL_WORLD_SIZE", "1")) > 1:
+        # several ranks share the host cores: idle staging threads must sleep, not spin (read by libgomp at load time)
+        os.environ.setdefault("OMP_WAIT_POLICY", "passive")
     L = C.CDLL(LIB_PATH)
     vp = C.c_void_p
     L.dnlp_device_count.restype = C.c_int
@@ -107,6 +110,7 @@ def lib():
     L.dnlp_output_ptr.restype = vp
     L.dnlp_instr_kernel.argtypes = [vp, C.c_int32]
     L.dnlp_instr_kernel.restype = C.c_char_p
+    L.dnlp_bind_outputs.argtypes = [vp, c_f64p, c_f64p, c_f64p, c_f64p, C.c_int32]
     L.dnlp_set_dynamic.argtypes = [vp, C.c_int32, c_i32p, C.c_int64]
     L.dnlp_eval_dyn.argtypes = [vp, C.c_int32, c_f64p, c_f64p, C.c_double, c_f64p]
     L.dnlp_batch_create.argtypes = [C.POINTER(TapeDesc), C.c_int, C.c_int32, C.POINTER(vp)]
@@ -140,6 +144,7 @@ def lib():
                                         C.c_int64, c_f64p, C.c_int64, c_i32p]
     L.dnlp_shard_root_handles.argtypes = [vp, cp]
     L.dnlp_shard_open_root.argtypes = [vp, cp]
+    L.dnlp_shard_set_layout.argtypes = [vp, C.c_int32, c_i64p, c_i64p, C.c_int32, c_i64p, c_i64p]
     L.dnlp_shard_eval.argtypes = [vp, C.c_int32, c_f64p, c_f64p, C.c_double, c_f64p]
     L.dnlp_shard_run_device.argtypes = [vp, C.c_int32, C.c_int32, c_f32p]
     _lib = L

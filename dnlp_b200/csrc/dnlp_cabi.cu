@@ -503,10 +503,18 @@ static bool stage_point(double *dst, const double *src, int64_t n, bool have_old
   }
   // OpenMP keeps its worker threads alive between calls (spawning std::threads cost more than the
   // copy itself for 16 MB points)
-  unsigned hw = std::thread::hardware_concurrency();
-  // measured on the GPU box (16 cores, tools/hostcmp_bench.c): comparing 16 MB takes 0.17 ms with 8
-  // threads, 0.11 ms with 12, 0.09 ms with 16; 12 leaves cores for the caller's own threads
-  const int T = (int)(hw >= 16 ? 12 : (hw >= 4 ? hw / 2 : 1));
+  // threads: measured on the GPU box (16 cores, tools/hostcmp_bench.c) comparing 16 MB takes 0.17 ms with 8
+  // threads, 0.11 ms with 12, 0.09 ms with 16.  One process per GPU shares the host cores: every rank takes
+  // its share (LOCAL_WORLD_SIZE), or the spinning OpenMP teams of the ranks oversubscribe the cores (2 ranks x
+  // 14 threads on 24 cores made a callback 6 ms instead of 0.5 ms).
+  static const int T = [] {
+    unsigned hw = std::thread::hardware_concurrency();
+    int ranks = 1;
+    if (const char *e = getenv("LOCAL_WORLD_SIZE")) ranks = atoi(e) > 0 ? atoi(e) : 1;
+    if (const char *e = getenv("DNLP_STAGE_THREADS")) return atoi(e) > 0 ? atoi(e) : 1;
+    int t = (int)(hw / (unsigned)ranks) - (ranks > 1 ? 1 : 2);
+    return t < 1 ? 1 : (t > 14 ? 14 : t);
+  }();
   const int64_t chunk = (n + T - 1) / T;
   int any = 0;
 #pragma omp parallel for num_threads(T) schedule(static, 1) reduction(| : any)
@@ -521,29 +529,83 @@ static bool stage_point(double *dst, const double *src, int64_t n, bool have_old
   return any != 0;
 }
 
+// Stage `count` doubles into the pinned mirror `hmir` of the device range `dev` and upload what changed.
+// Large vectors go in 4 MB pieces: the H2D copy of a piece runs while the host threads stage the next one,
+// and a piece that compares equal to the mirror is not uploaded at all (the mirror IS the device content).
+// Returns whether anything changed.
+static int stage_and_upload(double *hmir, double *dev, const double *src, int64_t count, bool have_old,
+                            cudaStream_t stream, bool *changed, std::string &err) {
+  *changed = false;
+  constexpr int64_t PIECE = (4 << 20) / sizeof(double);
+  for (int64_t lo = 0; lo < count; lo += PIECE) {
+    const int64_t len = count - lo < PIECE ? count - lo : PIECE;
+    if (stage_point(hmir + lo, src + lo, len, have_old)) {
+      CK(cudaMemcpyAsync(dev + lo, hmir + lo, (size_t)len * sizeof(double), cudaMemcpyHostToDevice, stream));
+      *changed = true;
+    }
+  }
+  return 0;
+}
+
 int dnlp_oracle::put_x(const double *x) {
-  const size_t bytes = (size_t)n * sizeof(double);
-  const bool changed = stage_point(hx, x, n, have_last_x && cache_enabled);
+  bool changed = false;
+  if (stage_and_upload(hx, V, x, n, have_last_x && cache_enabled, stream, &changed, err)) return 1;
   if (!changed && have_last_x && cache_enabled) return 0;
-  if (n > 0) CK(cudaMemcpyAsync(V, hx, bytes, cudaMemcpyHostToDevice, stream));
   invalidate(1);
   have_last_x = true;
+  ++x_epoch;
   return 0;
 }
 
 int dnlp_oracle::put_lam(const double *lam, double sigma) {
-  // sigma and lambda are adjacent in V: [n] = sigma, [n+1, n+1+m) = lambda; staged (multi-threaded
-  // for large m) into one pinned buffer and uploaded with a single copy, skipped when unchanged
-  bool changed = !have_last_lam || hlam[0] != sigma;
-  if (changed) invalidate(2);
-  hlam[0] = sigma;
-  if (m > 0) {
-    const bool lam_changed = stage_point(hlam + 1, lam, m, have_last_lam);
-    if (lam_changed) invalidate(4);
-    changed = lam_changed || changed;
+  // sigma and lambda are adjacent in V: [n] = sigma, [n+1, n+1+m) = lambda
+  if (!have_last_lam || hlam[0] != sigma) {
+    invalidate(2);
+    hlam[0] = sigma;
+    CK(cudaMemcpyAsync(V + n, hlam, sizeof(double), cudaMemcpyHostToDevice, stream));
   }
-  if (!changed) return 0;
-  CK(cudaMemcpyAsync(V + n, hlam, (size_t)(m + 1) * sizeof(double), cudaMemcpyHostToDevice, stream));
+  if (m > 0) {
+    bool lam_changed = false;
+    if (stage_and_upload(hlam + 1, V + n + 1, lam, m, have_last_lam, stream, &lam_changed, err)) return 1;
+    if (lam_changed) invalidate(4);
+  }
+  have_last_lam = true;
+  return 0;
+}
+
+int dnlp_oracle::put_x_runs(const double *xg, const std::vector<int64_t> &src, const std::vector<int64_t> &len) {
+  bool any = false;
+  int64_t off = 0;
+  for (size_t r = 0; r < src.size(); ++r) {
+    bool ch = false;
+    if (stage_and_upload(hx + off, V + off, xg + src[r], len[r], have_last_x && cache_enabled, stream, &ch, err)) return 1;
+    any = any || ch;
+    off += len[r];
+  }
+  if (off != n) { err = "variable runs do not cover the local point"; return 1; }
+  if (!any && have_last_x && cache_enabled) return 0;
+  invalidate(1);
+  have_last_x = true;
+  ++x_epoch;
+  return 0;
+}
+
+int dnlp_oracle::put_lam_runs(const double *lg, double sigma, const std::vector<int64_t> &src, const std::vector<int64_t> &len) {
+  if (!have_last_lam || hlam[0] != sigma) {
+    invalidate(2);
+    hlam[0] = sigma;
+    CK(cudaMemcpyAsync(V + n, hlam, sizeof(double), cudaMemcpyHostToDevice, stream));
+  }
+  int64_t off = 0;
+  bool any = false;
+  for (size_t r = 0; r < src.size(); ++r) {
+    bool ch = false;
+    if (stage_and_upload(hlam + 1 + off, V + n + 1 + off, lg + src[r], len[r], have_last_lam, stream, &ch, err)) return 1;
+    any = any || ch;
+    off += len[r];
+  }
+  if (off != m) { err = "constraint runs do not cover the local multipliers"; return 1; }
+  if (any) invalidate(4);
   have_last_lam = true;
   return 0;
 }
@@ -551,6 +613,46 @@ int dnlp_oracle::put_lam(const double *lam, double sigma) {
 int dnlp_oracle::fetch(int space, double *host) {
   if (host == nullptr || out_len[space] == 0) return 0;
   CK(cudaMemcpyAsync(host, out[space], (size_t)out_len[space] * sizeof(double), cudaMemcpyDeviceToHost, stream));
+  return 0;
+}
+
+// All x-only outputs at once + their D2H on the copy stream (see dnlp_engine.h, dnlp_bind_outputs).
+int dnlp_oracle::launch_eager() {
+  // the device outputs must not be overwritten while an earlier eager copy still reads them
+  CK(cudaStreamWaitEvent(stream, ev_copied, 0));
+  const int progs[4] = {DNLP_PROG_F, DNLP_PROG_GRAD, DNLP_PROG_G, DNLP_PROG_JAC};
+  if (run_programs(progs, 4, false)) return 1;
+  for (int s = DNLP_DST_GRAD; s <= DNLP_DST_JAC; ++s)
+    if (bound[s] && dyn_len[s] > 0) {
+      dnlp::gather_kernel<<<grid_for(dyn_len[s], 1), 256, 0, stream>>>(out[s], dyn_pos[s], dyn_buf[s], dyn_len[s]);
+      ++launches;
+    }
+  CK(cudaEventRecord(ev_ready, stream));
+  CK(cudaStreamWaitEvent(cstream, ev_ready, 0));
+  for (int s = DNLP_DST_F; s <= DNLP_DST_JAC; ++s) {
+    if (!bound[s]) continue;
+    const bool dyn = s != DNLP_DST_F && dyn_len[s] > 0;
+    const int64_t cnt = dyn ? dyn_len[s] : out_len[s];
+    if (cnt > 0)
+      CK(cudaMemcpyAsync(bound[s], dyn ? dyn_buf[s] : out[s], (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, cstream));
+    CK(cudaEventRecord(ev_out[s], cstream));
+  }
+  CK(cudaEventRecord(ev_copied, cstream));
+  eager_epoch = x_epoch;
+  return 0;
+}
+
+// One x-only callback: the eager path when the caller's buffer is the bound one, else compute + copy.
+int dnlp_oracle::deliver(int space, int prog, double *host_out) {
+  if (eager && cache_enabled && host_out != nullptr && bound[space] == host_out) {
+    if (eager_epoch != x_epoch && launch_eager()) return 1;
+    CK(cudaEventSynchronize(ev_out[space]));
+    return 0;
+  }
+  if (eager) CK(cudaStreamWaitEvent(stream, ev_copied, 0));   // an eager copy may still be reading the outputs
+  if (run_program(prog, false)) return 1;
+  if (fetch(space, host_out)) return 1;
+  CK(cudaStreamSynchronize(stream));
   return 0;
 }
 
@@ -582,8 +684,13 @@ void dnlp_destroy(dnlp_oracle *o) {
   for (void *p : o->owned) cudaFree(p);
   if (o->hx) cudaFreeHost(o->hx);
   if (o->hlam) cudaFreeHost(o->hlam);
+  if (o->cstream) cudaStreamSynchronize(o->cstream);
   if (o->ev0) cudaEventDestroy(o->ev0);
   if (o->ev1) cudaEventDestroy(o->ev1);
+  if (o->ev_ready) cudaEventDestroy(o->ev_ready);
+  if (o->ev_copied) cudaEventDestroy(o->ev_copied);
+  for (int s2 = 0; s2 < 6; ++s2) if (o->ev_out[s2]) cudaEventDestroy(o->ev_out[s2]);
+  if (o->cstream) cudaStreamDestroy(o->cstream);
   for (cudaEvent_t e : o->ev_pool) cudaEventDestroy(e);
   for (int l = 1; l < dnlp_oracle::NLANE; ++l) if (o->lane[l]) cudaStreamDestroy(o->lane[l]);
   if (o->stream) cudaStreamDestroy(o->stream);
@@ -599,6 +706,10 @@ static int create_impl(dnlp_oracle *o, const dnlp_tape_desc *t) {
   CK(cudaStreamCreateWithFlags(&o->stream, cudaStreamNonBlocking));
   CK(cudaEventCreate(&o->ev0));
   CK(cudaEventCreate(&o->ev1));
+  CK(cudaStreamCreateWithFlags(&o->cstream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&o->ev_ready, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&o->ev_copied, cudaEventDisableTiming));
+  for (int s2 = 0; s2 < 6; ++s2) CK(cudaEventCreateWithFlags(&o->ev_out[s2], cudaEventDisableTiming));
   o->n = t->n; o->m = t->m; o->nslots = t->nslots; o->nnz_jac = t->nnz_jac; o->nnz_hess = t->nnz_hess;
   if (const char *e = getenv("DNLP_WIN_MIN_TERMS")) o->win_min_terms = atoll(e);   // tests: force the window path
   if (const char *e = getenv("DNLP_NO_SIGMA_CACHE")) o->sigma_cache_enabled = atoi(e) == 0;
@@ -813,29 +924,25 @@ int dnlp_create(const dnlp_tape_desc *t, int device, dnlp_oracle **out) {
 
 int dnlp_eval_f(dnlp_oracle *o, const double *x, double *f) {
   ENTER(o);
-  if (o->put_x(x) || o->run_program(DNLP_PROG_F, false) || o->fetch(DNLP_DST_F, f)) return 1;
-  CK(cudaStreamSynchronize(o->stream));
+  if (o->put_x(x) || o->deliver(DNLP_DST_F, DNLP_PROG_F, f)) return 1;
   return 0;
 }
 
 int dnlp_eval_grad(dnlp_oracle *o, const double *x, double *grad) {
   ENTER(o);
-  if (o->put_x(x) || o->run_program(DNLP_PROG_GRAD, false) || o->fetch(DNLP_DST_GRAD, grad)) return 1;
-  CK(cudaStreamSynchronize(o->stream));
+  if (o->put_x(x) || o->deliver(DNLP_DST_GRAD, DNLP_PROG_GRAD, grad)) return 1;
   return 0;
 }
 
 int dnlp_eval_g(dnlp_oracle *o, const double *x, double *g) {
   ENTER(o);
-  if (o->put_x(x) || o->run_program(DNLP_PROG_G, false) || o->fetch(DNLP_DST_G, g)) return 1;
-  CK(cudaStreamSynchronize(o->stream));
+  if (o->put_x(x) || o->deliver(DNLP_DST_G, DNLP_PROG_G, g)) return 1;
   return 0;
 }
 
 int dnlp_eval_jac(dnlp_oracle *o, const double *x, double *vals) {
   ENTER(o);
-  if (o->put_x(x) || o->run_program(DNLP_PROG_JAC, false) || o->fetch(DNLP_DST_JAC, vals)) return 1;
-  CK(cudaStreamSynchronize(o->stream));
+  if (o->put_x(x) || o->deliver(DNLP_DST_JAC, DNLP_PROG_JAC, vals)) return 1;
   return 0;
 }
 
@@ -850,10 +957,20 @@ int dnlp_eval_hess(dnlp_oracle *o, const double *x, const double *lam, double si
 int dnlp_eval_all(dnlp_oracle *o, const double *x, const double *lam, double sigma,
                   double *f, double *grad, double *g, double *jac, double *hess) {
   ENTER(o);
+  if (o->eager) CK(cudaStreamWaitEvent(o->stream, o->ev_copied, 0));
   if (o->put_x(x) || o->put_lam(lam, sigma) || o->run_program(DNLP_PROG_ALL, false)) return 1;
   if (o->fetch(DNLP_DST_F, f) || o->fetch(DNLP_DST_GRAD, grad) || o->fetch(DNLP_DST_G, g) ||
       o->fetch(DNLP_DST_JAC, jac) || o->fetch(DNLP_DST_HESS, hess)) return 1;
   CK(cudaStreamSynchronize(o->stream));
+  return 0;
+}
+
+int dnlp_bind_outputs(dnlp_oracle *o, double *f, double *grad, double *g, double *jac, int32_t eager) {
+  ENTER(o);
+  CK(cudaStreamSynchronize(o->cstream));
+  o->bound[DNLP_DST_F] = f; o->bound[DNLP_DST_GRAD] = grad; o->bound[DNLP_DST_G] = g; o->bound[DNLP_DST_JAC] = jac;
+  o->eager = eager != 0;
+  o->eager_epoch = ~0ull;
   return 0;
 }
 
@@ -877,6 +994,13 @@ int dnlp_eval_dyn(dnlp_oracle *o, int32_t prog, const double *x, const double *l
   if (prog < DNLP_PROG_GRAD || prog > DNLP_PROG_HESS) { err = "bad program id"; return 1; }
   const int space = prog + 1;          // program i writes output i + 1
   if (o->put_x(x)) return 1;
+  if (prog != DNLP_PROG_HESS && o->eager && o->cache_enabled && compact != nullptr && o->bound[space] == compact &&
+      o->dyn_len[space] > 0) {
+    if (o->eager_epoch != o->x_epoch && o->launch_eager()) return 1;
+    CK(cudaEventSynchronize(o->ev_out[space]));
+    return 0;
+  }
+  if (o->eager) CK(cudaStreamWaitEvent(o->stream, o->ev_copied, 0));
   if (prog == DNLP_PROG_HESS && o->put_lam(lam, sigma)) return 1;
   if (o->run_program(prog, false)) return 1;
   const int64_t cnt = o->dyn_len[space];
@@ -892,6 +1016,7 @@ int dnlp_eval_dyn(dnlp_oracle *o, int32_t prog, const double *x, const double *l
 
 int dnlp_run(dnlp_oracle *o, int32_t prog, const double *x, const double *lam, double sigma) {
   ENTER(o);
+  if (o->cstream) CK(cudaStreamSynchronize(o->cstream));
   if (prog < 0 || prog >= DNLP_NPROG) { err = "bad program id"; return 1; }
   if (o->put_x(x)) return 1;
   if ((prog == DNLP_PROG_HESS || prog == DNLP_PROG_ALL) && o->put_lam(lam, sigma)) return 1;
@@ -926,6 +1051,7 @@ int dnlp_upload_point(dnlp_oracle *o, const double *x, const double *lam, double
 
 int dnlp_run_device(dnlp_oracle *o, int32_t prog_mask, int32_t iters, float *elapsed_ms) {
   ENTER(o);
+  if (o->cstream) CK(cudaStreamSynchronize(o->cstream));
   // one step = every cache invalidated, then the requested programs; the whole step is captured
   // once into a CUDA graph and replayed `iters` times
   int progs[DNLP_NPROG], nprogs = 0;
@@ -970,6 +1096,7 @@ int dnlp_run_device(dnlp_oracle *o, int32_t prog_mask, int32_t iters, float *ela
 
 int dnlp_profile_instrs(dnlp_oracle *o, int32_t p, int32_t iters, float *ms_per_instr) {
   ENTER(o);
+  if (o->cstream) CK(cudaStreamSynchronize(o->cstream));
   if (p < 0 || p >= DNLP_NPROG) { err = "bad program id"; return 1; }
   const size_t ni = o->instrs.size();
   for (size_t i = 0; i < ni; ++i) ms_per_instr[i] = 0.f;
@@ -996,6 +1123,7 @@ int dnlp_profile_instrs(dnlp_oracle *o, int32_t p, int32_t iters, float *ms_per_
 
 int dnlp_read_output(dnlp_oracle *o, int32_t space, double *out) {
   ENTER(o);
+  if (o->cstream) CK(cudaStreamSynchronize(o->cstream));
   if (space < 1 || space > 5) { err = "bad output id"; return 1; }
   if (o->fetch(space, out)) return 1;
   CK(cudaStreamSynchronize(o->stream));

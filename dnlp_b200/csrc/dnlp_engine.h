@@ -83,6 +83,17 @@ struct dnlp_oracle {
   int64_t launches = 0;
   std::string err;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // ---- eager delivery (dnlp_bind_outputs): at a NEW x every x-only output (f, grad, g, J) is computed at once
+  // and copied to the caller's pinned arrays on a second stream, so the D2H of the gradient / constraints /
+  // Jacobian overlaps the solver's next callbacks, the host-side staging of lambda and its H2D (PCIe is full
+  // duplex); a later callback at the same x only waits for its event.
+  cudaStream_t cstream = nullptr;
+  cudaEvent_t ev_ready = nullptr, ev_copied = nullptr, ev_out[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  double *bound[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool eager = false;
+  uint64_t x_epoch = 0, eager_epoch = ~0ull;
+  int launch_eager();
+  int deliver(int space, int prog, double *host_out);
   // CUDA graphs of the launch sequences actually encountered: key = (program, which of its cacheable
   // instructions are already valid).  IPOPT's call order produces a handful of distinct sequences;
   // replaying them as graphs removes the per-kernel launch gaps that dominate small problems.
@@ -171,6 +182,10 @@ struct dnlp_oracle {
   cudaEvent_t event_at(size_t i);
   int put_x(const double *x);
   int put_lam(const double *lam, double sigma);
+  // the same from a GLOBAL vector of which this oracle sees a few contiguous runs (row-sharded evaluation):
+  // run r = global[src[r] .. src[r] + len[r]) -> consecutive local positions
+  int put_x_runs(const double *xg, const std::vector<int64_t> &src, const std::vector<int64_t> &len);
+  int put_lam_runs(const double *lg, double sigma, const std::vector<int64_t> &src, const std::vector<int64_t> &len);
   int fetch(int space, double *host);
 };
 

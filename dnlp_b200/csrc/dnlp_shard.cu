@@ -228,6 +228,7 @@ struct dnlp_shard {
   int allreduce_mode = 0;             // 0 auto (P2P up to P2P_MAX, NCCL above), 1 force NCCL, 2 force P2P
   std::vector<void *> owned;
   std::vector<void *> opened;         // IPC mappings to close
+  std::vector<int64_t> xsrc, xlen, lsrc, llen;   // runs of the global x / lambda this rank sees (dnlp_shard_set_layout)
   std::string err;
 
   template <typename T>
@@ -516,6 +517,20 @@ int dnlp_shard_open_root(dnlp_shard *s, const char *handles384) {
   return 0;
 }
 
+// After this call dnlp_shard_eval takes the GLOBAL x and lambda: run r of the local point is
+// global[src[r] .. src[r] + len[r]) (a shard sees a few long ranges of the global vectors).
+int dnlp_shard_set_layout(dnlp_shard *s, int32_t n_xruns, const int64_t *xsrc, const int64_t *xlen,
+                          int32_t n_lruns, const int64_t *lsrc, const int64_t *llen) {
+  if (!s) { g_comm_error = "shard handle is NULL"; return 1; }
+  int64_t nx = 0, nl = 0;
+  for (int i = 0; i < n_xruns; ++i) nx += xlen[i];
+  for (int i = 0; i < n_lruns; ++i) nl += llen[i];
+  if (nx != s->o->n || nl != s->o->m) { s->err = "runs do not cover the local point / multipliers"; return 1; }
+  s->xsrc.assign(xsrc, xsrc + n_xruns); s->xlen.assign(xlen, xlen + n_xruns);
+  s->lsrc.assign(lsrc, lsrc + n_lruns); s->llen.assign(llen, llen + n_lruns);
+  return 0;
+}
+
 static int check_comm_error(dnlp_shard *s) {
   if (*s->c->error) {
     s->err = *s->c->error == 1 ? "sharded exchange timed out waiting for a peer's contribution"
@@ -536,8 +551,13 @@ int dnlp_shard_eval(dnlp_shard *s, int32_t prog, const double *x_local, const do
   CK(cudaSetDevice(o->device));
   if (prog < DNLP_PROG_F || prog > DNLP_PROG_HESS) { err = "bad program id"; return 1; }
   const int space = prog + 1;
-  if (o->put_x(x_local)) { err = o->err; return 1; }
-  if (prog == DNLP_PROG_HESS && o->put_lam(lam_local, sigma)) { err = o->err; return 1; }
+  if (!s->xsrc.empty()) {            // global vectors: staged run by run, no gathered host copy
+    if (o->put_x_runs(x_local, s->xsrc, s->xlen)) { err = o->err; return 1; }
+    if (prog == DNLP_PROG_HESS && o->put_lam_runs(lam_local, sigma, s->lsrc, s->llen)) { err = o->err; return 1; }
+  } else {
+    if (o->put_x(x_local)) { err = o->err; return 1; }
+    if (prog == DNLP_PROG_HESS && o->put_lam(lam_local, sigma)) { err = o->err; return 1; }
+  }
   if (o->run_program(prog, false)) { err = o->err; return 1; }
   if (s->exchange(space, true)) return 1;
   ShardOut &S = s->out[space];

@@ -31,8 +31,9 @@ class _DeviceArray:
 class GpuOracles:
     ELIDE_MIN = 4096               # outputs shorter than this are always copied whole
     ELIDE_MAX_FRACTION = 0.5       # elide constants when at most this share of entries is dynamic
+    EAGER_MIN_BYTES = 1 << 20      # eager delivery (all x-only outputs at a new x, async D2H) from this output volume on
 
-    def __init__(self, problem_ir, device=0, pinned_outputs=True, with_hessian=True, tape=None):
+    def __init__(self, problem_ir, device=0, pinned_outputs=True, with_hessian=True, tape=None, eager=None):
         """``problem_ir``: a ``dnlp_b200.ir.ProblemIR`` (see frontend_cvxpy.data_to_ir).
         ``tape``: an already compiled tape of this problem (skips the DAG compiler)."""
         self.problem = problem_ir
@@ -82,6 +83,16 @@ class GpuOracles:
                 self.dev.check(self.dev._L.dnlp_set_dynamic(self.dev.h, space, pos.ctypes.data_as(_cabi.c_i32p),
                                                            int(pos.size)))
                 self._dyn[name] = (pos, alloc(pos.size))
+        # Eager delivery: the library learns which host arrays the callbacks hand it, and at a new x computes
+        # f, grad, g, J together and copies them out on a second stream (dnlp_bind_outputs).  Worth it when the
+        # outputs are large enough for PCIe to matter; tiny problems stay on the one-callback-one-program path.
+        xonly = 8 * sum(self._dyn[k][0].size if k in self._dyn else v
+                        for k, v in (("grad", self.n), ("g", self.m), ("jac", self.nnz_jac)))
+        self.eager = bool(pinned_outputs and (xonly >= self.EAGER_MIN_BYTES if eager is None else eager))
+        bound = [self._dyn[k][1] if k in self._dyn else buf
+                 for k, buf in (("grad", self.grad_obj), ("g", self._g), ("jac", self._jac))]
+        self.dev.check(self.dev._L.dnlp_bind_outputs(self.dev.h, _ptr(self._f), *[_ptr(b) for b in bound],
+                                                    int(self.eager)))
 
     def rearm(self, problem_ir):
         """Reuse this compiled oracle for another solve of the same smooth problem (next start of a

@@ -159,6 +159,17 @@ class _DeviceShard:
                 elif not dense:
                     self.compact[name] = _cabi.pinned_empty(max(nd, 1))
         self._f, self._fh = _cabi.pinned_empty(1)
+        # hand the library the runs of the global x / lambda this shard sees: the callbacks then pass the
+        # GLOBAL vectors and staging reads them in place (no gathered host copy per callback)
+        self.global_inputs = False
+        if owner._var_runs is not None:
+            vr, cr = owner._var_runs, owner._con_runs
+            a64 = lambda v: np.ascontiguousarray(v, dtype=np.int64)      # noqa: E731
+            xs, xl = a64([r[0] for r in vr]), a64([r[1] - r[0] for r in vr])
+            ls, ll = a64([r[0] for r in cr]), a64([r[1] - r[0] for r in cr])
+            p64 = lambda v: v.ctypes.data_as(_cabi.c_i64p)               # noqa: E731
+            self.check(L.dnlp_shard_set_layout(self.h, int(xs.size), p64(xs), p64(xl), int(ls.size), p64(ls), p64(ll)))
+            self.global_inputs = True
         hb = C.create_string_buffer(384)
         if self.is_root:
             self.check(L.dnlp_shard_root_handles(self.h, hb))
@@ -303,8 +314,16 @@ class RowShardedOracles:
         out[dyn] = buf[:dyn.size]
         return out
 
+    def _global_x(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
+        if x.size != self.n:
+            raise ValueError("x has %d entries, expected %d" % (x.size, self.n))
+        return x
+
     def objective(self, x):
         # constants of the objective live in rank 0's local problem (it carries every non-row term)
+        if self._dev is not None and self._dev.global_inputs:
+            return self._dev.eval("f", self._global_x(x))
         xl = self._local_x(x)
         if self._dev is not None:
             return self._dev.eval("f", xl)
@@ -312,6 +331,8 @@ class RowShardedOracles:
         return np.float64(allreduce_sum(self.store, np.array([float(self.local.objective(xl))]))[0])
 
     def _callback(self, name, x, lam=None, sigma=1.0):
+        if self._dev is not None and self._dev.global_inputs:
+            return self._dev.eval(name, self._global_x(x), lam, sigma)
         xl = self._local_x(x)
         if self._dev is not None:
             return self._dev.eval(name, xl, lam, sigma)
@@ -332,6 +353,11 @@ class RowShardedOracles:
         return self.gs.jac_rows, self.gs.jac_cols
 
     def hessian(self, x, duals, obj_factor):
+        if self._dev is not None and self._dev.global_inputs:
+            lam = np.ascontiguousarray(duals, dtype=np.float64).reshape(-1)
+            if lam.size < self.m:
+                raise ValueError("duals has %d entries, expected at least %d" % (lam.size, self.m))
+            return self._callback("hess", x, lam, obj_factor)
         return self._callback("hess", x, self._local_lam(duals), obj_factor)
 
     def hessianstructure(self):

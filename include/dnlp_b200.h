@@ -136,6 +136,15 @@ int dnlp_set_dynamic(dnlp_oracle *o, int32_t dst_space, const int32_t *pos, int6
 int dnlp_eval_dyn(dnlp_oracle *o, int32_t prog, const double *x, const double *lam, double sigma,
                   double *compact);
 
+/* ---- eager delivery of the x-only outputs ----
+ * The caller names the (pinned) host arrays it passes to dnlp_eval_f / _grad / _g / _jac (or, for an
+ * output with registered dynamic positions, the compact array it passes to dnlp_eval_dyn).  With
+ * `eager` != 0 the first callback at a NEW x computes f, grad, g and J together and copies them to
+ * those arrays on a second stream: the D2H of the later callbacks' results overlaps the solver's own
+ * work, the staging of lambda and its H2D (PCIe is full duplex); a later callback at the same x only
+ * waits for its copy.  The Hessian (needs lambda, sigma) keeps its own call. */
+int dnlp_bind_outputs(dnlp_oracle *o, double *f, double *grad, double *g, double *jac, int32_t eager);
+
 /* ---- device-resident results (multi-GPU assembly: outputs are reduced / gathered over NVLink
  *      without a host round trip) ----
  * dnlp_run stages the inputs and executes program `prog`, leaving the result in HBM;
@@ -208,6 +217,8 @@ int dnlp_shard_set_output(dnlp_shard *s, int32_t dst_space, int64_t n_shared_tot
                           int64_t n_dyn, const int32_t *dyn_global_pos);
 int dnlp_shard_root_handles(dnlp_shard *s, char *out384);           /* root: IPC handles of its global arrays */
 int dnlp_shard_open_root(dnlp_shard *s, const char *handles384);    /* every rank: map them */
+int dnlp_shard_set_layout(dnlp_shard *s, int32_t n_xruns, const int64_t *xsrc, const int64_t *xlen,
+                          int32_t n_lruns, const int64_t *lsrc, const int64_t *llen);   /* eval then takes GLOBAL x / lambda */
 int dnlp_shard_eval(dnlp_shard *s, int32_t prog, const double *x_local, const double *lam_local, double sigma,
                     double *host_out /* root only */);
 int dnlp_shard_run_device(dnlp_shard *s, int32_t prog_mask, int32_t iters, float *elapsed_ms);

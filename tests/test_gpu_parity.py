@@ -622,3 +622,47 @@ def test_gpu_fused_spmv_jacobian(flat, gpu_mod, monkeypatch):
         assert_close(o.read_output("g"), ref.constraints(x), "g after device loop", atol=1e-11)
     finally:
         o.close()
+
+
+@pytest.mark.parametrize("name", ["c3_logistic_small", "hs071", "c5_microbench_small", "c2_eigen_qcqp_small"])
+def test_gpu_eager_delivery_random_callback_orders(name, gpu_mod, monkeypatch):
+    """Eager delivery (dnlp_bind_outputs): at a new x every x-only output is computed and copied on a second
+    stream.  Any interleaving of callbacks and points - IPOPT's order, line-search points that ask for f and g
+    only, repeated calls, x changing while copies are in flight - must return exactly what the one-program
+    path returns."""
+    g = Golden(name)
+    ref = RefOracles(g.problem)
+    ref.jacobianstructure(), ref.hessianstructure()
+    monkeypatch.setattr(gpu_mod, "ELIDE_MIN", 8)           # compact (dynamic-entry) delivery on these small problems too
+    o = gpu_mod(g.problem, eager=True)
+    plain = gpu_mod(g.problem, eager=False)
+    try:
+        assert o.eager and not plain.eager
+        rng = np.random.default_rng(5)
+        pts = [p["x"] * (1 + 0.01 * rng.standard_normal(p["x"].size)) for p in g.points for _ in range(2)]
+        lam0 = g.points[0]["lam"]
+        calls = ["f", "grad", "g", "jac", "hess"]
+        for step in range(60):
+            x = pts[rng.integers(len(pts))] if step % 3 else pts[step % len(pts)].copy()
+            for c in rng.permutation(calls)[:rng.integers(1, 6)]:
+                lam = lam0 * rng.uniform(0.5, 1.5)
+                if c == "f":
+                    assert_close(o.objective(x), ref.objective(x), "f")
+                elif c == "grad":
+                    assert_close(o.gradient(x), ref.gradient(x), "grad")
+                elif c == "g":
+                    assert_close(o.constraints(x), ref.constraints(x), "g", atol=1e-11)
+                elif c == "jac":
+                    assert_close(o.jacobian(x), ref.jacobian(x), "jac")
+                else:
+                    assert_close(o.hessian(x, lam, 0.9), ref.hessian(x, lam, 0.9), "hess")
+                    assert_close(plain.hessian(x, lam, 0.9), ref.hessian(x, lam, 0.9), "hess/plain")
+        # IPOPT's order at one iterate costs ONE launch sequence for the four x-only outputs
+        x = pts[0] * 1.001
+        l0 = o.kernel_launches()
+        o.objective(x)
+        l1 = o.kernel_launches()
+        o.gradient(x), o.constraints(x), o.jacobian(x)
+        assert o.kernel_launches() == l1 > l0
+    finally:
+        o.close(), plain.close()

@@ -13,8 +13,9 @@ from bench import build_workload, eval_point  # noqa: E402
 from dnlp_b200.oracles import GpuOracles  # noqa: E402
 
 name = sys.argv[1] if len(sys.argv) > 1 else "c3"
-prob, desc = build_workload(name)
-o = GpuOracles(prob)
+prob = build_workload(name)
+eager = None if len(sys.argv) < 3 else bool(int(sys.argv[2]))
+o = GpuOracles(prob, eager=eager)
 x, lam, sigma = eval_point(prob, 0)
 rng = np.random.default_rng(7)
 xs = [x * (1.0 + 1e-3 * rng.standard_normal(prob.n)) for _ in range(4)]
@@ -34,6 +35,7 @@ for i in range(reps):
         fn(xs[i % 4], lams[i % 4])
         tot[k] += time.perf_counter() - t0
 t_all = time.perf_counter() - t_all
+print("eager delivery: %s" % o.eager)
 print("%s: n=%d m=%d nnzJ=%d nnzH=%d  cores=%d  dyn=%s" % (name, prob.n, prob.m, o.nnz_jac, o.nnz_hess, os.cpu_count(),
       {k: int(v[0].size) for k, v in o._dyn.items()}))
 for k, _ in calls:
