@@ -299,6 +299,11 @@ class DeviceTape:
                 raise RuntimeError("dnlp_b200: oracle closed")
             raise RuntimeError("dnlp_b200: %s" % self._L.dnlp_last_error(self.h).decode())
 
+    def bind_outputs(self, f, grad, g, jac, eager):
+        """Name the host arrays the x-only callbacks deliver into (dnlp_bind_outputs)."""
+        p = lambda a: a.ctypes.data_as(c_f64p)      # noqa: E731
+        self.check(self._L.dnlp_bind_outputs(self.h, p(f), p(grad), p(g), p(jac), int(bool(eager))))
+
     def close(self):
         if getattr(self, "h", None):
             self._L.dnlp_destroy(self.h)

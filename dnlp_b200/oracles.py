@@ -91,8 +91,7 @@ class GpuOracles:
         self.eager = bool(pinned_outputs and (xonly >= self.EAGER_MIN_BYTES if eager is None else eager))
         bound = [self._dyn[k][1] if k in self._dyn else buf
                  for k, buf in (("grad", self.grad_obj), ("g", self._g), ("jac", self._jac))]
-        self.dev.check(self.dev._L.dnlp_bind_outputs(self.dev.h, _ptr(self._f), *[_ptr(b) for b in bound],
-                                                    int(self.eager)))
+        self.dev.bind_outputs(self._f, *bound, eager=self.eager)
 
     def rearm(self, problem_ir):
         """Reuse this compiled oracle for another solve of the same smooth problem (next start of a

@@ -50,6 +50,9 @@ def test_install_swaps_the_oracle_and_structures_match(cp, monkeypatch):
 
         def close(self):
             pass
+
+        def bind_outputs(self, *a, **k):
+            pass
     monkeypatch.setattr(_cabi, "DeviceTape", FakeDevice)
     monkeypatch.setattr(_cabi, "pinned_empty", lambda k: (np.empty(k), types.SimpleNamespace(free=lambda: None)))
 
@@ -94,6 +97,9 @@ def test_best_of_style_reapplied_chain_reuses_the_compiled_oracle(cp, monkeypatc
 
         def close(self):
             pass
+
+        def bind_outputs(self, *a, **k):
+            pass
     monkeypatch.setattr(_cabi, "DeviceTape", FakeDevice)
     monkeypatch.setattr(_cabi, "pinned_empty", lambda k: (np.empty(k), types.SimpleNamespace(free=lambda: None)))
 
@@ -133,6 +139,9 @@ def test_reference_best_of_loop_compiles_once(cp, monkeypatch):
             self.tape = tape
 
         def close(self):
+            pass
+
+        def bind_outputs(self, *a, **k):
             pass
     monkeypatch.setattr(_cabi, "DeviceTape", FakeDevice)
     monkeypatch.setattr(_cabi, "pinned_empty", lambda k: (np.empty(k), types.SimpleNamespace(free=lambda: None)))
@@ -178,6 +187,9 @@ def test_parameter_values_are_compile_time_constants(cp, monkeypatch):
             self.tape = tape
 
         def close(self):
+            pass
+
+        def bind_outputs(self, *a, **k):
             pass
     monkeypatch.setattr(_cabi, "DeviceTape", FakeDevice)
     monkeypatch.setattr(_cabi, "pinned_empty", lambda k: (np.empty(k), types.SimpleNamespace(free=lambda: None)))
