@@ -44,6 +44,7 @@ class TapeDesc(C.Structure):
         ("prog", c_i32p * NPROG), ("prog_len", C.c_int32 * NPROG),
         ("f_const", C.c_double), ("grad_const", c_f64p), ("g_const", c_f64p),
         ("jac_const", c_f64p), ("hess_const", c_f64p),
+        ("n_params", C.c_int64), ("params", c_f64p),
     ]
 
 
@@ -51,7 +52,7 @@ EXPORTS = [
     "dnlp_device_count", "dnlp_version", "dnlp_device_synchronize", "dnlp_create", "dnlp_destroy", "dnlp_last_error",
     "dnlp_eval_f", "dnlp_eval_grad", "dnlp_eval_g", "dnlp_eval_jac", "dnlp_eval_hess", "dnlp_eval_all",
     "dnlp_host_alloc", "dnlp_host_free", "dnlp_upload_point", "dnlp_run_device", "dnlp_profile_instrs",
-    "dnlp_read_output", "dnlp_kernel_launches", "dnlp_set_cache", "dnlp_set_graphs", "dnlp_set_parallel", "dnlp_set_windows", "dnlp_set_dynamic", "dnlp_eval_dyn", "dnlp_bind_outputs", "dnlp_instr_kernel", "dnlp_run", "dnlp_output_ptr",
+    "dnlp_read_output", "dnlp_kernel_launches", "dnlp_set_cache", "dnlp_set_graphs", "dnlp_set_parallel", "dnlp_set_windows", "dnlp_set_dynamic", "dnlp_eval_dyn", "dnlp_bind_outputs", "dnlp_set_params", "dnlp_instr_kernel", "dnlp_run", "dnlp_output_ptr",
     "dnlp_batch_create", "dnlp_batch_destroy", "dnlp_batch_last_error", "dnlp_batch_eval", "dnlp_batch_upload",
     "dnlp_batch_run_device", "dnlp_batch_profile_instrs", "dnlp_batch_kernel_launches",
     "dnlp_comm_unique_id", "dnlp_comm_create", "dnlp_comm_destroy", "dnlp_comm_last_error", "dnlp_comm_has_nccl",
@@ -110,6 +111,7 @@ def lib():
     L.dnlp_output_ptr.restype = vp
     L.dnlp_instr_kernel.argtypes = [vp, C.c_int32]
     L.dnlp_instr_kernel.restype = C.c_char_p
+    L.dnlp_set_params.argtypes = [vp, c_f64p, C.c_int64]
     L.dnlp_bind_outputs.argtypes = [vp, c_f64p, c_f64p, c_f64p, c_f64p, C.c_int32]
     L.dnlp_set_dynamic.argtypes = [vp, C.c_int32, c_i32p, C.c_int64]
     L.dnlp_eval_dyn.argtypes = [vp, C.c_int32, c_f64p, c_f64p, C.c_double, c_f64p]
@@ -270,6 +272,12 @@ def make_tape_desc(tape):
     keep += consts
     td.f_const = float(tape.f_const)
     td.grad_const, td.g_const, td.jac_const, td.hess_const = [_p(c, c_f64p) if c.size else None for c in consts]
+    pv = f64(getattr(tape, "param_values", np.zeros(0)))
+    keep.append(pv)
+    td.n_params = int(getattr(tape, "n_params", 0))
+    if pv.size != td.n_params:
+        raise ValueError("tape has %d parameter slots but %d values" % (td.n_params, pv.size))
+    td.params = _p(pv, c_f64p) if pv.size else None
     keep += [arr, td]
     return td, keep
 
@@ -298,6 +306,9 @@ class DeviceTape:
             if not self.h:
                 raise RuntimeError("dnlp_b200: oracle closed")
             raise RuntimeError("dnlp_b200: %s" % self._L.dnlp_last_error(self.h).decode())
+
+    def set_params(self, values):
+        self.check(self._L.dnlp_set_params(self.h, values.ctypes.data_as(c_f64p), int(values.size)))
 
     def bind_outputs(self, f, grad, g, jac, eager):
         """Name the host arrays the x-only callbacks deliver into (dnlp_bind_outputs)."""

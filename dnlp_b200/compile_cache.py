@@ -67,6 +67,7 @@ def fingerprint(prob):
     """Hex digest identifying the tape ``compile_problem(prob)`` would produce."""
     h = hashlib.blake2b(digest_size=20)
     var_index = {id(v): i for i, v in enumerate(prob.variables)}
+    param_index = {id(q): i for i, q in enumerate(getattr(prob, "params", []))}
     memo = {}
 
     def visit(n):
@@ -79,6 +80,9 @@ def fingerprint(prob):
         if n.op == "var":
             # a variable is its position in the flat layout; one that is not listed cannot be compiled
             h.update(b"v%d" % var_index.get(k, -1))
+        elif n.op == "param":
+            # a parameter is a slot: its position and shape enter the tape, its VALUE does not
+            h.update(b"p%d" % param_index.get(k, -1))
         else:
             for name in sorted(n.attrs):
                 h.update(name.encode())

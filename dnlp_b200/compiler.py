@@ -135,6 +135,8 @@ def compile_problem(prob, with_hessian=True):
     L-BFGS when the object has no usable ``hessian``)."""
     b = Builder(prob)
     tape = b.tape
+    if tape.n_params:
+        tape.param_values = prob.param_values()
     n, m = prob.n, prob.m
     var_ids = [v.attrs["id"] for v in prob.variables]
     off = b.var_off

@@ -292,6 +292,11 @@ static int batch_create_impl(dnlp_batch *o, const dnlp_tape_desc *t) {
   o->owned.push_back(p);
   o->V = static_cast<double *>(p);
   CKB(cudaMemset(o->V, 0, (size_t)(t->nslots + 2) * B * sizeof(double)));
+  if (t->n_params > 0 && t->params) {          // every start sees the same parameter values
+    double *pd = nullptr;
+    if (o->upload(t->params, t->n_params, &pd)) return 1;
+    bfill_kernel<<<o->grid_for(t->n_params * (int64_t)B), 256, 0, o->stream>>>(pd, o->V + (t->n + 1 + t->m) * (int64_t)B, t->n_params, B);
+  }
   const int64_t lens[6] = {0, 1, t->n, t->m, t->nnz_jac, t->nnz_hess};
   const double *consts[6] = {nullptr, &t->f_const, t->grad_const, t->g_const, t->jac_const, t->hess_const};
   int64_t maxlen = t->n > t->m ? t->n : t->m;

@@ -711,6 +711,8 @@ static int create_impl(dnlp_oracle *o, const dnlp_tape_desc *t) {
   CK(cudaEventCreateWithFlags(&o->ev_copied, cudaEventDisableTiming));
   for (int s2 = 0; s2 < 6; ++s2) CK(cudaEventCreateWithFlags(&o->ev_out[s2], cudaEventDisableTiming));
   o->n = t->n; o->m = t->m; o->nslots = t->nslots; o->nnz_jac = t->nnz_jac; o->nnz_hess = t->nnz_hess;
+  o->n_params = t->n_params;
+  if (t->n_params < 0 || t->n + 1 + t->m + t->n_params > t->nslots) { err = "parameter slots exceed the value buffer"; return 1; }
   if (const char *e = getenv("DNLP_WIN_MIN_TERMS")) o->win_min_terms = atoll(e);   // tests: force the window path
   if (const char *e = getenv("DNLP_NO_SIGMA_CACHE")) o->sigma_cache_enabled = atoi(e) == 0;
   if (const char *e = getenv("DNLP_BATCH_SPLIT")) o->batch_split = atoll(e);        // tests: both batches on small problems
@@ -728,6 +730,8 @@ static int create_impl(dnlp_oracle *o, const dnlp_tape_desc *t) {
   o->owned.push_back(p);
   o->V = static_cast<double *>(p);
   CK(cudaMemset(o->V, 0, (size_t)(t->nslots + 2) * sizeof(double)));
+  if (t->n_params > 0 && t->params)
+    CK(cudaMemcpy(o->V + t->n + 1 + t->m, t->params, (size_t)t->n_params * sizeof(double), cudaMemcpyHostToDevice));
 
   CK(cudaMallocHost(&p, (size_t)(t->n + 2) * sizeof(double)));
   o->hx = static_cast<double *>(p);
@@ -962,6 +966,18 @@ int dnlp_eval_all(dnlp_oracle *o, const double *x, const double *lam, double sig
   if (o->fetch(DNLP_DST_F, f) || o->fetch(DNLP_DST_GRAD, grad) || o->fetch(DNLP_DST_G, g) ||
       o->fetch(DNLP_DST_JAC, jac) || o->fetch(DNLP_DST_HESS, hess)) return 1;
   CK(cudaStreamSynchronize(o->stream));
+  return 0;
+}
+
+int dnlp_set_params(dnlp_oracle *o, const double *values, int64_t count) {
+  ENTER(o);
+  if (count != o->n_params) { err = "wrong number of parameter values"; return 1; }
+  if (count == 0) return 0;
+  CK(cudaStreamSynchronize(o->cstream));
+  CK(cudaMemcpyAsync(o->V + o->n + 1 + o->m, values, (size_t)count * sizeof(double), cudaMemcpyHostToDevice, o->stream));
+  CK(cudaStreamSynchronize(o->stream));          // `values` is caller memory
+  o->invalidate(8);
+  ++o->x_epoch;                                  // x-only outputs may depend on the parameters: deliver them anew
   return 0;
 }
 

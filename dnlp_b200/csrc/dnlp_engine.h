@@ -64,7 +64,7 @@ using dnlp_detail::ElemBatch;
 struct dnlp_oracle {
   int device = 0;
   int sm_count = 148;
-  int64_t n = 0, m = 0, nslots = 0, nnz_jac = 0, nnz_hess = 0;
+  int64_t n = 0, m = 0, nslots = 0, nnz_jac = 0, nnz_hess = 0, n_params = 0;
   cudaStream_t stream = nullptr;
   double *V = nullptr;
   double *out[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};

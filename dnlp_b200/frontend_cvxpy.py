@@ -36,11 +36,63 @@ def _const(expr):
     return node
 
 
-def expr_to_ir(expr, memo):
+# Atoms under which a Parameter may stay a value slot: sums, elementwise products and the affine index /
+# shape atoms (dnlp_b200/rules.py handles their value, Jacobian and Hessian rules with a symbolic constant
+# factor).  Anywhere else (the matrix of a product with variables, quad_form's matrix, an exponent) the
+# parameter is FROZEN at its current value: correct, and a new value then means a new tape (the fingerprint
+# of a frozen parameter includes its value).
+_PARAM_OK_PARENTS = ("AddExpression", "NegExpression", "multiply", "Promote", "Sum", "index", "special_index",
+                     "reshape", "transpose", "broadcast_to")
+
+
+def _param_tree(expr, memo):
+    """IR of a constant sub-expression that contains Parameters, or None when some atom in it cannot carry a
+    parameter slot (then the caller folds the whole sub-expression to its current value)."""
+    cls = type(expr).__name__
+    if cls == "Parameter":
+        key = ("param", expr.id)
+        if key not in memo:
+            if expr.value is None:
+                raise ValueError("constant/parameter without a value: %s" % expr)
+            memo[key] = ir.Node("param", (), expr.shape, id=int(expr.id), name=expr.name(),
+                                value=np.asarray(expr.value, dtype=np.float64))
+        return memo[key]
+    if not expr.parameters():
+        return _const(expr)
+    if cls not in _PARAM_OK_PARENTS and cls != "MulExpression":
+        return None
+    kids = [_param_tree(a, memo) for a in expr.args]
+    if any(k is None for k in kids):
+        return None
+    if cls == "MulExpression":                    # constant @ parameter-tree (an affine map of the parameters)
+        if expr.args[0].parameters() or not expr.args[1].parameters():
+            return None
+        return ir.Node("matmul", kids, expr.shape)
+    if cls == "Sum":
+        return ir.Node("sum", kids, expr.shape, axis=expr.axis, keepdims=bool(expr.keepdims))
+    if cls == "index":
+        fkey = [(int(s.start), None if s.stop is None else int(s.stop), int(s.step)) for s in expr.key]
+        return ir.Node("index", kids, expr.shape, key=fkey, orig_key=ir._encode_key(expr._orig_key))
+    if cls == "special_index":
+        return ir.Node("special_index", kids, expr.shape, select=np.asarray(expr._select_mat, dtype=np.int64))
+    if cls == "reshape":
+        return ir.Node("reshape", kids, expr.shape, order=expr.order)
+    if cls == "transpose":
+        axes = getattr(expr, "axes", None)
+        return ir.Node("transpose", kids, expr.shape, axes=None if axes is None else tuple(int(a) for a in axes))
+    return ir.Node(_SIMPLE.get(cls, {"Promote": "promote", "broadcast_to": "broadcast_to"}.get(cls)), kids, expr.shape)
+
+
+def expr_to_ir(expr, memo, parent=None):
     key = id(expr)
     if key in memo:
         return memo[key]
     cls = type(expr).__name__
+    if expr.is_constant() and cls != "Variable" and expr.parameters() and (parent is None or parent in _PARAM_OK_PARENTS):
+        node = _param_tree(expr, memo)
+        if node is not None:
+            memo[key] = node
+            return node
     if cls == "Variable":
         bounds = getattr(expr, "bounds", None)
         node = ir.Node("var", (), expr.shape, id=int(expr.id), name=expr.name(),
@@ -49,7 +101,7 @@ def expr_to_ir(expr, memo):
     elif expr.is_constant():
         node = _const(expr)
     else:
-        args = [expr_to_ir(a, memo) for a in expr.args]
+        args = [expr_to_ir(a, memo, parent=cls) for a in expr.args]
         if cls in _SIMPLE:
             node = ir.Node(_SIMPLE[cls], args, expr.shape)
         elif cls == "Sum":

@@ -36,7 +36,7 @@ AFFINE_OPS = (
 )
 BILINEAR_OPS = ("multiply", "matmul")
 OTHER_SMOOTH = ("quad_form", "quad_over_lin", "rel_entr")
-ALL_OPS = ("var", "const") + AFFINE_OPS + BILINEAR_OPS + ELEMENTWISE_UNARY + OTHER_SMOOTH
+ALL_OPS = ("var", "const", "param") + AFFINE_OPS + BILINEAR_OPS + ELEMENTWISE_UNARY + OTHER_SMOOTH
 
 _var_ids = itertools.count(1)
 
@@ -49,7 +49,7 @@ class Node:
     """One atom.  ``shape`` is the cvxpy shape tuple, ``attrs`` the atom data."""
 
     __array_priority__ = 1000  # numpy defers to our __r*__ operators
-    __slots__ = ("op", "args", "shape", "attrs", "_vars")
+    __slots__ = ("op", "args", "shape", "attrs", "_vars", "_params")
 
     def __init__(self, op, args=(), shape=(), **attrs):
         if op not in ALL_OPS:
@@ -60,6 +60,7 @@ class Node:
         self.shape = tuple(int(s) for s in shape)
         self.attrs = attrs
         self._vars = None
+        self._params = None
 
     # ---- structural predicates (mirror Expression.is_constant / is_affine) ----
     @property
@@ -90,6 +91,25 @@ class Node:
 
     def is_constant(self):
         return self.op != "var" and (0 in self.shape or not self.variables())
+
+    def params(self):
+        """First-appearance ordered unique ``param`` leaves (cvxpy Parameters: constants whose VALUE may change
+        between solves, expressions/constants/parameter.py:35)."""
+        if self._params is None:
+            if self.op == "param":
+                self._params = [self]
+            else:
+                seen, out = set(), []
+                for a in self.args:
+                    for q in a.params():
+                        if id(q) not in seen:
+                            seen.add(id(q))
+                            out.append(q)
+                self._params = out
+        return self._params
+
+    def has_params(self):
+        return bool(self.params())
 
     def is_var(self):
         return self.op == "var"
@@ -156,6 +176,8 @@ class Node:
             return "var%d%s" % (self.attrs["id"], list(self.shape))
         if self.op == "const":
             return "const%s" % (list(self.shape),)
+        if self.op == "param":
+            return "param%d%s" % (self.attrs["id"], list(self.shape))
         return "%s(%s)" % (self.op, ", ".join(repr(a) for a in self.args))
 
 
@@ -177,8 +199,26 @@ def Constant(value):
     return Node("const", (), v.shape, value=v)
 
 
+def Parameter(shape=(), value=None, name=None):
+    """A constant whose value can change between solves WITHOUT recompiling the tape: it lives in the value
+    buffer next to x / sigma / lambda (``GpuOracles.set_parameters``)."""
+    if isinstance(shape, (int, np.integer)):
+        shape = (int(shape),)
+    pid = next(_var_ids)
+    v = np.zeros(shape) if value is None else np.asarray(value, dtype=np.float64).reshape(shape)
+    return Node("param", (), shape, id=pid, name=name or "param%d" % pid, value=v)
+
+
 def as_node(x):
     return x if isinstance(x, Node) else Constant(x)
+
+
+def eval_constant(node):
+    """Numeric value of a constant subtree (constants and parameters at their current values)."""
+    if node.op in ("const", "param"):
+        return node.attrs["value"]
+    from . import _consteval
+    return _consteval.numeric(node, [eval_constant(a) for a in node.args])
 
 
 # --------------------------------------------------------------------------
@@ -426,11 +466,44 @@ class ProblemIR:
         self.variables = list(variables)
         self.n = int(np.sum([v.size for v in self.variables], dtype=np.int64)) if self.variables else 0
         self.m = int(np.sum([c.size for c in self.constraints], dtype=np.int64)) if self.constraints else 0
+        seen, self.params = set(), []
+        for e in [self.objective] + self.constraints:
+            for q in e.params():
+                if id(q) not in seen:
+                    seen.add(id(q))
+                    self.params.append(q)
+        self.n_params = int(np.sum([q.size for q in self.params], dtype=np.int64)) if self.params else 0
         self.cl = None if cl is None else np.asarray(cl, dtype=np.float64)
         self.cu = None if cu is None else np.asarray(cu, dtype=np.float64)
         self.lb = None if lb is None else np.asarray(lb, dtype=np.float64)
         self.ub = None if ub is None else np.asarray(ub, dtype=np.float64)
         self.x0 = None if x0 is None else np.asarray(x0, dtype=np.float64)
+
+    def param_values(self):
+        """Current parameter values, flattened column-major in ``self.params`` order."""
+        if not self.params:
+            return np.zeros(0)
+        return np.concatenate([np.asarray(q.attrs["value"], dtype=np.float64).flatten(order="F") for q in self.params])
+
+    def folded(self):
+        """The same problem with every parameter-dependent constant subtree evaluated at the current values
+        (what the reference's rules see through ``.value``): input of the CPU oracle."""
+        memo = {}
+
+        def visit(n):
+            if id(n) in memo:
+                return memo[id(n)]
+            if n.op == "var" or not n.has_params():
+                out = n
+            elif n.is_constant():
+                v = np.asarray(eval_constant(n), dtype=np.float64)
+                out = Constant(v.reshape(n.shape, order="F") if v.size == n.size else v)
+            else:
+                out = Node(n.op, [visit(a) for a in n.args], n.shape, **n.attrs)
+            memo[id(n)] = out
+            return out
+        return ProblemIR(visit(self.objective), [visit(c) for c in self.constraints], self.variables,
+                         self.cl, self.cu, self.lb, self.ub, self.x0)
 
     def var_offsets(self):
         off, out = 0, {}

@@ -95,13 +95,25 @@ class GpuOracles:
 
     def rearm(self, problem_ir):
         """Reuse this compiled oracle for another solve of the same smooth problem (next start of a
-        ``best_of`` loop): new initial point, iteration counter back to zero.  The tape, the device
-        buffers and the captured graphs stay."""
-        if problem_ir.n != self.n or problem_ir.m != self.m:
+        ``best_of`` loop, or the same problem with new Parameter values): new initial point, new parameter
+        values, iteration counter back to zero.  The tape, the device buffers and the captured graphs stay."""
+        if problem_ir.n != self.n or problem_ir.m != self.m or \
+                getattr(problem_ir, "n_params", 0) != self.tape.n_params:
             raise ValueError("rearm: problem size differs from the compiled one")
         self.problem = problem_ir
         self.initial_point = problem_ir.x0
         self.iterations = 0
+        if self.tape.n_params:
+            self.set_parameters(problem_ir.param_values())
+
+    def set_parameters(self, values):
+        """New values for the Parameter slots (flat, ``ProblemIR.params`` order, each column-major).  Only
+        the instructions that depend on them are re-run; nothing is recompiled or re-uploaded."""
+        v = np.ascontiguousarray(values, dtype=np.float64).reshape(-1)
+        if v.size != self.tape.n_params:
+            raise ValueError("expected %d parameter values, got %d" % (self.tape.n_params, v.size))
+        self.dev.set_params(v)
+        self._hess_sigma = None          # sigma-keyed host entries may depend on parameters: fetch them again
 
     def _pinned(self, count):
         arr, h = _cabi.pinned_empty(count)

@@ -44,7 +44,12 @@ class Builder:
 
     def __init__(self, prob):
         self.prob = prob
-        self.tape = T.Tape(prob.n, prob.m)
+        self.tape = T.Tape(prob.n, prob.m, getattr(prob, "n_params", 0))
+        self.param_off = {}
+        poff = self.tape.param_slot
+        for q in getattr(prob, "params", []):
+            self.param_off[q.attrs["id"]] = poff
+            poff += q.size
         self.var_off = {}
         off = 0
         for v in prob.variables:
@@ -69,6 +74,8 @@ class Builder:
         self._last_mask = ((T.DEP_X if np.any(slots < self.tape.n) else 0)
                            | (T.DEP_SIGMA if np.any(slots == self.tape.n) else 0)
                            | (T.DEP_LAMBDA if np.any((slots > self.tape.n) & (slots < self.tape.n + 1 + self.tape.m))
+                              else 0)
+                           | (T.DEP_PARAM if np.any((slots >= self.tape.param_slot) & (slots < self.tape.tmp_slot))
                               else 0))
         deps = set()
         if self._producers and slots.size:
@@ -77,7 +84,7 @@ class Builder:
             ends = np.array([p[1] for p in prod], dtype=np.int64)
             ids = np.array([p[2] for p in prod], dtype=np.int64)
             odd = np.array([p[3] for p in prod], dtype=np.int64)
-            tmp = slots[slots >= self.tape.n + 1 + self.tape.m]
+            tmp = slots[slots >= self.tape.tmp_slot]
             if tmp.size:
                 k = np.searchsorted(starts, tmp, side="right") - 1
                 ok = (k >= 0) & (tmp < ends[np.maximum(k, 0)])
@@ -383,6 +390,8 @@ class Builder:
             return self.var_slots(node)
         if op == "const":
             return SymVec.const(_flatF(_dense(node.attrs["value"])))
+        if op == "param":                                  # expressions/constants/parameter.py:35: a constant
+            return SymVec.slot_range(self.param_off[node.attrs["id"]], node.size)   # whose value lives in V
         a = node.args
         if op == "add":                                    # affine/add_expr.py:72-73
             out = None
@@ -423,9 +432,9 @@ class Builder:
             return self.value(a[0]).gather(_flatF(I))
         if op == "multiply":                               # affine/binary_operators.py:431-438
             x, y = a
-            if x.is_constant():
+            if x.is_constant() and not x.has_params():
                 return self._bcast(self.value(y), y, node).scale(self._const_flat(x, node))
-            if y.is_constant():
+            if y.is_constant() and not y.has_params():
                 return self._bcast(self.value(x), x, node).scale(self._const_flat(y, node))
             return self.mul(self._bcast(self.value(x), x, node), self._bcast(self.value(y), y, node))
         if op == "matmul":                                 # affine/binary_operators.py:134-140
@@ -443,9 +452,22 @@ class Builder:
             s = self.mul(xv, xv).sum_all()
             return self.elem(T.F_DIV, s, self.value(a[1]))
         if op == "quad_form":                              # quad_form.py:41-47
+            self._reject_param_operands(node)
             xv = self.value(a[0])
             return self.mul(xv, self.quad_form_Qx(node)).sum_all()
         raise NotImplementedError(op)
+
+    def _reject_param_operands(self, node):
+        """Parameters are value slots; they may sit in sums, elementwise products and under affine atoms.  As
+        the constant MATRIX of a product with variables (or inside quad_form / power exponents) they would
+        change coefficient arrays of the tape: not expressible as a slot.  The cvxpy frontend freezes such
+        parameters (their value then belongs to the compile-cache fingerprint)."""
+        if node.is_constant():
+            return
+        for a in node.args:
+            if a.is_constant() and a.has_params():
+                raise NotImplementedError("a Parameter as the constant operand of %s is not supported as a value slot"
+                                          % node.op)
 
     def _bcast(self, v, arg, node):
         if v.K == node.size:
@@ -501,12 +523,13 @@ class Builder:
         def as2d(c, shape):
             v = c.attrs["value"]
             return v if sp.issparse(v) else sp.csr_array(np.asarray(v, dtype=np.float64).reshape(shape))
-        if X.is_constant():                                # vec(XY) = kron(I_p, X) vec(Y)
+        if X.is_constant() and not X.has_params():         # vec(XY) = kron(I_p, X) vec(Y)
             r, c, d = self._kron_map(sp.eye(p), as2d(X, xs))
             return self.value(Y).linear_map(r, c, d, node.size)
-        if Y.is_constant():                                # vec(XY) = kron(Y.T, I_m) vec(X)
+        if Y.is_constant() and not Y.has_params():         # vec(XY) = kron(Y.T, I_m) vec(X)
             r, c, d = self._kron_map(as2d(Y, ys).T, sp.eye(m))
             return self.value(X).linear_map(r, c, d, node.size)
+        self._reject_param_operands(node)
         i, l, j = np.meshgrid(np.arange(m), np.arange(n), np.arange(p), indexing="ij")
         i, l, j = i.reshape(-1), l.reshape(-1), j.reshape(-1)
         prod = self.mul(self.value(X).gather(i + l * m), self.value(Y).gather(l + j * n))
@@ -523,6 +546,8 @@ class Builder:
             return {}
         if not self._verify_jac(node):                     # atoms/atom.py:509-510
             raise ValueError("Argument error in jacobian for atom %s." % node.op)
+        if node.op not in ir.AFFINE_OPS and node.op != "multiply":
+            self._reject_param_operands(node)
         out = getattr(self, "_jac_" + (node.op if node.op not in T.UNARY_TABLE else "unary"))(node)
         return {k: (np.asarray(r, dtype=np.int64).reshape(-1), np.asarray(c, dtype=np.int64).reshape(-1), v)
                 for k, (r, c, v) in out.items()}
@@ -726,6 +751,16 @@ class Builder:
 
     def _jac_multiply(self, node):                         # affine/binary_operators.py:552-591
         x, y = node.args
+        if x.is_constant() and x.has_params():             # parameter-valued factor: same rule, symbolic value
+            xs = self.value(x)
+            return {k: (r, c, self.mul(v, xs.gather(np.asarray(r, dtype=np.int64).reshape(-1) if xs.K > 1
+                                                   else np.zeros(np.size(r), dtype=np.int64))))
+                    for k, (r, c, v) in self.jac(y).items()}
+        if y.is_constant() and y.has_params():
+            ys = self.value(y)
+            return {k: (r, c, self.mul(v, ys.gather(np.asarray(r, dtype=np.int64).reshape(-1) if ys.K > 1
+                                                   else np.zeros(np.size(r), dtype=np.int64))))
+                    for k, (r, c, v) in self.jac(x).items()}
         if x.is_constant():
             xv = _flatF(np.atleast_1d(_dense(x.attrs["value"])))
             return {k: (r, c, v.scale(xv[r])) for k, (r, c, v) in self.jac(y).items()}
@@ -893,7 +928,7 @@ class Builder:
     # Hessian-vector products  (Atom.hess_vec, atoms/atom.py:515-561)
     # =========================================================================
     def hv(self, node, vec):
-        if node.op in ("var", "const"):                    # variable.py:73-74, constant.py:119-125
+        if node.op in ("var", "const", "param"):                    # variable.py:73-74, constant.py:119-125
             return {}
         if vec.K != node.size:                             # atoms/atom.py:546-548
             raise ValueError("Dimension mismatch in hess_vec. vec.size != phi(x).size")
@@ -969,6 +1004,10 @@ class Builder:
 
     def _hv_multiply(self, node, vec):                     # affine/binary_operators.py:511-546
         x, y = node.args
+        if x.is_constant() and x.has_params():
+            return self.hv(y, self.mul(vec, self._bcast(self.value(x), x, node)))
+        if y.is_constant() and y.has_params():
+            return self.hv(x, self.mul(vec, self._bcast(self.value(y), y, node)))
         if x.is_constant():
             return self.hv(y, vec.scale(_flatF(_dense(x.attrs["value"]))))
         if y.is_constant():

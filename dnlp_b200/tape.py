@@ -5,7 +5,8 @@ Value buffer ``V`` (fp64, one per oracle, resident in HBM):
     [0, n)            x            the current point (uploaded per callback)
     [n]               sigma        objective factor   } uploaded by hessian()
     [n+1, n+1+m)      lambda       constraint duals   }
-    [n+1+m, nslots)   tmp          outputs of tape instructions
+    [n+1+m, n+1+m+P)  params       Parameter values (uploaded by set_parameters, kept between solves)
+    [n+1+m+P, nslots) tmp          outputs of tape instructions
 
 Instruction kinds (the C-ABI mirrors these as plain structs, include/dnlp_b200.h):
 
@@ -65,7 +66,7 @@ OUT_NAMES = {DST_F: "f", DST_GRAD: "grad", DST_G: "g", DST_JAC: "jac", DST_HESS:
 K_ELEM, K_POLY, K_GEMV, K_SCALE, K_SPMVJ = 1, 2, 3, 4, 5
 
 # what an instruction's result depends on (transitively): the point, the objective factor, the duals
-DEP_X, DEP_SIGMA, DEP_LAMBDA = 1, 2, 4
+DEP_X, DEP_SIGMA, DEP_LAMBDA, DEP_PARAM = 1, 2, 4, 8
 
 
 class Instr:
@@ -141,9 +142,9 @@ class Instr:
 class Tape:
     """Everything the device needs, as flat NumPy arrays plus small tables."""
 
-    def __init__(self, n, m):
-        self.n, self.m = n, m
-        self.nslots = n + 1 + m
+    def __init__(self, n, m, n_params=0):
+        self.n, self.m, self.n_params = n, m, int(n_params)
+        self.nslots = n + 1 + m + self.n_params
         self.instrs = []
         self.programs = {}          # name -> list of instruction ids
         self.jac_rows = self.jac_cols = None
@@ -156,6 +157,7 @@ class Tape:
         self.jac_is_list = False    # reference returns a Python list when all constraints are affine
         self.dynamic = {}           # output space -> int32 positions of the x/lambda-dependent entries
         self.dynamic_sigma = {}     # output space -> the subset of `dynamic` that depends on sigma ONLY
+        self.param_values = np.zeros(self.n_params)   # initial parameter values (uploaded with the tape)
 
     @property
     def sigma_slot(self):
@@ -164,6 +166,14 @@ class Tape:
     @property
     def lam_slot(self):
         return self.n + 1
+
+    @property
+    def param_slot(self):
+        return self.n + 1 + self.m
+
+    @property
+    def tmp_slot(self):
+        return self.n + 1 + self.m + self.n_params
 
     def alloc(self, count):
         start = self.nslots

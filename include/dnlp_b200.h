@@ -68,7 +68,7 @@ typedef struct {
   int32_t row_len;        /* uniform row length when ptr == NULL */
   int32_t uses_lam;       /* depends on (sigma, lambda): never cached across calls */
   int32_t level;          /* 0 = reads only x / lambda (no instruction feeds it) */
-  int32_t dep_mask;       /* what the result depends on, transitively: 1 = x, 2 = sigma, 4 = lambda */
+  int32_t dep_mask;       /* what the result depends on, transitively: 1 = x, 2 = sigma, 4 = lambda, 8 = parameters */
   /* GEMV: dst[i] = alpha * sum_j Q[i*ncols + j] * V[x_off + j] */
   const double *Q;
   int64_t ncols;
@@ -106,6 +106,10 @@ typedef struct {
   const double *g_const;      /* m */
   const double *jac_const;    /* nnz_jac */
   const double *hess_const;   /* nnz_hess */
+  /* Parameter values (cvxpy Parameters: constants whose value may change between solves) occupy
+   * V[n + 1 + m, n + 1 + m + n_params); instructions that read them carry dep_mask bit 8. */
+  int64_t n_params;
+  const double *params;       /* n_params initial values */
 } dnlp_tape_desc;
 
 int dnlp_device_count(void);
@@ -126,6 +130,9 @@ int dnlp_eval_hess(dnlp_oracle *o, const double *x, const double *lam /* m */, d
 /* all five at one (x, lam, sigma): one upload, shared forward sweep, outputs may be NULL to skip the copy */
 int dnlp_eval_all(dnlp_oracle *o, const double *x, const double *lam, double sigma,
                   double *f, double *grad, double *g, double *jac, double *hess);
+
+/* ---- parameters: new values for the slots V[n+1+m ..); invalidates exactly what depends on them (no recompilation) ---- */
+int dnlp_set_params(dnlp_oracle *o, const double *values, int64_t count);
 
 /* ---- constant-entry elision (reference quirk Q5: affine Jacobian rows never change) ----
  * dnlp_set_dynamic registers, for one output (DNLP_DST_GRAD..DNLP_DST_HESS), the positions of the

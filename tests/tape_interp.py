@@ -59,6 +59,12 @@ class TapeInterp:
     def __init__(self, tape):
         self.t = tape
         self.V = np.zeros(tape.nslots)
+        self.set_params(tape.param_values)
+
+    def set_params(self, values):
+        t = self.t
+        if getattr(t, "n_params", 0):
+            self.V[t.param_slot:t.param_slot + t.n_params] = values
 
     def _run(self, prog, outs):
         t, V = self.t, self.V

@@ -666,3 +666,53 @@ def test_gpu_eager_delivery_random_callback_orders(name, gpu_mod, monkeypatch):
         assert o.kernel_launches() == l1 > l0
     finally:
         o.close(), plain.close()
+
+
+def test_gpu_parameter_sweep_without_recompiling(gpu_mod):
+    """Parameter slots (expressions/constants/parameter.py:35): a sweep over parameter
+    values on ONE compiled oracle - every output must equal the CPU oracle of the problem with the
+    parameters folded at their current values, and only parameter-dependent work is repeated."""
+    from dnlp_b200 import ir
+    rng = np.random.default_rng(3)
+    n = 300
+    A = rng.standard_normal((40, n))
+    x, t = ir.Variable(n), ir.Variable(40)
+    gamma, b, w = ir.Parameter((), 0.5), ir.Parameter(n, rng.standard_normal(n)), ir.Parameter(40, rng.uniform(0.5, 2, 40))
+    # smooth form (atoms on bare variables): parameters as a scalar weight, an elementwise weight, a linear
+    # coefficient vector and right-hand sides
+    obj = ir.sum(ir.exp(x)) + ir.multiply(gamma, ir.sum(ir.power(x, 2))) + ir.sum(ir.multiply(b, x))
+    cons = [ir.multiply(w, ir.logistic(t)) + ir.neg(ir.promote(gamma, (40,))),
+            t + ir.neg(ir.matmul(A, x)),
+            ir.sum(ir.multiply(b, ir.power(x, 3))) + ir.neg(gamma)]
+    prob = ir.ProblemIR(obj, cons, [x, t], x0=0.1 * rng.standard_normal(n + 40))
+    assert prob.n_params == 1 + n + 40
+    o = gpu_mod(prob)
+    try:
+        assert o.tape.n_params == prob.n_params
+        xv = prob.x0 * 1.1
+        lam = rng.standard_normal(prob.m)
+        for trial in range(4):
+            if trial:
+                gamma.attrs["value"] = np.asarray(rng.uniform(0.1, 3.0))
+                b.attrs["value"] = rng.standard_normal(n)
+                w.attrs["value"] = rng.uniform(0.5, 2, 40)
+                o.set_parameters(prob.param_values())
+            ref = RefOracles(prob.folded())
+            np.testing.assert_array_equal(o.jacobianstructure()[0], ref.jacobianstructure()[0])
+            np.testing.assert_array_equal(o.hessianstructure()[1], ref.hessianstructure()[1])
+            assert_close(o.objective(xv), ref.objective(xv), "f")
+            assert_close(o.gradient(xv), ref.gradient(xv), "grad")
+            assert_close(o.constraints(xv), ref.constraints(xv), "g")
+            assert_close(o.jacobian(xv), ref.jacobian(xv), "jac")
+            assert_close(o.hessian(xv, lam, 0.6), ref.hessian(xv, lam, 0.6), "hess")
+            res = o.eval_all(xv, lam, 0.6)
+            assert_close(res["jac"], ref.jacobian(xv), "eval_all/jac")
+        # same x, same parameters: nothing x- or parameter-dependent is launched again
+        o.objective(xv)
+        l0 = o.kernel_launches()
+        o.objective(xv)
+        assert o.kernel_launches() - l0 <= 1
+        with pytest.raises(ValueError):
+            o.set_parameters(np.zeros(3))
+    finally:
+        o.close()

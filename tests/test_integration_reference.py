@@ -174,13 +174,18 @@ def test_reference_best_of_loop_compiles_once(cp, monkeypatch):
         np.testing.assert_array_equal(a, b)
 
 
-def test_parameter_values_are_compile_time_constants(cp, monkeypatch):
-    """A cvxpy Parameter reaches the oracle as a constant (the reference evaluates `.value` inside its
-    rules): the same value reuses the compiled oracle, a new value is a new fingerprint and a recompile
-    whose constants follow the parameter (Parameter slots are not built yet)."""
+def test_parameters_are_value_slots_no_recompile(cp, monkeypatch):
+    """cvxpy Parameters (expressions/constants/parameter.py:35) in sums and elementwise products become value
+    SLOTS of the tape: a new value re-arms the resident oracle (one small upload) instead of compiling a new
+    one, and every output follows the new value exactly as the reference's `.value`-reading rules do.  A
+    Parameter in a position that changes coefficient arrays (the matrix of a product with variables) is
+    frozen instead: a new value there is a new fingerprint."""
     import dnlp_b200.nlp_solver as gpu
     from dnlp_b200 import _cabi
+    from oracle.dnlp_oracle import RefOracles
     from tape_interp import TapeInterp
+
+    uploads = []
 
     class FakeDevice:
         def __init__(self, tape, device=0):
@@ -191,26 +196,65 @@ def test_parameter_values_are_compile_time_constants(cp, monkeypatch):
 
         def bind_outputs(self, *a, **k):
             pass
+
+        def set_params(self, values):
+            uploads.append(np.array(values, copy=True))
     monkeypatch.setattr(_cabi, "DeviceTape", FakeDevice)
     monkeypatch.setattr(_cabi, "pinned_empty", lambda k: (np.empty(k), types.SimpleNamespace(free=lambda: None)))
     gamma = cp.Parameter(nonneg=True)
     b = cp.Parameter(3)
     x = cp.Variable(3)
     x.value = np.array([0.3, 0.5, 0.2])
-    prob = cp.Problem(cp.Minimize(cp.sum(cp.exp(x)) + gamma * cp.sum_squares(x - b)), [cp.sum(x) == 1])
+    prob = cp.Problem(cp.Minimize(cp.sum(cp.exp(x)) + gamma * cp.sum_squares(x - b)),
+                      [cp.sum(x) == 1, cp.multiply(b, cp.exp(x)) <= 9 + gamma])
+    xv = np.array([0.3, 0.5, 0.2])
     with gpu.gpu_oracle():
         gpu.ORACLE_CACHE.hits = gpu.ORACLE_CACHE.misses = 0
-        gamma.value, b.value = 0.5, np.array([1.0, 2.0, 3.0])
+        # (np.float64, not float: the reference's multiply._hess_vec calls x.value.flatten, binary_operators.py:517)
+        gamma.value, b.value = np.float64(0.5), np.array([1.0, 2.0, 3.0])
         d1 = _chain(cp, prob)
         o1 = d1["oracles"]
-        f1 = TapeInterp(o1.tape).eval("f", d1["x0"])
-        assert _chain(cp, prob)["oracles"] is o1                          # same values: reused
-        gamma.value = 2.0
-        d2 = _chain(cp, prob)
-        o2 = d2["oracles"]
-        assert o2 is not o1 and gpu.ORACLE_CACHE.misses == 2
-        f2 = TapeInterp(o2.tape).eval("f", d2["x0"])
-    xv = np.array([0.3, 0.5, 0.2])
-    want = lambda g: np.exp(xv).sum() + g * ((xv - np.array([1.0, 2.0, 3.0])) ** 2).sum()   # noqa: E731
-    np.testing.assert_allclose(f1, want(0.5), rtol=1e-12)
-    np.testing.assert_allclose(f2, want(2.0), rtol=1e-12)
+        assert o1.tape.n_params == 4
+        it = TapeInterp(o1.tape)
+        ref = _chain_reference(cp, prob)
+        xv = np.asarray(d1["x0"], dtype=np.float64) * 1.05 + 0.01      # the smooth problem's point (aux variables too)
+        lam = np.linspace(-0.4, 0.6, len(d1["cl"]))
+        for gval, bval in ((0.5, [1.0, 2.0, 3.0]), (2.0, [1.0, 2.0, 3.0]), (0.1, [3.0, -1.0, 0.5])):
+            gamma.value, b.value = np.float64(gval), np.array(bval)
+            d = _chain(cp, prob)                                        # what prob.solve() does per solve
+            assert d["oracles"] is o1                                    # re-armed, never recompiled
+            np.testing.assert_array_equal(uploads[-1], np.concatenate([[gval], bval]) if o1.problem.params[0].size == 1
+                                          else np.concatenate([bval, [gval]]))
+            it.set_params(uploads[-1])
+            r = _chain_reference(cp, prob)["oracles"]
+            r.jacobianstructure(), r.hessianstructure()
+            np.testing.assert_allclose(it.eval("f", xv), r.objective(xv), rtol=1e-12)
+            np.testing.assert_allclose(it.eval("grad", xv), r.gradient(xv), rtol=1e-12)
+            np.testing.assert_allclose(it.eval("g", xv), r.constraints(xv), rtol=1e-12)
+            np.testing.assert_allclose(it.eval("jac", xv), np.asarray(r.jacobian(xv)).ravel(), rtol=1e-12)
+            np.testing.assert_allclose(it.eval("hess", xv, lam, 0.7), np.asarray(r.hessian(xv, lam, 0.7)).ravel(), rtol=1e-12)
+            # the CPU oracle sees the folded problem (parameters at their current values)
+            ro = RefOracles(d["oracles"].problem.folded())
+            np.testing.assert_allclose(ro.objective(xv), r.objective(xv), rtol=1e-12)
+        assert gpu.ORACLE_CACHE.misses == 1
+        # a parameter MATRIX multiplying variables is frozen: new value -> new tape
+        P = cp.Parameter((2, 3))
+        P.value = np.arange(6.0).reshape(2, 3)
+        prob2 = cp.Problem(cp.Minimize(cp.sum(cp.exp(P @ x))), [cp.sum(x) == 1])
+        oa = _chain(cp, prob2)["oracles"]
+        assert oa.tape.n_params == 0
+        P.value = P.value + 1.0
+        assert _chain(cp, prob2)["oracles"] is not oa
+
+
+def _chain_reference(cp, prob):
+    """The reference's own Oracles for the same problem (install() not active)."""
+    import importlib
+    mod = importlib.import_module("cvxpy.reductions.solvers.nlp_solvers.nlp_solver")
+    import dnlp_b200.nlp_solver as gpu
+    saved = mod.Oracles
+    mod.Oracles = gpu._saved.get("Oracles", saved)
+    try:
+        return _chain(cp, prob)
+    finally:
+        mod.Oracles = saved
