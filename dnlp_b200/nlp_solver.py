@@ -43,7 +43,9 @@ def gpu_oracles(problem, initial_point, num_constraints):
     return oracle
 
 
-def install(device=0):
+def install(device=0, duals=True):
+    """Rebind the reference's ``Oracles`` name to the GPU oracle.  ``duals``: also recover constraint duals
+    from the solver's multipliers (dnlp_b200/duals.py; the reference returns none, ipopt_nlpif.py:100)."""
     global DEVICE
     if device != DEVICE:
         ORACLE_CACHE.clear()       # resident oracles live on the previous device
@@ -52,12 +54,44 @@ def install(device=0):
     if "Oracles" not in _saved:
         _saved["Oracles"] = mod.Oracles
     mod.Oracles = gpu_oracles
+    if duals:
+        install_dual_recovery()
     return mod
 
 
+def install_dual_recovery():
+    """Wrap ``NLPsolver._prepare_data_and_inv_data`` (records which slice of g every constraint of the smooth
+    problem got) and the NLP solver interfaces' ``invert`` (fills ``Solution.dual_vars`` from ``mult_g``).
+    Independent of the GPU oracle: works with the reference's own ``Oracles`` too."""
+    from . import duals as D
+    mod = importlib.import_module(_REF_MODULE)
+    if "prepare" not in _saved:
+        orig_prepare = mod.NLPsolver._prepare_data_and_inv_data
+        _saved["prepare"] = orig_prepare
+
+        def prepare(self, problem):
+            problem_, data, inverse_data = orig_prepare(self, problem)
+            D.record(problem, inverse_data)
+            return problem_, data, inverse_data
+        mod.NLPsolver._prepare_data_and_inv_data = prepare
+    if "invert" not in _saved:
+        ipopt_mod = importlib.import_module("cvxpy.reductions.solvers.nlp_solvers.ipopt_nlpif")
+        orig_invert = ipopt_mod.IPOPT.invert
+        _saved["invert"] = orig_invert
+
+        def invert(self, solution, inverse_data):
+            return D.attach(orig_invert(self, solution, inverse_data), solution, inverse_data)
+        ipopt_mod.IPOPT.invert = invert
+
+
 def uninstall():
+    mod = importlib.import_module(_REF_MODULE)
     if "Oracles" in _saved:
-        importlib.import_module(_REF_MODULE).Oracles = _saved.pop("Oracles")
+        mod.Oracles = _saved.pop("Oracles")
+    if "prepare" in _saved:
+        mod.NLPsolver._prepare_data_and_inv_data = _saved.pop("prepare")
+    if "invert" in _saved:
+        importlib.import_module("cvxpy.reductions.solvers.nlp_solvers.ipopt_nlpif").IPOPT.invert = _saved.pop("invert")
     ORACLE_CACHE.clear()
 
 

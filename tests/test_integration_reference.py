@@ -258,3 +258,47 @@ def _chain_reference(cp, prob):
         return _chain(cp, prob)
     finally:
         mod.Oracles = saved
+
+
+def test_dual_recovery_through_the_reference_chain(cp):
+    """the reference returns no duals (ipopt_nlpif.py:100).  With install_dual_recovery()
+    the solver's constraint multipliers travel back through the reference's own invert chain
+    (canonicalization.py:76-84) to `constraint.dual_value`.  IPOPT is not installed, so the multipliers come
+    from the Newton-KKT stand-in driving the reference's own Oracles (same Lagrangian f + mult_g' g); the
+    recovered duals must make the ORIGINAL problem's Lagrangian stationary, with cvxpy's signs."""
+    import dnlp_b200.nlp_solver as gpu
+    import kkt_newton
+    from cvxpy.reductions.cvx_attr2constr import CvxAttr2Constr
+    from cvxpy.reductions.dnlp2smooth.dnlp2smooth import Dnlp2Smooth
+    from cvxpy.reductions.solvers.nlp_solvers.ipopt_nlpif import IPOPT
+    from cvxpy.reductions.solvers.solving_chain import SolvingChain
+    rng = np.random.default_rng(0)
+    n = 6
+    A = rng.standard_normal((2, n))
+    x = cp.Variable(n)
+    x.value = np.full(n, 0.3)
+    eq = A @ x == np.array([0.5, -0.2])
+    ineq = cp.sum(cp.exp(x)) >= 6.5                      # active at the optimum (treated as an equality by the stand-in)
+    prob = cp.Problem(cp.Minimize(cp.sum(cp.logistic(x)) + cp.sum_squares(x)), [eq, ineq])
+    gpu.install_dual_recovery()
+    try:
+        chain = SolvingChain(reductions=[CvxAttr2Constr(reduce_bounds=False), Dnlp2Smooth(), IPOPT()])
+        data, inverse_data = chain.apply(problem=prob)
+        o = data["oracles"]
+        xs, lam, f, iters = kkt_newton.solve(o, data["x0"], tol=1e-11)
+        info = {"status": 0, "x": xs, "obj_val": f, "mult_g": lam, "iterations": iters}
+        prob.unpack_results(info, chain, inverse_data)               # runs chain.invert: solver stage first
+    finally:
+        gpu.uninstall()
+    nu, mu = np.asarray(eq.dual_value, float), float(ineq.dual_value)
+    assert nu.shape == (2,) and mu > 0                   # an active inequality: nonnegative dual
+    xv = np.asarray(x.value, float)
+    assert abs(np.exp(xv).sum() - 6.5) < 1e-8
+    # stationarity of f + nu'(A x - b) + mu (6.5 - sum exp(x)) in the ORIGINAL variables
+    grad_f = np.exp(xv) / (1 + np.exp(xv)) + 2 * xv
+    resid = grad_f + A.T @ nu - mu * np.exp(xv)
+    assert np.linalg.norm(resid, np.inf) < 1e-7, resid
+    # without the hook the reference hands back no duals at all
+    data, inverse_data = chain.apply(problem=prob)
+    sol = chain.invert({"status": 0, "x": xs, "obj_val": f, "mult_g": lam, "iterations": iters}, inverse_data)
+    assert not sol.dual_vars
