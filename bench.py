@@ -631,7 +631,8 @@ def bench_multistart(args, grp, hbm_peak, peak_src):
         gemm_fl = float(sum(2.0 * o.tape.instrs[i].count * o.tape.instrs[i].ncols * B for i in gemm_ids))
         other_ms = float(sum(per[i] for i in o.tape.programs["all"] if i not in gemm_ids))
         step_ms = ms / (args.steps * E)
-        gemm_ms_grouped = max(step_ms - other_ms, 1e-9)
+        groups = o.profile_gemm_groups(iters=5)
+        gemm_ms_grouped = groups[0][0] if groups else max(step_ms - other_ms, 1e-9)
         hess_bytes = 8.0 * o.nnz_hess * B
         t_min = gemm_fl / (FP64_TENSOR_PEAK * 1e12) + hess_bytes / (hbm_peak * 1e9)
         top = int(np.argmax(per))
@@ -655,11 +656,12 @@ def bench_multistart(args, grp, hbm_peak, peak_src):
                "evals_per_step": E * Btot, "batches_per_step": E, "ms_per_batch": step_ms,
                "config": dict(config_of("c4", world, args.scale), starts_per_gpu=B), "clocks": clocks, "parity": parity,
                "gpu_launches": int(launches), "roofline": roof,
-               "dmma": {"gemm_tflops_grouped_launch_est": gemm_fl / (gemm_ms_grouped * 1e-3) / 1e12,
+               "dmma": {"gemm_tflops_grouped_launch": gemm_fl / (gemm_ms_grouped * 1e-3) / 1e12,
+                        "gemm_ms_grouped_launch": gemm_ms_grouped,
                         "gemm_tflops_individual_launches":
                             gemm_fl / max(float(sum(per[i] for i in gemm_ids)) * 1e-3, 1e-12) / 1e12,
-                        "note": "the k+1 independent maps run as ONE grouped grid inside the step; its time is the step "
-                                "time minus the other instructions' own times",
+                        "note": "the k+1 independent maps run as ONE grouped grid inside the step, timed on its own with "
+                                "CUDA events (dnlp_batch_profile_groups)",
                         "peak_measured_tflops": FP64_TENSOR_PEAK, "peak_source": FP64_TENSOR_PEAK_SRC,
                         "cublas_same_shape_tflops": 27.3},
                "roofline_whole_batch": {"t_min_ms": t_min * 1e3, "frac": t_min * 1e3 / step_ms,

@@ -72,6 +72,10 @@ struct dnlp_batch {
   struct MaskGraph { cudaGraphExec_t exec = nullptr; int64_t nlaunch = 0; };
   MaskGraph graphs[64];
   bool graphs_enabled = true;
+  bool dmma_k8 = false;          // m16n8k8 DMMA shape instead of m8n8k4 (A/B: DNLP_DMMA_K8)
+  double *split_scratch = nullptr;         // partial sums of the term-split long-row kernel
+  unsigned int *split_tickets = nullptr;
+  int64_t split_scratch_len = 0, split_ticket_len = 0;
   int launch(const BInstr &I);
   int run_program(int p);
   int run_union(int32_t prog_mask);
@@ -140,6 +144,18 @@ int dnlp_batch::launch(const BInstr &I) {
       }
       if (d.count > 0 && d.nterms / d.count >= 128) {
         const int64_t blocks = d.count * ((B + 31) / 32);
+        // very few (row, start-chunk) pairs: the terms of a row are split over KS CTAs as well
+        const int64_t mean_terms = d.nterms / d.count;
+        int KS = (int)((int64_t)sm_count * 2 / (blocks > 0 ? blocks : 1));
+        if (KS > mean_terms / 32) KS = (int)(mean_terms / 32);
+        if (KS > 32) KS = 32;
+        if (KS >= 2 && (int64_t)KS * d.count * B <= split_scratch_len && blocks <= split_ticket_len) {
+          if (I.has_f2)
+            bpoly_long_split_kernel<true, 8><<<(int)(blocks * KS), 256, 0, stream>>>(V, dst, d.ptr, d.row_len, d.coef, d.f1, d.f2, d.pos, d.count, d.accumulate, B, KS, split_scratch, split_tickets);
+          else
+            bpoly_long_split_kernel<false, 8><<<(int)(blocks * KS), 256, 0, stream>>>(V, dst, d.ptr, d.row_len, d.coef, d.f1, d.f2, d.pos, d.count, d.accumulate, B, KS, split_scratch, split_tickets);
+          break;
+        }
         // few (row, start-chunk) pairs: 16 warps split the terms; enough of them to fill the machine: 8
         if (blocks <= (int64_t)sm_count * 2) {
           if (I.has_f2)
@@ -170,7 +186,10 @@ int dnlp_batch::launch(const BInstr &I) {
       // (a GEMV that belongs to a group never reaches here: run_union launches the group once)
       const int tiles = (int)(((d.count + GM - 1) / GM) * ((B + GN - 1) / GN));
       const int cap = sm_count * 4;
-      bgemm_dmma_kernel<<<tiles < cap ? tiles : cap, 128, BGEMM_SMEM, stream>>>(I.one_desc, 1, (int)d.count, B, (int)d.ncols);
+      if (dmma_k8)
+        bgemm_dmma_kernel<true><<<tiles < cap ? tiles : cap, 128, BGEMM_SMEM, stream>>>(I.one_desc, 1, (int)d.count, B, (int)d.ncols);
+      else
+        bgemm_dmma_kernel<false><<<tiles < cap ? tiles : cap, 128, BGEMM_SMEM, stream>>>(I.one_desc, 1, (int)d.count, B, (int)d.ncols);
       break;
     }
     case DNLP_SCALE:
@@ -229,8 +248,12 @@ int dnlp_batch::issue_union(int32_t prog_mask) {
       GemmGroup &G = groups[gi];
       const int64_t tiles = ((G.M + GM - 1) / GM) * ((B + GN - 1) / GN) * (int64_t)G.members.size();
       const int64_t cap = (int64_t)sm_count * 4;
-      bgemm_dmma_kernel<<<(int)(tiles < cap ? tiles : cap), 128, BGEMM_SMEM, stream>>>(
-          G.descs, (int)G.members.size(), (int)G.M, B, (int)G.K);
+      if (dmma_k8)
+        bgemm_dmma_kernel<true><<<(int)(tiles < cap ? tiles : cap), 128, BGEMM_SMEM, stream>>>(
+            G.descs, (int)G.members.size(), (int)G.M, B, (int)G.K);
+      else
+        bgemm_dmma_kernel<false><<<(int)(tiles < cap ? tiles : cap), 128, BGEMM_SMEM, stream>>>(
+            G.descs, (int)G.members.size(), (int)G.M, B, (int)G.K);
       ++launches;
       cudaError_t e = cudaPeekAtLastError();
       if (e != cudaSuccess) { err = std::string("kernel launch failed: ") + cudaGetErrorString(e); return 1; }
@@ -308,6 +331,15 @@ static int batch_create_impl(dnlp_batch *o, const dnlp_tape_desc *t) {
     o->out[s] = static_cast<double *>(p);
     if (lens[s] > 0 && consts[s]) { if (o->upload(consts[s], lens[s], &o->out_const[s])) return 1; }
   }
+  o->split_scratch_len = (int64_t)32 * 64 * B;          // KS <= 32 slices x up to 64 long rows x B starts
+  o->split_ticket_len = 64 * (int64_t)((B + 31) / 32) + 64;
+  CKB(cudaMalloc(&p, (size_t)o->split_scratch_len * sizeof(double)));
+  o->owned.push_back(p);
+  o->split_scratch = static_cast<double *>(p);
+  CKB(cudaMalloc(&p, (size_t)o->split_ticket_len * sizeof(unsigned int)));
+  o->owned.push_back(p);
+  o->split_tickets = static_cast<unsigned int *>(p);
+  CKB(cudaMemset(o->split_tickets, 0, (size_t)o->split_ticket_len * sizeof(unsigned int)));
   o->stage_len = maxlen + 2;
   CKB(cudaMalloc(&p, (size_t)o->stage_len * B * sizeof(double)));
   o->owned.push_back(p);
@@ -372,8 +404,10 @@ static int batch_create_impl(dnlp_batch *o, const dnlp_tape_desc *t) {
     if (o->upload(hd.data(), (int64_t)hd.size(), &G.descs)) return 1;
   }
   if (const char *e = getenv("DNLP_BATCH_NO_GRAPHS")) o->graphs_enabled = atoi(e) == 0;
+  if (const char *e = getenv("DNLP_DMMA_K8")) o->dmma_k8 = atoi(e) != 0;
   if (o->reset_outputs()) return 1;
-  CKB(cudaFuncSetAttribute(dnlp::bgemm_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dnlp::BGEMM_SMEM));
+  CKB(cudaFuncSetAttribute(dnlp::bgemm_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dnlp::BGEMM_SMEM));
+  CKB(cudaFuncSetAttribute(dnlp::bgemm_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dnlp::BGEMM_SMEM));
   CKB(cudaStreamSynchronize(o->stream));
   return 0;
 }
@@ -482,6 +516,36 @@ int dnlp_batch_profile_instrs(dnlp_batch *o, int32_t p, int32_t iters, float *ms
       ms_per_instr[id] += ms / (float)iters;
     }
   return 0;
+}
+
+// CUDA-event time of every GROUPED GEMM launch (the k+1 independent quad_form maps of a QCQP as one grid):
+// ms_per_group[g], flops_per_group[g]; returns the number of groups (<= max_groups) or -1.
+int dnlp_batch_profile_groups(dnlp_batch *o, int32_t iters, float *ms_per_group, double *flops_per_group, int32_t max_groups) {
+  if (o == nullptr) { g_batch_create_error = "batch handle is NULL (closed or never created)"; return -1; }
+  if (cudaSetDevice(o->device) != cudaSuccess) return -1;
+  int ng = 0;
+  for (size_t gi = 0; gi < o->groups.size() && ng < max_groups; ++gi) {
+    auto &G = o->groups[gi];
+    if (G.members.size() < 2) continue;
+    const int64_t tiles = ((G.M + dnlp::GM - 1) / dnlp::GM) * ((o->B + dnlp::GN - 1) / dnlp::GN) * (int64_t)G.members.size();
+    const int64_t cap = (int64_t)o->sm_count * 4;
+    const int grid = (int)(tiles < cap ? tiles : cap);
+    auto go = [&]() {
+      if (o->dmma_k8) dnlp::bgemm_dmma_kernel<true><<<grid, 128, dnlp::BGEMM_SMEM, o->stream>>>(G.descs, (int)G.members.size(), (int)G.M, o->B, (int)G.K);
+      else dnlp::bgemm_dmma_kernel<false><<<grid, 128, dnlp::BGEMM_SMEM, o->stream>>>(G.descs, (int)G.members.size(), (int)G.M, o->B, (int)G.K);
+    };
+    go();
+    cudaEventRecord(o->ev0, o->stream);
+    for (int it = 0; it < iters; ++it) go();
+    cudaEventRecord(o->ev1, o->stream);
+    if (cudaEventSynchronize(o->ev1) != cudaSuccess) return -1;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, o->ev0, o->ev1);
+    ms_per_group[ng] = ms / (float)(iters > 0 ? iters : 1);
+    flops_per_group[ng] = 2.0 * (double)G.M * (double)G.K * (double)o->B * (double)G.members.size();
+    ++ng;
+  }
+  return ng;
 }
 
 int64_t dnlp_batch_kernel_launches(dnlp_batch *o) { return o ? o->launches : -1; }

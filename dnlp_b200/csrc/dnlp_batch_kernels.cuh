@@ -63,7 +63,7 @@ bsmallk_kernel(const double *__restrict__ V, double *__restrict__ dst, const dou
                const int32_t *__restrict__ slots, const int32_t *__restrict__ pos, int64_t count,
                int accumulate, int B, int rows_per_block) {
   constexpr int TR = 64;                       // coefficient rows staged per shared-memory tile
-  __shared__ double ctile[2][TR * L];
+  __shared__ __align__(16) double ctile[2][TR * L];
   const int bchunks = (B + blockDim.x * NB - 1) / (blockDim.x * NB);
   const int64_t rblocks = (count + rows_per_block - 1) / rows_per_block;
   for (int64_t blk = blockIdx.x; blk < rblocks * bchunks; blk += gridDim.x) {
@@ -96,7 +96,35 @@ bsmallk_kernel(const double *__restrict__ V, double *__restrict__ dst, const dou
       const int nr = (int)(r1 - rs < TR ? r1 - rs : TR);
       const double *c = ctile[buf];
       double *__restrict__ out = dst + (pos ? 0 : rs * (int64_t)B) + b0;
-      for (int rr = 0; rr < nr; ++rr, c += L) {
+      int rr = 0;
+      if (NB <= 2 && !pos) {
+        // few starts per thread: two coefficient rows per pass (their 2L doubles are 16-byte aligned pairs in the
+        // tile), so that 2 x NB stores are in flight per thread and the broadcast loads are 128-bit
+        for (; rr + 2 <= nr; rr += 2, c += 2 * L) {
+          double a0[NB], a1[NB];
+#pragma unroll
+          for (int u = 0; u < NB; ++u) a0[u] = a1[u] = 0.0;
+          double cc[2 * L];
+#pragma unroll
+          for (int j = 0; j < L; ++j) {
+            const double2 v = *reinterpret_cast<const double2 *>(c + 2 * j);
+            cc[2 * j] = v.x; cc[2 * j + 1] = v.y;
+          }
+#pragma unroll
+          for (int j = 0; j < L; ++j)
+#pragma unroll
+            for (int u = 0; u < NB; ++u) { a0[u] = fma(cc[j], lam[j][u], a0[u]); a1[u] = fma(cc[L + j], lam[j][u], a1[u]); }
+          double *__restrict__ o0 = out + (int64_t)rr * B;
+#pragma unroll
+          for (int u = 0; u < NB; ++u) {
+            if (b0 + u * (int)blockDim.x < B) {
+              if (accumulate) { o0[u * blockDim.x] += a0[u]; o0[B + u * blockDim.x] += a1[u]; }
+              else { __stcs(o0 + u * blockDim.x, a0[u]); __stcs(o0 + B + u * blockDim.x, a1[u]); }
+            }
+          }
+        }
+      }
+      for (; rr < nr; ++rr, c += L) {
         double acc[NB];
 #pragma unroll
         for (int u = 0; u < NB; ++u) acc[u] = 0.0;
@@ -175,6 +203,77 @@ bpoly_long_kernel(const double *__restrict__ V, double *__restrict__ dst, const 
   }
 }
 
+// The same with the TERMS of a row also split over KS CTAs: a slice of 512 starts per GPU has only
+// rows x 16 (row, start-chunk) pairs - 16 CTAs for the objective row - so the term loop was the floor of small
+// batches (0.028 ms for f, 0.034 ms for g at B = 512).  Every CTA writes its partial sums to scratch; the last
+// one to arrive for a (row, start-chunk) pair adds the KS partials in slice order (deterministic) and stores.
+template <bool HAS_F2, int NW>
+__global__ void __launch_bounds__(NW * 32)
+bpoly_long_split_kernel(const double *__restrict__ V, double *__restrict__ dst, const int64_t *__restrict__ ptr,
+                        int row_len, const double *__restrict__ coef, const int32_t *__restrict__ f1,
+                        const int32_t *__restrict__ f2, const int32_t *__restrict__ pos, int64_t count,
+                        int accumulate, int B, int KS, double *__restrict__ scratch, unsigned int *__restrict__ tickets) {
+  __shared__ double part[NW][33];
+  __shared__ bool last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int bchunks = (B + 31) / 32;
+  const int64_t blk = blockIdx.x;
+  const int ks = (int)(blk % KS);
+  const int64_t pair = blk / KS;                    // (row, start-chunk)
+  const int64_t row = pair / bchunks;
+  const int b = (int)(pair - row * bchunks) * 32 + lane;
+  int64_t t0, t1;
+  if (ptr) { t0 = __ldg(ptr + row); t1 = __ldg(ptr + row + 1); }
+  else { t0 = row * (int64_t)row_len; t1 = t0 + row_len; }
+  const int64_t slice = (t1 - t0 + KS - 1) / KS;
+  const int64_t s0 = t0 + ks * slice, s1 = s0 + slice < t1 ? s0 + slice : t1;
+  double acc = 0.0;
+  if (b < B) {
+    constexpr int U = 4;
+    for (int64_t t = s0 + warp; t < s1; t += (int64_t)U * NW) {
+      int i1[U], i2[U];
+      double c[U], v1[U], v2[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t tt = t + (int64_t)u * NW;
+        const bool ok = tt < s1;
+        i1[u] = ok ? __ldg(f1 + tt) : -1;
+        i2[u] = (HAS_F2 && ok) ? __ldg(f2 + tt) : -1;
+        c[u] = ok ? __ldg(coef + tt) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        v1[u] = i1[u] >= 0 ? V[(int64_t)i1[u] * B + b] : 1.0;
+        v2[u] = (HAS_F2 && i2[u] >= 0) ? V[(int64_t)i2[u] * B + b] : 1.0;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) acc += HAS_F2 ? c[u] * v1[u] * v2[u] : c[u] * v1[u];
+    }
+  }
+  part[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) t += part[w][lane];
+    if (b < B) scratch[((int64_t)ks * count + row) * B + b] = t;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(tickets + pair, 1u) == (unsigned)KS - 1;
+  __syncthreads();
+  if (last && warp == 0) {
+    __threadfence();
+    if (b < B) {
+      double t = 0.0;
+      for (int k = 0; k < KS; ++k) t += __ldcg(scratch + ((int64_t)k * count + row) * B + b);
+      const int64_t d = (pos ? (int64_t)__ldg(pos + row) : row) * B + b;
+      dst[d] = accumulate ? dst[d] + t : t;
+    }
+    if (lane == 0) tickets[pair] = 0;
+  }
+}
+
 static __global__ void __launch_bounds__(256)
 bscale_kernel(const double *__restrict__ V, int64_t s_slot, const double *__restrict__ coef,
               double *__restrict__ dst, const int32_t *__restrict__ pos, int64_t count, int accumulate, int B) {
@@ -246,6 +345,13 @@ __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, do
                : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
+// sm_90+ shape: 16 x 8 x 8 per instruction (4x the work of m8n8k4 per issue slot and per operand fetch)
+__device__ __forceinline__ void dmma_m16n8k8(double (&d)[4], const double (&a)[4], const double (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+d"(d[0]), "+d"(d[1]), "+d"(d[2]), "+d"(d[3])
+               : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(b[0]), "d"(b[1]));
+}
+
 constexpr int GM = 64, GN = 64, GK = 16;
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
@@ -274,7 +380,8 @@ struct GemmDesc {
 // Grouped launch: the k+1 independent quad_form maps of a QCQP (9 x [512x512]x[512x4096]) fill the
 // machine as one grid of 4608 tiles instead of nine grids of 512 (512 tiles on 592 CTA slots waste
 // 14 % of the tensor pipe to quantisation).
-static __global__ void __launch_bounds__(128)
+template <bool K8>
+__global__ void __launch_bounds__(128)
 bgemm_dmma_kernel(const GemmDesc *__restrict__ descs, int ngroups, int M, int N, int K) {
   extern __shared__ __align__(16) double gsm[];
   double (*As)[GM][GA_LD] = reinterpret_cast<double (*)[GM][GA_LD]>(gsm);
@@ -295,7 +402,8 @@ bgemm_dmma_kernel(const GemmDesc *__restrict__ descs, int ngroups, int M, int N,
     const bool aligned = (K & 1) == 0 && (N & 1) == 0 &&
                          ((reinterpret_cast<uintptr_t>(Q) | reinterpret_cast<uintptr_t>(X)) & 15) == 0;
     const int m0 = (tile / tiles_n) * GM, n0 = (tile % tiles_n) * GN;
-    double acc[4][4][2];
+    double acc[4][4][2];                 // m8n8k4: [m-tile of 8][n-tile of 8][2];  m16n8k8: viewed as [2][4][4]
+    double (*acc16)[4][4] = reinterpret_cast<double (*)[4][4]>(&acc[0][0][0]);
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -335,30 +443,68 @@ bgemm_dmma_kernel(const GemmDesc *__restrict__ descs, int ngroups, int M, int N,
       if (ks + GSTAGES - 1 < ksteps) load_tiles((ks + GSTAGES - 1) % GSTAGES, (ks + GSTAGES - 1) * GK);
       cp_async_commit();
       const int buf = ks % GSTAGES;
+      if (K8) {
 #pragma unroll
-      for (int kk = 0; kk < GK; kk += 4) {
-        double a[4], b[4];
+        for (int kk = 0; kk < GK; kk += 8) {
+          double a[2][4], b[4][2];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = As[buf][wm + i * 8 + g][kk + tg];
+          for (int i = 0; i < 2; ++i) {
+            a[i][0] = As[buf][wm + i * 16 + g][kk + tg];
+            a[i][1] = As[buf][wm + i * 16 + g + 8][kk + tg];
+            a[i][2] = As[buf][wm + i * 16 + g][kk + tg + 4];
+            a[i][3] = As[buf][wm + i * 16 + g + 8][kk + tg + 4];
+          }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) b[j] = Bs[buf][kk + tg][wn + j * 8 + g];
+          for (int j = 0; j < 4; ++j) {
+            b[j][0] = Bs[buf][kk + tg][wn + j * 8 + g];
+            b[j][1] = Bs[buf][kk + tg + 4][wn + j * 8 + g];
+          }
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+          for (int i = 0; i < 2; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+            for (int j = 0; j < 4; ++j) dmma_m16n8k8(acc16[i][j], a[i], b[j]);
+        }
+      } else {
+#pragma unroll
+        for (int kk = 0; kk < GK; kk += 4) {
+          double a[4], b[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) a[i] = As[buf][wm + i * 8 + g][kk + tg];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) b[j] = Bs[buf][kk + tg][wn + j * 8 + g];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
       }
     }
     cp_async_wait<0>();
+    if (K8) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 2; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int r = m0 + wm + i * 8 + g, c = n0 + wn + j * 8 + tg * 2;
-        if (r < M) {
-          if (c < N) Y[(int64_t)r * N + c] = alpha * acc[i][j][0];
-          if (c + 1 < N) Y[(int64_t)r * N + c + 1] = alpha * acc[i][j][1];
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int r = m0 + wm + i * 16 + g + h * 8, c = n0 + wn + j * 8 + tg * 2;
+            if (r < M) {
+              if (c < N) Y[(int64_t)r * N + c] = alpha * acc16[i][j][2 * h];
+              if (c + 1 < N) Y[(int64_t)r * N + c + 1] = alpha * acc16[i][j][2 * h + 1];
+            }
+          }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int r = m0 + wm + i * 8 + g, c = n0 + wn + j * 8 + tg * 2;
+          if (r < M) {
+            if (c < N) Y[(int64_t)r * N + c] = alpha * acc[i][j][0];
+            if (c + 1 < N) Y[(int64_t)r * N + c + 1] = alpha * acc[i][j][1];
+          }
         }
-      }
+    }
   }
 }
 

@@ -860,8 +860,13 @@ __device__ __forceinline__ void fused_tile(double *__restrict__ V, const ElemDes
   for (int o = 0; o < d.nout; ++o)
     want_val = want_val || d.fcode[o] == F_LOGISTIC || d.fcode[o] == F_TANH || d.fcode[o] == F_TANH_D2;
   if (vec_ok) {
-    for (int64_t k = e0 + 2 * threadIdx.x; k < e1; k += 512) {
-      const double2 a = *reinterpret_cast<const double2 *>(A + k);
+    // software pipeline: the next 16-byte load is issued before the (long, dependent) fp64 chains of the current
+    // pair start - the kernel was latency-bound at 24 warps per SM (ncu: fp64 pipe 16 %, issue 39 %,
+    // long-scoreboard stalls), and a second set of results in registers would spill
+    int64_t k = e0 + 2 * threadIdx.x;
+    double2 a = k < e1 ? *reinterpret_cast<const double2 *>(A + k) : make_double2(0.0, 0.0);
+    for (; k < e1; k += 512) {
+      const double2 an = k + 512 < e1 ? *reinterpret_cast<const double2 *>(A + k + 512) : a;
       double rx[3], ry[3];
       fused_point<GRP>(a.x, d, want_val, rx);
       fused_point<GRP>(a.y, d, want_val, ry);
@@ -869,6 +874,7 @@ __device__ __forceinline__ void fused_tile(double *__restrict__ V, const ElemDes
       for (int o = 0; o < 3; ++o)
         if (o < d.nout)
           *reinterpret_cast<double2 *>(V + d.dst_off[o] + k) = make_double2(d.scale[o] * rx[o], d.scale[o] * ry[o]);
+      a = an;
     }
   } else {
     // value and first derivative of a pair region land next to each other: one 16-byte store per element
@@ -903,17 +909,20 @@ __device__ __forceinline__ void elem_tile(double *__restrict__ V, const ElemDesc
   const double p = d.param[o], sc = d.scale[o];
   const int ds = d.dst_stride[o];
   if (vec_ok) {
-    for (int64_t k = e0 + 2 * threadIdx.x; k < e1; k += 512) {
-      const double2 a = *reinterpret_cast<const double2 *>(A + k);
-      double2 b = make_double2(0.0, 0.0);
-      if (F >= F_REL_ENTR) {
-        if (d.b_stride == 1) b = *reinterpret_cast<const double2 *>(B + k);
-        else b = make_double2(B[0], B[0]);
-      }
+    int64_t k = e0 + 2 * threadIdx.x;                               // next load in flight during the math (see fused_tile)
+    const bool bvec = F >= F_REL_ENTR && d.b_stride == 1;
+    double2 a = k < e1 ? *reinterpret_cast<const double2 *>(A + k) : make_double2(0.0, 0.0);
+    double2 b = make_double2(0.0, 0.0);
+    if (F >= F_REL_ENTR) b = bvec ? (k < e1 ? *reinterpret_cast<const double2 *>(B + k) : b) : make_double2(B[0], B[0]);
+    for (; k < e1; k += 512) {
+      const bool more = k + 512 < e1;
+      const double2 an = more ? *reinterpret_cast<const double2 *>(A + k + 512) : a;
+      const double2 bn = (bvec && more) ? *reinterpret_cast<const double2 *>(B + k + 512) : b;
       double2 r;
       r.x = sc * apply_fn<F>(a.x, b.x, p);
       r.y = sc * apply_fn<F>(a.y, b.y, p);
       *reinterpret_cast<double2 *>(D + k) = r;
+      a = an; b = bn;
     }
   } else {
     for (int64_t k = e0 + threadIdx.x; k < e1; k += 256)

@@ -82,5 +82,15 @@ class BatchedOracles:
                                                             out.ctypes.data_as(_cabi.c_f32p)))
         return out[:len(self.tape.instrs)]
 
+    def profile_gemm_groups(self, iters=5):
+        """[(ms, TFLOP/s)] of every grouped DMMA GEMM launch (independent dense maps of one shape as one grid)."""
+        ms = np.zeros(8, dtype=np.float32)
+        fl = np.zeros(8, dtype=np.float64)
+        n = self.dev._L.dnlp_batch_profile_groups(self.dev.h, int(iters), ms.ctypes.data_as(_cabi.c_f32p),
+                                                  fl.ctypes.data_as(_cabi.c_f64p), 8)
+        if n < 0:
+            raise RuntimeError("dnlp_batch_profile_groups failed")
+        return [(float(ms[i]), float(fl[i] / (ms[i] * 1e-3) / 1e12) if ms[i] > 0 else 0.0) for i in range(n)]
+
     def kernel_launches(self):
         return int(self.dev._L.dnlp_batch_kernel_launches(self.dev.h))

@@ -194,6 +194,8 @@ int dnlp_batch_eval(dnlp_batch *b, const double *X, const double *LAM, const dou
 int dnlp_batch_upload(dnlp_batch *b, const double *X, const double *LAM, const double *SIGMA);
 int dnlp_batch_run_device(dnlp_batch *b, int32_t prog_mask, int32_t iters, float *elapsed_ms);
 int dnlp_batch_profile_instrs(dnlp_batch *b, int32_t prog, int32_t iters, float *ms_per_instr);
+int dnlp_batch_profile_groups(dnlp_batch *b, int32_t iters, float *ms_per_group, double *flops_per_group,
+                              int32_t max_groups);   /* grouped DMMA GEMM launches, timed with CUDA events */
 int64_t dnlp_batch_kernel_launches(dnlp_batch *b);
 
 /* ---- row-sharded evaluation across the GPUs of one node (BASELINE config 3) ----

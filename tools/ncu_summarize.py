@@ -3,9 +3,9 @@
 
     python tools/ncu_summarize.py c2 [c3 c5 ...]
 
-  gpurun_out/launches_<w>.csv  -> profiles/r01_<w>_launches.csv (copy) + r01_<w>_launch_shares.txt
-  gpurun_out/prof_<w>_raw.csv  -> profiles/r01_<w>_ncu_full_summary.csv and the per-kernel DRAM
-                                  traffic table profiles/r01_ncu_traffic.json that bench.py reads
+  gpurun_out/launches_<w>.csv  -> profiles/r02_<w>_launches.csv (copy) + r02_<w>_launch_shares.txt
+  gpurun_out/prof_<w>_raw.csv  -> profiles/r02_<w>_ncu_full_summary.csv and the per-kernel DRAM
+                                  traffic table profiles/r02_ncu_traffic.json that bench.py reads
 """
 import csv
 import json
@@ -45,7 +45,7 @@ def launches(w):
     src = os.path.join(OUT, "launches_%s.csv" % w)
     if not os.path.exists(src):
         return
-    shutil.copy(src, os.path.join(PROF, "r01_%s_launches.csv" % w))
+    shutil.copy(src, os.path.join(PROF, "r02_%s_launches.csv" % w))
     rows = [r for r in csv.reader(l for l in open(src) if l.startswith('"'))]
     hdr = rows[0]
     k, v, u = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
@@ -56,7 +56,7 @@ def launches(w):
         a[0] += 1
         a[1] += t
     total = sum(a[1] for a in agg.values())
-    with open(os.path.join(PROF, "r01_%s_launch_shares.txt" % w), "w") as f:
+    with open(os.path.join(PROF, "r02_%s_launch_shares.txt" % w), "w") as f:
         f.write("# ncu --metrics gpu__time_duration.sum --clock-control none, python bench.py --device-only --steps 2 --warmup 3 (%s)\n" % w)
         f.write("# per-launch times are cold-cache and serialised: compare SHARES with bench.py's roofline.share_of_step\n")
         for name, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -71,7 +71,7 @@ def full(w, traffic):
     hdr, units = rows[0], rows[1]
     idx = {c: hdr.index(c) for c in COLS if c in hdr}
     kcol = hdr.index("Kernel Name")
-    with open(os.path.join(PROF, "r01_%s_ncu_full_summary.csv" % w), "w", newline="") as f:
+    with open(os.path.join(PROF, "r02_%s_ncu_full_summary.csv" % w), "w", newline="") as f:
         wr = csv.writer(f)
         wr.writerow(["Kernel Name"] + list(idx))
         wr.writerow([""] + [units[i] for i in idx.values()])
@@ -94,7 +94,7 @@ def full(w, traffic):
 
 
 def main():
-    tj = os.path.join(PROF, "r01_ncu_traffic.json")
+    tj = os.path.join(PROF, "r02_ncu_traffic.json")
     traffic = json.load(open(tj)) if os.path.exists(tj) else {}
     for w in sys.argv[1:]:
         launches(w)
