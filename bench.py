@@ -397,6 +397,8 @@ def roofline_of(o, name, sizes, hbm_peak, peak_src):
         quantity = "g"
     elif ins.kind == 2 and ins.dst_space == 4 and nterms >= nnz > 0:
         quantity = "J"
+    elif ins.kind == 2 and ins.dst_space == 5 and nterms >= nnz > 0:
+        quantity = "H"
     if quantity == "g+J" and "g" in sb:
         alg, src = sb["g"] + sb["J"], "SURVEY 8(d): quantities g + J of this config (one fused kernel)"
     elif quantity and quantity in sb:
