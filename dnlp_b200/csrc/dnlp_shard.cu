@@ -29,6 +29,8 @@ namespace {
 constexpr int MAXW = 16;                       // ranks per node supported by the exchange area
 constexpr int64_t P2P_MAX = 16384;             // doubles per rank slice of the one-shot all-reduce
 constexpr int NSPACE = 6;
+constexpr int NSLOT = 4;                       // exchange slices per rank, indexed by epoch & 3: with the reduce of
+                                               // epoch e deferred behind the push of e + 1 a peer can be two epochs ahead
 
 struct AreaHeader {
   unsigned long long flag[MAXW];               // flag[r]: last epoch rank r finished pushing to this rank
@@ -36,7 +38,7 @@ struct AreaHeader {
   unsigned long long pad[8];
 };
 constexpr size_t AREA_SLOTS_OFF = 512;         // >= sizeof(AreaHeader), 16-byte aligned
-constexpr size_t AREA_BYTES = AREA_SLOTS_OFF + (size_t)2 * MAXW * P2P_MAX * sizeof(double);
+constexpr size_t AREA_BYTES = AREA_SLOTS_OFF + (size_t)NSLOT * MAXW * P2P_MAX * sizeof(double);
 static_assert(sizeof(AreaHeader) <= AREA_SLOTS_OFF, "exchange header too large");
 
 thread_local std::string g_comm_error;
@@ -96,8 +98,8 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ double *area_slice(char *area, int parity, int rank) {
-  return reinterpret_cast<double *>(area + AREA_SLOTS_OFF) + ((int64_t)parity * MAXW + rank) * P2P_MAX;
+__device__ __forceinline__ double *area_slice(char *area, int slot, int rank) {
+  return reinterpret_cast<double *>(area + AREA_SLOTS_OFF) + ((int64_t)slot * MAXW + rank) * P2P_MAX;
 }
 // spin until *p >= want; false (and *error = code) once `timeout` GPU clocks have passed
 __device__ __forceinline__ bool wait_ge(const unsigned long long *p, unsigned long long want, int *error, int code,
@@ -117,13 +119,12 @@ __device__ __forceinline__ bool wait_ge(const unsigned long long *p, unsigned lo
 //   3. the last CTA to finish publishes flag[rank] = e in every peer's area.
 __global__ void __launch_bounds__(256)
 shard_push_kernel(const double *__restrict__ out, char *const *__restrict__ peer_area, int rank, int world, int root,
-                  const unsigned long long *__restrict__ epoch_ctr,
+                  const unsigned long long e,
                   const int32_t *__restrict__ sh_src, int64_t n_sh_total,
                   const int32_t *__restrict__ ow_pos, const int32_t *__restrict__ ow_gpos, int64_t n_ow,
                   double *__restrict__ root_gout, int space, unsigned long long credit_needed,
                   unsigned int *__restrict__ ticket, int *__restrict__ error, long long timeout) {
-  const unsigned long long e = *epoch_ctr + 1;
-  const int parity = (int)(e & 1);
+  const int parity = (int)(e & (NSLOT - 1));
   __shared__ bool go;
   if (threadIdx.x == 0) {
     go = true;
@@ -160,11 +161,10 @@ shard_push_kernel(const double *__restrict__ out, char *const *__restrict__ peer
 //      keeps this rank's own contribution, which the x-keyed cache may reuse in the next exchange.
 __global__ void __launch_bounds__(1024)
 shard_reduce_kernel(const double *__restrict__ out, char *const *__restrict__ peer_area, int rank, int world, int root,
-                    unsigned long long *__restrict__ epoch_ctr, const int32_t *__restrict__ sh_src, int64_t n_sh_total,
+                    const unsigned long long e, const int32_t *__restrict__ sh_src, int64_t n_sh_total,
                     const int32_t *__restrict__ sh_gpos, double *__restrict__ root_gout, double *__restrict__ sums,
                     int *__restrict__ error, long long timeout) {
-  const unsigned long long e = *epoch_ctr + 1;
-  const int parity = (int)(e & 1);
+  const int parity = (int)(e & (NSLOT - 1));
   char *mine = peer_area[rank];
   if ((int)threadIdx.x < world)
     wait_ge(&reinterpret_cast<const AreaHeader *>(mine)->flag[threadIdx.x], e, error, 1, timeout);
@@ -175,8 +175,6 @@ shard_reduce_kernel(const double *__restrict__ out, char *const *__restrict__ pe
     if (sums) sums[k] = acc;
     if (rank == root && root_gout) root_gout[sh_gpos[k]] = acc;
   }
-  __syncthreads();
-  if (threadIdx.x == 0) *epoch_ctr = e;
 }
 
 // the root tells every peer that output `space` of epoch e has left for the host
@@ -225,6 +223,7 @@ struct dnlp_shard {
   int root = 0;
   ShardOut out[NSPACE];
   unsigned int *ticket = nullptr;
+  bool defer_enabled = true;          // DNLP_SHARD_NO_DEFER=1: every evaluation closes with its own reduce
   int allreduce_mode = 0;             // 0 auto (P2P up to P2P_MAX, NCCL above), 1 force NCCL, 2 force P2P
   std::vector<void *> owned;
   std::vector<void *> opened;         // IPC mappings to close
@@ -242,7 +241,9 @@ struct dnlp_shard {
     *dev = static_cast<T *>(p);
     return 0;
   }
-  int exchange(int space, bool deliver);
+  int exchange(int space, bool deliver, bool defer_reduce = false);
+  int launch_reduce(int space, unsigned long long e, bool deliver);
+  unsigned long long pending_epoch[NSPACE] = {0, 0, 0, 0, 0, 0};   // deferred reduce of this epoch (0 = none)
   bool use_nccl(const ShardOut &S) const {
     if (c->world == 1) return false;
     if (allreduce_mode == 1) return c->nccl != nullptr && S.n_sh_total > 0;
@@ -251,8 +252,21 @@ struct dnlp_shard {
   }
 };
 
-// one exchange of output `space` on the oracle's stream (asynchronous)
-int dnlp_shard::exchange(int space, bool deliver) {
+int dnlp_shard::launch_reduce(int space, unsigned long long e, bool deliver) {
+  ShardOut &S = out[space];
+  const bool nccl_route = use_nccl(S);
+  shard_reduce_kernel<<<1, 1024, 0, o->stream>>>(o->out[space], c->peer_area_dev, c->rank, c->world, root, e, S.sh_src,
+                                                 nccl_route ? 0 : S.n_sh_total, S.sh_gpos,
+                                                 (c->rank == root && deliver) ? S.gout : nullptr,
+                                                 nccl_route ? nullptr : S.S, c->error, c->timeout_cycles);
+  ++o->launches;
+  return 0;
+}
+
+// one exchange of output `space` on the oracle's stream (asynchronous).  `defer_reduce`: only the push is
+// issued now; the reduce of this epoch follows the NEXT push (dnlp_shard_run_device), so the wait for the
+// peers' flags overlaps the next evaluation's local work instead of closing every evaluation with a barrier.
+int dnlp_shard::exchange(int space, bool deliver, bool defer_reduce) {
   ShardOut &S = out[space];
   if (!S.configured) { err = "output not configured for sharding"; return 1; }
   cudaStream_t st = o->stream;
@@ -277,17 +291,21 @@ int dnlp_shard::exchange(int space, bool deliver) {
   const int64_t work = std::max<int64_t>(n_ow, n_sh_p2p);
   int grid = (int)std::min<int64_t>((work + 255) / 256, (int64_t)o->sm_count * 4);
   if (grid < 1) grid = 1;
-  shard_push_kernel<<<grid, 256, 0, st>>>(lout, c->peer_area_dev, c->rank, c->world, root, c->epoch,
+  const unsigned long long e = ++c->epoch_host;
+  shard_push_kernel<<<grid, 256, 0, st>>>(lout, c->peer_area_dev, c->rank, c->world, root, e,
                                           S.sh_src, n_sh_p2p, S.ow_pos, S.ow_gpos, n_ow, S.root_gout, space,
                                           S.last_push, ticket, c->error, c->timeout_cycles);
-  shard_reduce_kernel<<<1, 1024, 0, st>>>(lout, c->peer_area_dev, c->rank, c->world, root, c->epoch, S.sh_src, n_sh_p2p,
-                                          S.sh_gpos, (c->rank == root && deliver) ? S.gout : nullptr,
-                                          nccl_route ? nullptr : S.S, c->error, c->timeout_cycles);
-  o->launches += 2;
-  ++c->epoch_host;
-  if (n_ow > 0) S.last_push = c->epoch_host;
-  cudaError_t e = cudaPeekAtLastError();
-  if (e != cudaSuccess) { err = std::string("kernel launch failed: ") + cudaGetErrorString(e); return 1; }
+  ++o->launches;
+  if (defer_reduce) {
+    if (pending_epoch[space]) launch_reduce(space, pending_epoch[space], false);
+    pending_epoch[space] = e;
+  } else {
+    if (pending_epoch[space]) { launch_reduce(space, pending_epoch[space], false); pending_epoch[space] = 0; }
+    launch_reduce(space, e, deliver);
+  }
+  if (n_ow > 0) S.last_push = e;
+  cudaError_t ce = cudaPeekAtLastError();
+  if (ce != cudaSuccess) { err = std::string("kernel launch failed: ") + cudaGetErrorString(ce); return 1; }
   return 0;
 }
 
@@ -421,6 +439,7 @@ int dnlp_shard_create(dnlp_oracle *local, dnlp_comm *comm, int root, dnlp_shard 
   if (local->device != comm->device) { g_comm_error = "oracle and comm live on different devices"; return 1; }
   dnlp_shard *s = new dnlp_shard();
   s->o = local; s->c = comm; s->root = root;
+  if (const char *e = getenv("DNLP_SHARD_NO_DEFER")) s->defer_enabled = atoi(e) == 0;
   if (const char *e = getenv("DNLP_SHARD_ALLREDUCE")) s->allreduce_mode = !strcmp(e, "nccl") ? 1 : (!strcmp(e, "p2p") ? 2 : 0);
   std::string &err = s->err;
   auto body = [&]() -> int {
@@ -595,6 +614,13 @@ int dnlp_shard_run_device(dnlp_shard *s, int32_t prog_mask, int32_t iters, float
   int run[DNLP_NPROG], nrun = nprogs;
   for (int i = 0; i < nprogs; ++i) run[i] = progs[i];
   if ((prog_mask & 0x1F) == 0x1F) { run[0] = DNLP_PROG_ALL; nrun = 1; }
+  int nex = 0;
+  for (int i = 0; i < nprogs; ++i) {
+    ShardOut &S = s->out[progs[i] + 1];
+    if (S.configured && S.n_sh_total > 0) ++nex;
+  }
+  // one exchanged output per evaluation (C3: only f is shared): its reduce trails one evaluation behind
+  const bool defer = nex == 1 && s->defer_enabled;
   CK(cudaEventRecord(o->ev0, o->stream));
   for (int it = 0; it < iters; ++it) {
     std::fill(o->valid.begin(), o->valid.end(), 0);
@@ -602,9 +628,11 @@ int dnlp_shard_run_device(dnlp_shard *s, int32_t prog_mask, int32_t iters, float
     for (int i = 0; i < nprogs; ++i) {
       ShardOut &S = s->out[progs[i] + 1];
       if (!S.configured || S.n_sh_total == 0) continue;
-      if (s->exchange(progs[i] + 1, false)) return 1;
+      if (s->exchange(progs[i] + 1, false, defer && !s->use_nccl(S))) return 1;
     }
   }
+  for (int sp = 1; sp < NSPACE; ++sp)
+    if (s->pending_epoch[sp]) { s->launch_reduce(sp, s->pending_epoch[sp], false); s->pending_epoch[sp] = 0; }
   CK(cudaEventRecord(o->ev1, o->stream));
   CK(cudaEventSynchronize(o->ev1));
   float ms = 0.f;
@@ -635,11 +663,11 @@ int dnlp_comm_allreduce_host(dnlp_comm *c, double *vec, int64_t count) {
     const int64_t n = std::min<int64_t>(P2P_MAX, count - off);
     CK(cudaMemcpy(d, vec + off, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
     const int grid = (int)((n + 255) / 256);
-    shard_push_kernel<<<grid, 256>>>(d, c->peer_area_dev, c->rank, c->world, 0, c->epoch, src, n, nullptr, nullptr, 0,
+    const unsigned long long e = ++c->epoch_host;
+    shard_push_kernel<<<grid, 256>>>(d, c->peer_area_dev, c->rank, c->world, 0, e, src, n, nullptr, nullptr, 0,
                                      nullptr, 0, 0, ticket, c->error, c->timeout_cycles);
-    shard_reduce_kernel<<<1, 1024>>>(d, c->peer_area_dev, c->rank, c->world, 0, c->epoch, src, n, nullptr, nullptr, d,
+    shard_reduce_kernel<<<1, 1024>>>(d, c->peer_area_dev, c->rank, c->world, 0, e, src, n, nullptr, nullptr, d,
                                      c->error, c->timeout_cycles);
-    ++c->epoch_host;
     CK(cudaDeviceSynchronize());
     if (*c->error) { err = "all-reduce timed out waiting for a peer"; rc = 1; break; }
     CK(cudaMemcpy(vec + off, d, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
