@@ -483,6 +483,19 @@ int dnlp_oracle::run_programs(const int *progs, int nprogs, bool force) {
   return 0;
 }
 
+// number of host threads the staging helpers use (see stage_point)
+static int stage_threads() {
+  static const int T = [] {
+    unsigned hw = std::thread::hardware_concurrency();
+    int ranks = 1;
+    if (const char *e = getenv("LOCAL_WORLD_SIZE")) ranks = atoi(e) > 0 ? atoi(e) : 1;
+    if (const char *e = getenv("DNLP_STAGE_THREADS")) return atoi(e) > 0 ? atoi(e) : 1;
+    int t = (int)(hw / (unsigned)ranks) - (ranks > 1 ? 1 : 2);
+    return t < 1 ? 1 : (t > 14 ? 14 : t);
+  }();
+  return T;
+}
+
 // Copy x into the pinned staging buffer and report whether it differs from the point already on
 // the device.  IPOPT issues its five callbacks at the same iterate with fresh copies of x, so an
 // unchanged point keeps every x-only instruction valid (no upload, no recomputation).  Large
@@ -507,14 +520,7 @@ static bool stage_point(double *dst, const double *src, int64_t n, bool have_old
   // threads, 0.11 ms with 12, 0.09 ms with 16.  One process per GPU shares the host cores: every rank takes
   // its share (LOCAL_WORLD_SIZE), or the spinning OpenMP teams of the ranks oversubscribe the cores (2 ranks x
   // 14 threads on 24 cores made a callback 6 ms instead of 0.5 ms).
-  static const int T = [] {
-    unsigned hw = std::thread::hardware_concurrency();
-    int ranks = 1;
-    if (const char *e = getenv("LOCAL_WORLD_SIZE")) ranks = atoi(e) > 0 ? atoi(e) : 1;
-    if (const char *e = getenv("DNLP_STAGE_THREADS")) return atoi(e) > 0 ? atoi(e) : 1;
-    int t = (int)(hw / (unsigned)ranks) - (ranks > 1 ? 1 : 2);
-    return t < 1 ? 1 : (t > 14 ? 14 : t);
-  }();
+  const int T = stage_threads();
   const int64_t chunk = (n + T - 1) / T;
   int any = 0;
 #pragma omp parallel for num_threads(T) schedule(static, 1) reduction(| : any)
@@ -529,13 +535,30 @@ static bool stage_point(double *dst, const double *src, int64_t n, bool have_old
   return any != 0;
 }
 
+// Is src[0..n) byte-identical to the mirror?  ONE parallel region over the whole vector (four of the five
+// callbacks at an iterate only ever need this answer, and a fork/join per 4 MB piece cost more than the compare).
+static bool same_as_mirror(const double *mir, const double *src, int64_t n) {
+  const size_t bytes = (size_t)n * sizeof(double);
+  if (bytes < (1u << 20)) return memcmp(mir, src, bytes) == 0;
+  const int T = stage_threads();
+  const int64_t chunk = (n + T - 1) / T;
+  int diff = 0;
+#pragma omp parallel for num_threads(T) schedule(static, 1) reduction(| : diff)
+  for (int t = 0; t < T; ++t) {
+    const int64_t lo = t * chunk, hi = lo + chunk < n ? lo + chunk : n;
+    if (lo < hi && memcmp(mir + lo, src + lo, (size_t)(hi - lo) * sizeof(double)) != 0) diff |= 1;
+  }
+  return diff == 0;
+}
+
 // Stage `count` doubles into the pinned mirror `hmir` of the device range `dev` and upload what changed.
-// Large vectors go in 4 MB pieces: the H2D copy of a piece runs while the host threads stage the next one,
-// and a piece that compares equal to the mirror is not uploaded at all (the mirror IS the device content).
-// Returns whether anything changed.
+// Unchanged vectors are recognised by one parallel compare.  Changed ones go in 4 MB pieces: the H2D copy of
+// a piece runs while the host threads stage the next one, and a piece that compares equal to the mirror is not
+// uploaded at all (the mirror IS the device content).  Returns whether anything changed.
 static int stage_and_upload(double *hmir, double *dev, const double *src, int64_t count, bool have_old,
                             cudaStream_t stream, bool *changed, std::string &err) {
   *changed = false;
+  if (have_old && count > 0 && same_as_mirror(hmir, src, count)) return 0;
   constexpr int64_t PIECE = (4 << 20) / sizeof(double);
   for (int64_t lo = 0; lo < count; lo += PIECE) {
     const int64_t len = count - lo < PIECE ? count - lo : PIECE;

@@ -668,7 +668,8 @@ def test_gpu_eager_delivery_random_callback_orders(name, gpu_mod, monkeypatch):
         o.close(), plain.close()
 
 
-def test_gpu_parameter_sweep_without_recompiling(gpu_mod):
+@pytest.mark.parametrize("eager", [False, True])
+def test_gpu_parameter_sweep_without_recompiling(eager, gpu_mod):
     """Parameter slots (expressions/constants/parameter.py:35): a sweep over parameter
     values on ONE compiled oracle - every output must equal the CPU oracle of the problem with the
     parameters folded at their current values, and only parameter-dependent work is repeated."""
@@ -686,9 +687,9 @@ def test_gpu_parameter_sweep_without_recompiling(gpu_mod):
             ir.sum(ir.multiply(b, ir.power(x, 3))) + ir.neg(gamma)]
     prob = ir.ProblemIR(obj, cons, [x, t], x0=0.1 * rng.standard_normal(n + 40))
     assert prob.n_params == 1 + n + 40
-    o = gpu_mod(prob)
+    o = gpu_mod(prob, eager=eager)           # eager delivery must re-deliver the x-only outputs after new parameters
     try:
-        assert o.tape.n_params == prob.n_params
+        assert o.tape.n_params == prob.n_params and o.eager == eager
         xv = prob.x0 * 1.1
         lam = rng.standard_normal(prob.m)
         for trial in range(4):
