@@ -559,8 +559,11 @@ def bench_c3_sharded(args, grp, hbm_peak, peak_src):
         e2e = {"value": args.steps * E2 / dt, "unit": "evals/s", "evals_per_step": E2,
                "h2d_bytes_per_step": int(E2 * h2d),
                "d2h_bytes_per_step": int(E2 * 8 * (1 + glob.n + glob.m + gs.dynamic["jac"].size + gs.hess_rows.size)),
-               "api": "RowShardedOracles five callbacks on every rank (collective), host buffers; owned entries are stored "
-                      "into the root's global array over NVLink, one D2H per callback leaves the root"}
+               "api": "RowShardedOracles five callbacks on every rank (collective), host buffers; " + (
+                   "outputs %s: every GPU copies the runs it owns over its own PCIe link into one host array shared by "
+                   "the ranks (every rank returns the full output); the rest is stored into the root's device array over "
+                   "NVLink and leaves the root in one D2H" % sorted(o._dev.shared) if o._dev.shared else
+                   "owned entries are stored into the root's global array over NVLink, one D2H per callback leaves the root")}
     sb = survey_bytes("c3", s)
     total_8d = int(sum(sb.values()))
     local_sizes = dict(s, m=layout.con_map.size - (2 * s["n"] if rank == 0 else 0))

@@ -59,6 +59,7 @@ EXPORTS = [
     "dnlp_comm_ipc_handle", "dnlp_comm_open_peers", "dnlp_comm_allreduce_host",
     "dnlp_shard_create", "dnlp_shard_destroy", "dnlp_shard_last_error", "dnlp_shard_set_output",
     "dnlp_shard_root_handles", "dnlp_shard_open_root", "dnlp_shard_eval", "dnlp_shard_run_device", "dnlp_shard_set_layout",
+    "dnlp_shard_share_control", "dnlp_shard_share_output", "dnlp_shard_share_unlink", "dnlp_shard_share_release",
 ]
 
 _lib = None
@@ -150,6 +151,11 @@ def lib():
     L.dnlp_shard_set_layout.argtypes = [vp, C.c_int32, c_i64p, c_i64p, C.c_int32, c_i64p, c_i64p]
     L.dnlp_shard_eval.argtypes = [vp, C.c_int32, c_f64p, c_f64p, C.c_double, c_f64p]
     L.dnlp_shard_run_device.argtypes = [vp, C.c_int32, C.c_int32, c_f32p]
+    L.dnlp_shard_share_control.argtypes = [vp, C.c_char_p, C.c_int32]
+    L.dnlp_shard_share_output.argtypes = [vp, C.c_int32, C.c_char_p, C.c_int32, C.c_int64, c_i64p, c_i64p, c_i64p,
+                                          C.POINTER(c_f64p)]
+    L.dnlp_shard_share_unlink.argtypes = [C.c_char_p]
+    L.dnlp_shard_share_release.argtypes = [C.c_void_p, C.c_int64]
     _lib = L
     return L
 
@@ -187,6 +193,27 @@ def pinned_empty(count):
     buf._dnlp_handle = handle
     arr = np.frombuffer(buf, dtype=np.float64, count=int(count))
     return arr, handle
+
+
+def shared_view(addr, count):
+    """float64 NumPy array over a shared-host output array (dnlp_shard_share_output); the mapping is unpinned and
+    unmapped when the LAST view disappears, so arrays handed to a solver outlive the shard handle."""
+    buf = (C.c_double * max(int(count), 1)).from_address(addr)
+    buf._dnlp_handle = _SharedHandle(addr, int(count))
+    return np.frombuffer(buf, dtype=np.float64, count=int(count))
+
+
+class _SharedHandle:
+    def __init__(self, addr, count):
+        self.addr, self.count = addr, count
+
+    def __del__(self):
+        try:
+            if self.addr:
+                lib().dnlp_shard_share_release(self.addr, self.count)
+                self.addr = None
+        except Exception:
+            pass
 
 
 class _PinnedHandle:

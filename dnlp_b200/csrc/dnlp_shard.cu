@@ -12,15 +12,26 @@
 //   * entries owned by exactly one rank (everything tied to sharded rows) are written by their owner
 //     directly into the ROOT's copy of the global output array at their global positions (fused
 //     gather + remote store), so the solver-facing array leaves the root in one D2H copy.
+//   * SHARED-HOST DELIVERY (dnlp_shard_share_*): a dense output without summed entries whose owned
+//     entries form a few contiguous runs skips the device-side exchange altogether - the global
+//     output array lives in one POSIX shared-memory segment that every rank page-locks, each GPU
+//     copies its own runs into it over its OWN PCIe link, and host-side epoch counters in a second
+//     segment tell every rank when all slices have landed.  Every rank's callback then returns the
+//     full global array (not only the root's), and the D2H time of a callback drops by the world size.
 //
 // Flags are monotone epochs in each rank's exchange area; every wait has a clock-based timeout that
 // raises an error flag instead of hanging the GPU.
 #include "dnlp_engine.h"
 
 #include <dlfcn.h>
+#include <fcntl.h>
 #include <nccl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
+#include <cerrno>
 #include <chrono>
 #include <thread>
 
@@ -198,6 +209,21 @@ shard_unpack_kernel(const int32_t *__restrict__ sh_gpos, int64_t n, const double
     root_gout[sh_gpos[k]] = S[k];
 }
 
+// shared-host delivery: control block in POSIX shared memory (one cache line per counter)
+struct HostCell { unsigned long long v; unsigned long long pad[7]; };
+struct HostCtl {
+  HostCell entered[MAXW];            // entered[r]: number of callbacks rank r has entered
+  HostCell done[NSPACE][MAXW];       // done[s][r]: callback number of rank r's last finished copy into output s
+  HostCell failed;                   // any rank that gives up raises it, so the others stop waiting
+};
+struct HostShare {
+  double *base = nullptr;            // the global output array (shared mapping, page-locked here)
+  size_t bytes = 0;
+  std::vector<int64_t> lsrc, gdst, len;   // this rank's owned runs: local start, global start, length
+  bool active = false;
+  unsigned long long last_write = 0; // callback number of this rank's previous copy into the array
+};
+
 struct ShardOut {
   int64_t n_sh_total = 0;
   int32_t *sh_src = nullptr;         // n_sh_total: local position contributing to shared slot k, or -1
@@ -228,7 +254,13 @@ struct dnlp_shard {
   std::vector<void *> owned;
   std::vector<void *> opened;         // IPC mappings to close
   std::vector<int64_t> xsrc, xlen, lsrc, llen;   // runs of the global x / lambda this rank sees (dnlp_shard_set_layout)
+  HostShare hs[NSPACE];
+  HostCtl *ctl = nullptr;
+  unsigned long long calls = 0;       // callbacks entered (every rank makes the same sequence of calls)
+  double host_timeout_s = 30.0;
   std::string err;
+  int deliver_shared_host(int space);
+  bool host_wait(const unsigned long long *cell, unsigned long long want, const char *what);
 
   template <typename T>
   int upload(const T *host, int64_t count, T **dev) {
@@ -308,6 +340,66 @@ int dnlp_shard::exchange(int space, bool deliver, bool defer_reduce) {
   if (ce != cudaSuccess) { err = std::string("kernel launch failed: ") + cudaGetErrorString(ce); return 1; }
   return 0;
 }
+
+// ---- shared-host delivery ---------------------------------------------------------------------------
+// spin (politely) until *cell >= want; gives up after host_timeout_s or when a peer has raised `failed`
+bool dnlp_shard::host_wait(const unsigned long long *cell, unsigned long long want, const char *what) {
+  if (__atomic_load_n(cell, __ATOMIC_ACQUIRE) >= want) return true;
+  const auto t0 = std::chrono::steady_clock::now();
+  for (unsigned spins = 0;; ++spins) {
+    if (__atomic_load_n(cell, __ATOMIC_ACQUIRE) >= want) return true;
+    if ((spins & 1023u) == 1023u) {
+      if (__atomic_load_n(&ctl->failed.v, __ATOMIC_ACQUIRE)) { err = std::string("a peer gave up while this rank waited for ") + what; return false; }
+      const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      if (dt > host_timeout_s) {
+        __atomic_store_n(&ctl->failed.v, 1ull, __ATOMIC_RELEASE);
+        err = std::string("timed out waiting for ") + what + " (a rank skipped or reordered a callback?)";
+        return false;
+      }
+      if (dt > 2e-3) std::this_thread::yield();
+    }
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+  }
+}
+
+// Output `space` of callback number `calls`: wait until every rank has left the callback that last read the
+// array, copy this rank's runs into it on the oracle's stream, publish, wait for everybody's slices.
+int dnlp_shard::deliver_shared_host(int space) {
+  HostShare &H = hs[space];
+  const int W = c->world, me = c->rank;
+  for (int r = 0; r < W; ++r)
+    if (!host_wait(&ctl->entered[r].v, H.last_write + 1, "the peers to release the output array")) return 1;
+  const double *lout = o->out[space];
+  for (size_t i = 0; i < H.len.size(); ++i)
+    CK(cudaMemcpyAsync(H.base + H.gdst[i], lout + H.lsrc[i], (size_t)H.len[i] * sizeof(double), cudaMemcpyDeviceToHost, o->stream));
+  CK(cudaStreamSynchronize(o->stream));
+  __atomic_store_n(&ctl->done[space][me].v, calls, __ATOMIC_RELEASE);
+  H.last_write = calls;
+  for (int r = 0; r < W; ++r)
+    if (!host_wait(&ctl->done[space][r].v, calls, "the peers' slices of the output")) return 1;
+  return 0;
+}
+
+namespace {
+void *map_segment(const char *name, size_t bytes, bool create, std::string &err) {
+  int fd = shm_open(name, create ? (O_CREAT | O_EXCL | O_RDWR) : O_RDWR, 0600);
+  if (fd < 0) { err = std::string("shm_open ") + name + ": " + strerror(errno); return nullptr; }
+  if (create) {
+    // posix_fallocate: running out of /dev/shm must be an error here, not a SIGBUS at the first touch
+    int rc = ftruncate(fd, (off_t)bytes) != 0 ? errno : posix_fallocate(fd, 0, (off_t)bytes);
+    if (rc != 0) { err = std::string("cannot size shared segment ") + name + ": " + strerror(rc); close(fd); shm_unlink(name); return nullptr; }
+  } else {
+    struct stat st;
+    if (fstat(fd, &st) != 0 || (size_t)st.st_size < bytes) { err = std::string("shared segment ") + name + " is smaller than expected"; close(fd); return nullptr; }
+  }
+  void *p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  if (p == MAP_FAILED) { err = std::string("mmap ") + name + ": " + strerror(errno); if (create) shm_unlink(name); return nullptr; }
+  return p;
+}
+}  // namespace
 
 // ---------------------------------------------------------------------------------------------------
 // extern "C"
@@ -429,6 +521,8 @@ void dnlp_shard_destroy(dnlp_shard *s) {
   cudaDeviceSynchronize();
   for (void *p : s->opened) cudaIpcCloseMemHandle(p);
   for (void *p : s->owned) cudaFree(p);
+  // the shared output arrays outlive the handle (the caller may still hold them): dnlp_shard_share_release
+  if (s->ctl) munmap(s->ctl, sizeof(HostCtl));
   delete s;
 }
 
@@ -440,6 +534,7 @@ int dnlp_shard_create(dnlp_oracle *local, dnlp_comm *comm, int root, dnlp_shard 
   dnlp_shard *s = new dnlp_shard();
   s->o = local; s->c = comm; s->root = root;
   if (const char *e = getenv("DNLP_SHARD_NO_DEFER")) s->defer_enabled = atoi(e) == 0;
+  if (const char *e = getenv("DNLP_SHARD_TIMEOUT_S")) s->host_timeout_s = atof(e) > 0 ? atof(e) : s->host_timeout_s;
   if (const char *e = getenv("DNLP_SHARD_ALLREDUCE")) s->allreduce_mode = !strcmp(e, "nccl") ? 1 : (!strcmp(e, "p2p") ? 2 : 0);
   std::string &err = s->err;
   auto body = [&]() -> int {
@@ -559,17 +654,94 @@ static int check_comm_error(dnlp_shard *s) {
   return 0;
 }
 
+// ---- shared-host delivery (see the file header) ------------------------------------------------------
+// Segment names are chosen by the caller (unique per job, the same on every rank).  `create` = 1 on exactly
+// one rank, which must have returned before the others attach; once every rank has attached the creator
+// removes the names with dnlp_shard_share_unlink (the mappings live on).
+int dnlp_shard_share_control(dnlp_shard *s, const char *shm_name, int32_t create) {
+  if (!s) { g_comm_error = "shard handle is NULL"; return 1; }
+  if (s->ctl) { s->err = "control segment already mapped"; return 1; }
+  void *p = map_segment(shm_name, sizeof(HostCtl), create != 0, s->err);
+  if (!p) return 1;
+  if (create) memset(p, 0, sizeof(HostCtl));
+  s->ctl = static_cast<HostCtl *>(p);
+  return 0;
+}
+
+// Output `space` (global_len doubles) is delivered through the shared array from now on; this rank's owned
+// entries are the runs local[local_start[i] : +length[i]] -> global[global_start[i] : +length[i]].  The
+// output must have no summed entries (dnlp_shard_set_output n_shared_total == 0) and every rank must make
+// the same sequence of dnlp_shard_eval calls.  *host_array = this process's mapping of the array (the
+// creator fills in the constant part before the others attach); it stays mapped after dnlp_shard_destroy,
+// until dnlp_shard_share_release.
+int dnlp_shard_share_output(dnlp_shard *s, int32_t space, const char *shm_name, int32_t create, int64_t n_runs,
+                            const int64_t *local_start, const int64_t *global_start, const int64_t *length,
+                            double **host_array) {
+  if (!s) { g_comm_error = "shard handle is NULL"; return 1; }
+  std::string &err = s->err;
+  if (space <= DNLP_DST_F || space >= NSPACE) { err = "bad output id for shared-host delivery"; return 1; }
+  ShardOut &S = s->out[space];
+  HostShare &H = s->hs[space];
+  if (!S.configured || S.glen <= 0) { err = "output not configured"; return 1; }
+  if (S.n_sh_total != 0) { err = "outputs with summed entries cannot use shared-host delivery"; return 1; }
+  if (!s->ctl) { err = "map the control segment first (dnlp_shard_share_control)"; return 1; }
+  if (H.base) { err = "output already shared"; return 1; }
+  const int64_t llen = s->o->out_len[space];
+  int64_t total = 0;
+  for (int64_t i = 0; i < n_runs; ++i) {
+    if (length[i] < 0 || local_start[i] < 0 || local_start[i] + length[i] > llen || global_start[i] < 0 ||
+        global_start[i] + length[i] > S.glen) { err = "owned run out of range"; return 1; }
+    total += length[i];
+  }
+  if (total != S.n_ow) { err = "owned runs do not cover the owned entries"; return 1; }
+  CK(cudaSetDevice(s->o->device));
+  const size_t bytes = (size_t)S.glen * sizeof(double);
+  void *p = map_segment(shm_name, bytes, create != 0, err);
+  if (!p) return 1;
+  cudaError_t ce = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+  if (ce != cudaSuccess) { err = std::string("cudaHostRegister of the shared array: ") + cudaGetErrorString(ce); munmap(p, bytes); if (create) shm_unlink(shm_name); return 1; }
+  H.base = static_cast<double *>(p);
+  H.bytes = bytes;
+  H.lsrc.assign(local_start, local_start + n_runs);
+  H.gdst.assign(global_start, global_start + n_runs);
+  H.len.assign(length, length + n_runs);
+  H.active = true;
+  *host_array = H.base;
+  return 0;
+}
+
+int dnlp_shard_share_unlink(const char *shm_name) { return shm_unlink(shm_name) == 0 ? 0 : 1; }
+
+// Unpin and unmap an array handed out by dnlp_shard_share_output, once the shard handle is gone (or will
+// no longer be evaluated) and nothing reads the array any more.
+int dnlp_shard_share_release(double *host_array, int64_t count) {
+  if (!host_array || count <= 0) return 1;
+  cudaHostUnregister(host_array);
+  return munmap(host_array, (size_t)count * sizeof(double)) == 0 ? 0 : 1;
+}
+
+
 // One callback, collectively: local program -> exchange -> (root) the GLOBAL output on the host.
 // `host_out`: root only; the whole global array (n_dyn < 0 at set_output time) or its n_dyn dynamic
 // entries, compacted in dyn_gpos order.  Program DNLP_PROG_F delivers the summed objective in host_out[0].
+static int shard_eval_body(dnlp_shard *s, int32_t prog, const double *x_local, const double *lam_local, double sigma,
+                           double *host_out);
 int dnlp_shard_eval(dnlp_shard *s, int32_t prog, const double *x_local, const double *lam_local, double sigma,
                     double *host_out) {
   if (!s) { g_comm_error = "shard handle is NULL"; return 1; }
+  const int rc = shard_eval_body(s, prog, x_local, lam_local, sigma, host_out);
+  if (rc != 0 && s->ctl) __atomic_store_n(&s->ctl->failed.v, 1ull, __ATOMIC_RELEASE);   // peers waiting on the host stop too
+  return rc;
+}
+static int shard_eval_body(dnlp_shard *s, int32_t prog, const double *x_local, const double *lam_local, double sigma,
+                           double *host_out) {
   std::string &err = s->err;
   dnlp_oracle *o = s->o;
   CK(cudaSetDevice(o->device));
   if (prog < DNLP_PROG_F || prog > DNLP_PROG_HESS) { err = "bad program id"; return 1; }
   const int space = prog + 1;
+  ++s->calls;
+  if (s->ctl) __atomic_store_n(&s->ctl->entered[s->c->rank].v, s->calls, __ATOMIC_RELEASE);
   if (!s->xsrc.empty()) {            // global vectors: staged run by run, no gathered host copy
     if (o->put_x_runs(x_local, s->xsrc, s->xlen)) { err = o->err; return 1; }
     if (prog == DNLP_PROG_HESS && o->put_lam_runs(lam_local, sigma, s->lsrc, s->llen)) { err = o->err; return 1; }
@@ -578,6 +750,10 @@ int dnlp_shard_eval(dnlp_shard *s, int32_t prog, const double *x_local, const do
     if (prog == DNLP_PROG_HESS && o->put_lam(lam_local, sigma)) { err = o->err; return 1; }
   }
   if (o->run_program(prog, false)) { err = o->err; return 1; }
+  if (s->hs[space].active) {         // nothing to sum: every owner copies its runs into the shared host array
+    if (s->deliver_shared_host(space)) return 1;
+    return check_comm_error(s);
+  }
   if (s->exchange(space, true)) return 1;
   ShardOut &S = s->out[space];
   if (space == DNLP_DST_F && host_out && s->c->rank != s->root) {

@@ -85,6 +85,20 @@ def _runs(idx):
     return [(int(idx[a]), int(idx[a]) + int(b - a), int(a)) for a, b in zip(starts, stops)]
 
 
+def _pair_runs(src, dst, limit=64):
+    """Runs along which BOTH index maps advance by one: [(src_start, dst_start, length)], or None when there are
+    more than ``limit`` of them."""
+    src, dst = np.asarray(src, dtype=np.int64), np.asarray(dst, dtype=np.int64)
+    if src.size == 0:
+        return []
+    brk = np.where((np.diff(src) != 1) | (np.diff(dst) != 1))[0] + 1
+    if brk.size + 1 > limit:
+        return None
+    starts = np.concatenate([[0], brk])
+    stops = np.concatenate([brk, [src.size]])
+    return [(int(src[a]), int(dst[a]), int(b - a)) for a, b in zip(starts, stops)]
+
+
 def _take(src, runs, out):
     if len(runs) > 64:
         raise ValueError("index map too fragmented")
@@ -100,8 +114,10 @@ _PROG = {"f": 0, "grad": 1, "g": 2, "jac": 3, "hess": 4}
 class _DeviceShard:
     """GPU path of ``RowShardedOracles``: the ``dnlp_shard`` object of include/dnlp_b200.h.  Local outputs
     stay in HBM; shared entries are summed by the one-shot peer-memory all-reduce (ncclAllReduce above
-    16384 doubles), owned entries are stored by their owner into the root's global array over NVLink,
-    and one D2H per callback leaves the root (csrc/dnlp_shard.cu)."""
+    16384 doubles).  Owned entries reach the host one of two ways (csrc/dnlp_shard.cu): dense outputs with
+    nothing to sum and contiguous owned runs go from every GPU over its own PCIe link into ONE host array
+    shared by the ranks (``self.shared``: every rank then returns the full global output); anything else is
+    stored by its owner into the root's device array over NVLink and leaves the root in one D2H."""
 
     DENSE_FRACTION = 0.5
 
@@ -123,6 +139,7 @@ class _DeviceShard:
         ptr = lambda a: a.ctypes.data_as(i32p) if a.size else None       # noqa: E731
         self.compact, self.dense = {}, {}
         gs = owner.gs
+        info = {}
         for name in ("f", "grad", "g", "jac", "hess"):
             if name == "f":
                 glen, gconst, dyn = 1, np.zeros(1), np.zeros(1, np.int64)
@@ -149,15 +166,21 @@ class _DeviceShard:
                 self.h, _SPACE[name], int(shared_slots.size), ptr(a[0]), ptr(a[1]), int(ow_pos.size), ptr(a[2]), ptr(a[3]),
                 int(glen), gconst.ctypes.data_as(_cabi.c_f64p) if self.is_root and glen else None,
                 -1 if dense else int(nd), None if dense else ptr(a[4])))
-            if self.is_root:
-                if dense and name != "f":
+            info[name] = (dense, int(shared_slots.size), ow_pos, ow_gpos, int(glen))
+        self.shared = self._share_host_arrays(info) if store.world > 1 else {}
+        if self.is_root:
+            for name in ("grad", "g", "jac", "hess"):
+                dense, glen = info[name][0], info[name][4]
+                if name in self.shared:
+                    continue
+                if dense:
                     buf, hd = _cabi.pinned_empty(glen)               # the solver-facing array itself is pinned
                     buf[:] = owner._out[name]
                     owner._out[name], owner._keep = buf, getattr(owner, "_keep", []) + [hd]
                     if name == "grad":
                         owner.grad_obj = buf
-                elif not dense:
-                    self.compact[name] = _cabi.pinned_empty(max(nd, 1))
+                else:
+                    self.compact[name] = _cabi.pinned_empty(max(gs.dynamic[name].size, 1))
         self._f, self._fh = _cabi.pinned_empty(1)
         # hand the library the runs of the global x / lambda this shard sees: the callbacks then pass the
         # GLOBAL vectors and staging reads them in place (no gathered host copy per callback)
@@ -177,6 +200,73 @@ class _DeviceShard:
         self.check(L.dnlp_shard_open_root(self.h, table))
         barrier(store)
 
+    def _share_host_arrays(self, info):
+        """Shared-host delivery (csrc/dnlp_shard.cu): every dense output that has no summed entries and whose
+        owned entries are a few contiguous runs ON EVERY RANK gets one global array in POSIX shared memory;
+        each rank's GPU copies its runs there over its own PCIe link and every rank returns the full array.
+        ``DNLP_SHARD_HOST_SHARE=0`` keeps the NVLink route (owners store into the root's device array)."""
+        import os
+        import time
+
+        from . import _cabi
+        from .comm import allgather_array, barrier, bcast
+        C, L, store, o = self.C, self._L, self.store, self.o
+        if os.environ.get("DNLP_SHARD_HOST_SHARE", "1") == "0":
+            return {}
+        names = ("grad", "g", "jac", "hess")
+        runs, mine = {}, np.zeros(len(names), dtype=np.int32)
+        for j, name in enumerate(names):
+            dense, n_shared, ow_pos, ow_gpos, glen = info[name]
+            if dense and n_shared == 0 and glen > 0:
+                r = _pair_runs(ow_pos, ow_gpos)
+                if r is not None:
+                    runs[name], mine[j] = r, 1
+        everyone = np.min(np.stack(allgather_array(store, mine)), axis=0)
+        chosen = [name for j, name in enumerate(names) if everyone[j]]
+        if not chosen:
+            return {}
+        tag = bcast(store, ("/dnlp_%d_%06x" % (os.getpid(), time.time_ns() & 0xFFFFFF)).encode(), self.root).decode()
+        seg = lambda name: ("%s_%s" % (tag, name)).encode()              # noqa: E731
+        arrays = {}
+
+        def attach(create):
+            self.check(L.dnlp_shard_share_control(self.h, seg("ctl"), create))
+            for name in chosen:
+                r = runs[name]
+                a64 = lambda k: np.ascontiguousarray([t[k] for t in r], dtype=np.int64)    # noqa: E731
+                ls, gd, ln = a64(0), a64(1), a64(2)
+                p64 = lambda v: v.ctypes.data_as(_cabi.c_i64p) if v.size else None         # noqa: E731
+                base = _cabi.c_f64p()
+                self.check(L.dnlp_shard_share_output(self.h, _SPACE[name], seg(name), create, len(r), p64(ls), p64(gd),
+                                                     p64(ln), C.byref(base)))
+                arrays[name] = _cabi.shared_view(C.cast(base, C.c_void_p).value, info[name][4])
+        status = b"ok"
+        if self.is_root:
+            try:
+                attach(1)
+                for name in chosen:
+                    arrays[name][:] = o._out[name]                       # the constant part, before anybody attaches
+            except RuntimeError as e:
+                status = str(e).encode()
+        status = bcast(store, status, self.root)
+        if status != b"ok":
+            if self.is_root:
+                for name in ["ctl"] + chosen:
+                    L.dnlp_shard_share_unlink(seg(name))
+            raise RuntimeError("shared-host delivery could not be set up (%s); DNLP_SHARD_HOST_SHARE=0 keeps the "
+                               "NVLink route" % status.decode())
+        if not self.is_root:
+            attach(0)
+        barrier(store)
+        if self.is_root:                                                 # names gone, mappings live on
+            for name in ["ctl"] + chosen:
+                L.dnlp_shard_share_unlink(seg(name))
+        for name in chosen:
+            o._out[name] = arrays[name]
+            if name == "grad":
+                o.grad_obj = arrays[name]
+        return arrays
+
     def check(self, rc):
         if rc != 0:
             raise RuntimeError("dnlp_b200 shard: %s" % self._L.dnlp_shard_last_error(self.h).decode())
@@ -188,6 +278,8 @@ class _DeviceShard:
         out = None
         if name == "f":
             out = self._f
+        elif name in self.shared:
+            out = None                                # every owner copies its runs into the shared array
         elif self.is_root:
             out = o._out[name] if self.dense[name] else self.compact[name][0]
         self.check(self._L.dnlp_shard_eval(
@@ -195,7 +287,7 @@ class _DeviceShard:
             float(sigma), None if out is None else out.ctypes.data_as(f64p)))
         if name == "f":
             return np.float64(self._f[0])
-        if self.is_root and not self.dense[name]:
+        if self.is_root and not self.dense[name] and name not in self.shared:
             dyn = o.gs.dynamic[name]
             o._out[name][dyn] = self.compact[name][0][:dyn.size]
         return o._out[name]
@@ -213,6 +305,7 @@ class _DeviceShard:
         if getattr(self, "h", None):
             from .comm import barrier
             barrier(self.store)
+            self.shared = {}                          # the arrays (owner._out) stay mapped until their last view dies
             self._L.dnlp_shard_destroy(self.h)
             self.h = None
             self.comm.close()

@@ -232,6 +232,22 @@ int dnlp_shard_eval(dnlp_shard *s, int32_t prog, const double *x_local, const do
                     double *host_out /* root only */);
 int dnlp_shard_run_device(dnlp_shard *s, int32_t prog_mask, int32_t iters, float *elapsed_ms);
 
+/* Shared-host delivery of a sharded output (csrc/dnlp_shard.cu): the global output array lives in one POSIX
+ * shared-memory segment page-locked by every rank; each GPU copies the runs it owns into it over its own
+ * PCIe link and host-side epoch counters (the control segment) tell every rank when all slices have landed,
+ * so EVERY rank's callback returns the full global array.  Only for outputs without summed entries whose
+ * owned entries form contiguous runs; every rank must make the same sequence of dnlp_shard_eval calls.
+ * `create` = 1 on exactly one rank, which returns before the others attach; after all have attached the
+ * creator removes the names (dnlp_shard_share_unlink).  *host_array stays valid after dnlp_shard_destroy, until
+ * dnlp_shard_share_release.  The reference has no counterpart: it evaluates the
+ * whole problem in one process (cvxpy/reductions/solvers/nlp_solvers/nlp_solver.py:200-377). */
+int dnlp_shard_share_control(dnlp_shard *s, const char *shm_name, int32_t create);
+int dnlp_shard_share_output(dnlp_shard *s, int32_t dst_space, const char *shm_name, int32_t create, int64_t n_runs,
+                            const int64_t *local_start, const int64_t *global_start, const int64_t *length,
+                            double **host_array);
+int dnlp_shard_share_unlink(const char *shm_name);
+int dnlp_shard_share_release(double *host_array, int64_t count);   /* unpin + unmap; the array outlives dnlp_shard_destroy */
+
 #ifdef __cplusplus
 }
 #endif

@@ -182,3 +182,14 @@ def test_socket_store_collectives(world):
         p.join(timeout=30)
     for rank, msg in results:
         assert msg == "ok", "rank %d: %s" % (rank, msg)
+
+
+def test_pair_runs_follow_both_index_maps():
+    from dnlp_b200.sharded import _pair_runs
+    assert _pair_runs([], []) == []
+    assert _pair_runs([0, 1, 2, 3], [10, 11, 12, 13]) == [(0, 10, 4)]
+    # a break in either map starts a new run
+    assert _pair_runs([0, 1, 2, 5, 6], [10, 11, 12, 13, 14]) == [(0, 10, 3), (5, 13, 2)]
+    assert _pair_runs([0, 1, 2, 3], [10, 11, 20, 21]) == [(0, 10, 2), (2, 20, 2)]
+    assert _pair_runs(np.arange(0, 200, 2), np.arange(100)) is None           # too fragmented: NVLink route
+    assert len(_pair_runs(np.arange(0, 20, 2), np.arange(10))) == 10

@@ -1,7 +1,9 @@
 """Row-sharded oracle with the device-side exchange of csrc/dnlp_shard.cu (one process per rank).
 
 * 2 and 3 ranks SHARING one GPU: the peer-memory path alone (CUDA IPC exchange areas, one-shot
-  all-reduce kernels, direct stores into the root's global array) - runs on the 1-GPU test box;
+  all-reduce kernels, direct stores into the root's global array) and the shared-host delivery of
+  outputs that have nothing to sum (one host array for all ranks, every rank copies its own runs,
+  every rank returns the full output) - runs on the 1-GPU test box;
 * 2 ranks on 2 GPUs with NCCL as well (the ncclAllReduce route forced for the shared entries) -
   skipped when the box has one GPU.
 
@@ -26,11 +28,12 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q, same_gpu, kind, allreduce):
+def _worker(rank, world, port, q, same_gpu, kind, allreduce, host_share=True):
     try:
         sys.path.insert(0, ROOT)
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         os.environ["DNLP_SHARD_ALLREDUCE"] = allreduce
+        os.environ["DNLP_SHARD_HOST_SHARE"] = "1" if host_share else "0"
         from dnlp_b200 import workloads as W
         from dnlp_b200.comm import SocketStore, barrier
         from dnlp_b200.oracles import GpuOracles
@@ -53,6 +56,10 @@ def _worker(rank, world, port, q, same_gpu, kind, allreduce):
         assert o._dev is not None, "device-side exchange not active"
         if allreduce == "nccl":
             assert o._dev.comm.has_nccl
+        shared = set(o._dev.shared)
+        if kind == "c3":       # gradient, constraints and Hessian of C3 have nothing to sum and contiguous owned runs
+            assert shared == ({"grad", "g", "hess"} if host_share else set()), shared
+        full = lambda name: rank == 0 or name in shared      # noqa: E731  (shared-host outputs are complete on EVERY rank)
         np.testing.assert_array_equal(o.jacobianstructure()[0], ref.jacobianstructure()[0])
         np.testing.assert_array_equal(o.jacobianstructure()[1], ref.jacobianstructure()[1])
         np.testing.assert_array_equal(o.hessianstructure()[0], ref.hessianstructure()[0])
@@ -67,20 +74,25 @@ def _worker(rank, world, port, q, same_gpu, kind, allreduce):
             got = [o.gradient(x), o.constraints(x), o.jacobian(x), o.hessian(x, lam, sigma)]
             if it == 1:                                              # the same output twice in a row (line search)
                 got[1] = o.constraints(x)
-            if rank == 0:
+            if full("grad"):
                 assert_close(got[0], ref.gradient(x), "grad")
+            if full("g"):
                 assert_close(got[1], ref.constraints(x), "g", atol=1e-11)
+            if full("jac"):
                 assert_close(got[2], ref.jacobian(x), "jac")
+            if full("hess"):
                 assert_close(got[3], ref.hessian(x, lam, sigma), "hess")
         ms = o.run_device(iters=5)                        # reduce of the shared entries trails one evaluation behind
         assert ms > 0
         x = glob.x0 * 1.02                                # ... and the callbacks still agree afterwards
         assert_close(o.objective(x), ref.objective(x), "f after the device loop")
         hh = o.hessian(x, lam, 0.7)
-        if rank == 0:
+        if full("hess"):
             assert_close(hh, ref.hessian(x, lam, 0.7), "hess after the device loop")
         barrier(store)
         o.close(), ref.close()
+        if full("hess"):
+            assert_close(o._out["hess"], hh, "the output array outlives the shard handle")
         store.close()
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
@@ -88,17 +100,32 @@ def _worker(rank, world, port, q, same_gpu, kind, allreduce):
         q.put((rank, "FAIL: %s\n%s" % (e, traceback.format_exc())))
 
 
-def _run(world, same_gpu, kind, allreduce="auto"):
+def _run(world, same_gpu, kind, allreduce="auto", host_share=True):
     import multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q, same_gpu, kind, allreduce)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, same_gpu, kind, allreduce, host_share)) for r in range(world)]
     for p in procs:
         p.start()
-    results = [q.get(timeout=300) for _ in procs]
+    import queue
+    import time
+    results, deadline, problem = [], time.time() + 300, None
+    while len(results) < world and problem is None:
+        try:
+            results.append(q.get(timeout=2))
+        except queue.Empty:
+            done = {r for r, _ in results}
+            dead = [(i, p.exitcode) for i, p in enumerate(procs) if p.exitcode not in (None, 0) and i not in done]
+            if dead:
+                problem = "rank(s) died without reporting (rank, exit code): %s" % dead
+            elif time.time() > deadline:
+                problem = "no report within 300 s"
     for p in procs:
+        if problem is not None and p.is_alive():
+            p.terminate()
         p.join(timeout=60)
+    assert problem is None, problem
     for rank, msg in results:
         assert msg == "ok", "rank %d: %s" % (rank, msg)
 
@@ -106,6 +133,11 @@ def _run(world, same_gpu, kind, allreduce="auto"):
 @pytest.mark.parametrize("world,kind", [(2, "c3"), (3, "c3"), (2, "c5")])
 def test_row_sharded_peer_memory_exchange_on_one_gpu(world, kind):
     _run(world, True, kind)
+
+
+def test_row_sharded_nvlink_delivery_without_the_shared_host_array():
+    """DNLP_SHARD_HOST_SHARE=0: owners store into the root's device array, one D2H leaves the root."""
+    _run(2, True, "c3", host_share=False)
 
 
 @pytest.mark.parametrize("kind,allreduce", [("c3", "auto"), ("c5", "auto"), ("c5", "nccl")])
