@@ -737,6 +737,8 @@ def main():
         print(json.dumps(line, default=float))
         return
 
+    # stdout carries exactly one JSON line: NCCL's own banner / debug lines (NCCL_DEBUG set on the box) go to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     grp = Group(rank, world, local_rank)
     if headline == "c3" and world > 1:
         main_res = bench_c3_sharded(args, grp, hbm_peak, peak_src)

@@ -59,7 +59,7 @@ EXPORTS = [
     "dnlp_comm_ipc_handle", "dnlp_comm_open_peers", "dnlp_comm_allreduce_host",
     "dnlp_shard_create", "dnlp_shard_destroy", "dnlp_shard_last_error", "dnlp_shard_set_output",
     "dnlp_shard_root_handles", "dnlp_shard_open_root", "dnlp_shard_eval", "dnlp_shard_run_device", "dnlp_shard_set_layout",
-    "dnlp_shard_share_control", "dnlp_shard_share_output", "dnlp_shard_share_unlink", "dnlp_shard_share_release",
+    "dnlp_shard_share_control", "dnlp_shard_share_output", "dnlp_shard_share_unlink", "dnlp_shard_share_release", "dnlp_shard_share_reset",
 ]
 
 _lib = None
@@ -74,9 +74,10 @@ def lib():
         raise RuntimeError(
             "dnlp_b200: %s is missing - build it with `python -m dnlp_b200.build` "
             "(there is no CPU fallback for the oracle)" % LIB_PATH)
-    if int(os.environ.get("LOCAL_WORLD_SIZE", "1")) > 1:
-        # several ranks share the host cores: idle staging threads must sleep, not spin (read by libgomp at load time)
-        os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+    # Several ranks share the host cores: the staging helpers size their OpenMP teams to cores / LOCAL_WORLD_SIZE - 1
+    # (csrc/dnlp_cabi.cu stage_threads), so libgomp's default wait policy (spin briefly, then sleep) is kept: with
+    # OMP_WAIT_POLICY=passive every parallel region paid a thread wake-up (C3 on 2 GPUs: 3.2 ms per evaluation
+    # instead of 2.2, profiles/r02_e2e_breakdown_sharded.txt).
     L = C.CDLL(LIB_PATH)
     vp = C.c_void_p
     L.dnlp_device_count.restype = C.c_int
@@ -156,6 +157,7 @@ def lib():
                                           C.POINTER(c_f64p)]
     L.dnlp_shard_share_unlink.argtypes = [C.c_char_p]
     L.dnlp_shard_share_release.argtypes = [C.c_void_p, C.c_int64]
+    L.dnlp_shard_share_reset.argtypes = [vp]
     _lib = L
     return L
 

@@ -712,6 +712,15 @@ int dnlp_shard_share_output(dnlp_shard *s, int32_t space, const char *shm_name, 
 
 int dnlp_shard_share_unlink(const char *shm_name) { return shm_unlink(shm_name) == 0 ? 0 : 1; }
 
+// Give up shared-host delivery on this handle (a peer could not attach): every output goes back to the
+// device-side route.  Arrays already handed out stay mapped until dnlp_shard_share_release, as after destroy.
+int dnlp_shard_share_reset(dnlp_shard *s) {
+  if (!s) { g_comm_error = "shard handle is NULL"; return 1; }
+  for (HostShare &H : s->hs) H = HostShare();
+  if (s->ctl) { munmap(s->ctl, sizeof(HostCtl)); s->ctl = nullptr; }
+  return 0;
+}
+
 // Unpin and unmap an array handed out by dnlp_shard_share_output, once the shard handle is gone (or will
 // no longer be evaluated) and nothing reads the array any more.
 int dnlp_shard_share_release(double *host_array, int64_t count) {

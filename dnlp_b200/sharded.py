@@ -225,7 +225,8 @@ class _DeviceShard:
         chosen = [name for j, name in enumerate(names) if everyone[j]]
         if not chosen:
             return {}
-        tag = bcast(store, ("/dnlp_%d_%06x" % (os.getpid(), time.time_ns() & 0xFFFFFF)).encode(), self.root).decode()
+        prefix = os.environ.get("DNLP_SHARD_SHM_PREFIX", "/dnlp")          # POSIX shm name: one leading slash
+        tag = bcast(store, ("%s_%d_%06x" % (prefix, os.getpid(), time.time_ns() & 0xFFFFFF)).encode(), self.root).decode()
         seg = lambda name: ("%s_%s" % (tag, name)).encode()              # noqa: E731
         arrays = {}
 
@@ -240,6 +241,17 @@ class _DeviceShard:
                 self.check(L.dnlp_shard_share_output(self.h, _SPACE[name], seg(name), create, len(r), p64(ls), p64(gd),
                                                      p64(ln), C.byref(base)))
                 arrays[name] = _cabi.shared_view(C.cast(base, C.c_void_p).value, info[name][4])
+
+        def give_up(why):
+            import sys
+            L.dnlp_shard_share_reset(self.h)
+            arrays.clear()                            # the views release their mappings as they die
+            if self.is_root:
+                for name in ["ctl"] + chosen:
+                    L.dnlp_shard_share_unlink(seg(name))
+                sys.stderr.write("dnlp_b200: shared-host delivery not available (%s); owned entries go to the root over "
+                                 "NVLink instead\n" % why)
+            return {}
         status = b"ok"
         if self.is_root:
             try:
@@ -249,15 +261,16 @@ class _DeviceShard:
             except RuntimeError as e:
                 status = str(e).encode()
         status = bcast(store, status, self.root)
-        if status != b"ok":
-            if self.is_root:
-                for name in ["ctl"] + chosen:
-                    L.dnlp_shard_share_unlink(seg(name))
-            raise RuntimeError("shared-host delivery could not be set up (%s); DNLP_SHARD_HOST_SHARE=0 keeps the "
-                               "NVLink route" % status.decode())
+        if status != b"ok":                                              # e.g. /dev/shm too small, page-locking refused
+            return give_up(status.decode())
+        mine_ok = np.ones(1, dtype=np.int32)
         if not self.is_root:
-            attach(0)
-        barrier(store)
+            try:
+                attach(0)
+            except RuntimeError as e:
+                mine_ok[0], status = 0, str(e).encode()
+        if int(np.min(np.concatenate(allgather_array(store, mine_ok)))) == 0:
+            return give_up("a rank could not attach: %s" % status.decode())
         if self.is_root:                                                 # names gone, mappings live on
             for name in ["ctl"] + chosen:
                 L.dnlp_shard_share_unlink(seg(name))

@@ -246,6 +246,7 @@ int dnlp_shard_share_output(dnlp_shard *s, int32_t dst_space, const char *shm_na
                             const int64_t *local_start, const int64_t *global_start, const int64_t *length,
                             double **host_array);
 int dnlp_shard_share_unlink(const char *shm_name);
+int dnlp_shard_share_reset(dnlp_shard *s);      /* a peer could not attach: back to the device-side route */
 int dnlp_shard_share_release(double *host_array, int64_t count);   /* unpin + unmap; the array outlives dnlp_shard_destroy */
 
 #ifdef __cplusplus

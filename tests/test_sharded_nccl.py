@@ -34,6 +34,9 @@ def _worker(rank, world, port, q, same_gpu, kind, allreduce, host_share=True):
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         os.environ["DNLP_SHARD_ALLREDUCE"] = allreduce
         os.environ["DNLP_SHARD_HOST_SHARE"] = "1" if host_share else "0"
+        if host_share == "broken":                  # shm_open rejects the name: the setup must fall back, not fail
+            os.environ["DNLP_SHARD_SHM_PREFIX"] = "/no/such/dir/dnlp"
+            host_share = False
         from dnlp_b200 import workloads as W
         from dnlp_b200.comm import SocketStore, barrier
         from dnlp_b200.oracles import GpuOracles
@@ -138,6 +141,10 @@ def test_row_sharded_peer_memory_exchange_on_one_gpu(world, kind):
 def test_row_sharded_nvlink_delivery_without_the_shared_host_array():
     """DNLP_SHARD_HOST_SHARE=0: owners store into the root's device array, one D2H leaves the root."""
     _run(2, True, "c3", host_share=False)
+
+
+def test_row_sharded_falls_back_when_the_shared_segment_cannot_be_created():
+    _run(2, True, "c3", host_share="broken")
 
 
 @pytest.mark.parametrize("kind,allreduce", [("c3", "auto"), ("c5", "auto"), ("c5", "nccl")])
