@@ -530,7 +530,7 @@ def bench_c3_sharded(args, grp, hbm_peak, peak_src):
     ok = bool(grp.sum([1.0 if (rank != 0 or parity["ok"]) else 0.0])[0] == world)
     if not ok:
         if rank == 0:
-            print(json.dumps({"metric": METRIC, "value": None, "error": "sharded result differs from the single-GPU result",
+            emit(json.dumps({"metric": METRIC, "value": None, "error": "sharded result differs from the single-GPU result",
                               "parity": parity}))
         o.close()
         return None
@@ -690,7 +690,24 @@ def bench_multistart(args, grp, hbm_peak, peak_src):
 
 
 # ------------------------------------------------------------------ main
+_RESULT_OUT = None
+
+
+def emit(text):
+    """The one JSON line, on the process's ORIGINAL stdout (see main: fd 1 itself is pointed at stderr)."""
+    out = _RESULT_OUT if _RESULT_OUT is not None else sys.stdout
+    out.write(text + "\n")
+    out.flush()
+
+
 def main():
+    # stdout carries exactly one JSON line.  Libraries write banners straight to fd 1 (NCCL prints its version there
+    # when the box sets NCCL_DEBUG=VERSION, and NCCL_DEBUG_FILE is not honoured at that level): keep a private handle
+    # on the real stdout for the result and send everything else that lands on fd 1 to stderr.
+    global _RESULT_OUT
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -734,11 +751,9 @@ def main():
                                                  "cores in dense products"},
                 "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "wall_s": round(time.time() - t_start, 1)}
-        print(json.dumps(line, default=float))
+        emit(json.dumps(line, default=float))
         return
 
-    # stdout carries exactly one JSON line: NCCL's own banner / debug lines (NCCL_DEBUG set on the box) go to stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     grp = Group(rank, world, local_rank)
     if headline == "c3" and world > 1:
         main_res = bench_c3_sharded(args, grp, hbm_peak, peak_src)
@@ -785,7 +800,7 @@ def main():
                                             "check as soon as `import cyipopt` succeeds")
         if sub_res:
             line["configs"] = sub_res
-        print(json.dumps(line, default=float))
+        emit(json.dumps(line, default=float))
     grp.barrier()
     grp.close()
 
