@@ -504,9 +504,20 @@ class Builder:
             self._value_cache[key] = (node, out)
         return self._value_cache[key][1]
 
+    @staticmethod
+    def _kron(left, right, fmt):
+        """``sp.kron(left, right, format=fmt)``.  With a 1 x 1 identity on either side (matrix @ vector, the common
+        case) SciPy's COO path reduces to the other operand's own COO entries in their own order, so the 16 M-entry
+        repeat / tile / multiply passes are skipped; the result is the same object SciPy would build."""
+        for eye, other in ((left, right), (right, left)):
+            if sp.issparse(eye) and eye.shape == (1, 1) and eye.nnz == 1 and eye.tocoo().data[0] == 1.0 \
+                    and sp.issparse(other) and other.ndim == 2 and other.nnz > 0:
+                return sp.coo_array(other).asformat(fmt)
+        return sp.kron(left, right, format=fmt)
+
     def _kron_map(self, left, right):
         """COO (rows, cols, data) of kron(left, right) for constant operands."""
-        k = sp.coo_array(sp.kron(left, right, format="coo"))
+        k = sp.coo_array(self._kron(left, right, "coo"))
         return k.coords[0], k.coords[1], k.data
 
     def _value_matmul(self, node):
@@ -848,7 +859,7 @@ class Builder:
         dx_dict, dy_dict = {}, {}
         if not X.is_constant():
             Tm, yv = self._tag_matrix(Y)
-            dx = sp.kron(Tm.T, sp.eye(m), format="csr")
+            dx = self._kron(Tm.T, sp.eye(m), "csr")
             if not X.is_var():
                 dx_dict = self._chain_through(dx, yv, self.jac(X), X.size)
             else:
@@ -857,7 +868,7 @@ class Builder:
                                             yv.gather(np.rint(d.data).astype(np.int64) - 1))}
         if not Y.is_constant():
             Tm, xv = self._tag_matrix(X)
-            dy = sp.kron(sp.eye(p), Tm, format="csr")
+            dy = self._kron(sp.eye(p), Tm, "csr")
             if not Y.is_var():
                 dy_dict = self._chain_through(dy, xv, self.jac(Y), Y.size)
             else:

@@ -168,3 +168,22 @@ def test_column_panels_split_and_accumulate(monkeypatch):
             assert_close(it.eval("hess", p["x"], p["lam"], float(p["sigma"])), p["hess"], name + " hess")
             outs = _union(tape, p["x"], p["lam"], float(p["sigma"]))
             assert_close(outs[T.DST_G], p["g"], name + " union/g")
+
+
+def test_kron_fast_path_is_scipys_kron_entry_for_entry():
+    """rules.Builder._kron skips SciPy's repeat / tile passes when one side is a 1 x 1 identity (matrix @ vector);
+    the entries and their order must be exactly SciPy's, or the triplet order of the reference is lost."""
+    import scipy.sparse as sp
+    from dnlp_b200.rules import Builder
+    rng = np.random.default_rng(0)
+    for trial in range(24):
+        m, n = rng.integers(1, 9, 2)
+        A = sp.random(m, n, density=0.4, random_state=int(rng.integers(1e6)), format=("csr", "coo", "csc")[trial % 3])
+        A = sp.coo_array(A) if trial % 2 else A
+        for fmt in ("csr", "coo"):
+            for left, right in ((sp.eye(1), A), (A.T, sp.eye(1)), (sp.eye(2), A), (A, sp.eye(3))):
+                a, b = sp.coo_array(Builder._kron(left, right, fmt)), sp.coo_array(sp.kron(left, right, format=fmt))
+                assert a.shape == b.shape
+                np.testing.assert_array_equal(a.coords[0], b.coords[0])
+                np.testing.assert_array_equal(a.coords[1], b.coords[1])
+                np.testing.assert_array_equal(a.data, b.data)
