@@ -60,6 +60,7 @@ EXPORTS = [
     "dnlp_shard_create", "dnlp_shard_destroy", "dnlp_shard_last_error", "dnlp_shard_set_output",
     "dnlp_shard_root_handles", "dnlp_shard_open_root", "dnlp_shard_eval", "dnlp_shard_run_device", "dnlp_shard_set_layout",
     "dnlp_shard_share_control", "dnlp_shard_share_output", "dnlp_shard_share_unlink", "dnlp_shard_share_release", "dnlp_shard_share_reset",
+    "dnlp_shard_share_inputs", "dnlp_shard_post_command", "dnlp_shard_wait_command",
 ]
 
 _lib = None
@@ -158,6 +159,10 @@ def lib():
     L.dnlp_shard_share_unlink.argtypes = [C.c_char_p]
     L.dnlp_shard_share_release.argtypes = [C.c_void_p, C.c_int64]
     L.dnlp_shard_share_reset.argtypes = [vp]
+    L.dnlp_shard_share_inputs.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_int32, C.c_int64, C.c_int64,
+                                          C.POINTER(c_f64p), C.POINTER(c_f64p)]
+    L.dnlp_shard_post_command.argtypes = [vp, C.c_int32, c_f64p, c_f64p, C.c_double]
+    L.dnlp_shard_wait_command.argtypes = [vp, C.c_double, C.POINTER(C.c_int32), C.POINTER(C.c_double)]
     _lib = L
     return L
 

@@ -484,7 +484,8 @@ int dnlp_oracle::run_programs(const int *progs, int nprogs, bool force) {
 }
 
 // number of host threads the staging helpers use (see stage_point)
-static int stage_threads() {
+static int stage_threads() { return dnlp_stage_threads(); }
+int dnlp_stage_threads() {
   static const int T = [] {
     unsigned hw = std::thread::hardware_concurrency();
     int ranks = 1;

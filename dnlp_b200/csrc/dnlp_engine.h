@@ -11,6 +11,8 @@
 #include <unordered_map>
 #include <vector>
 
+int dnlp_stage_threads();   // csrc/dnlp_cabi.cu: host threads this rank may use for staging (cores / local ranks - 1, <= 14)
+
 namespace dnlp_detail {
 
 #define CK(call)                                                                           \

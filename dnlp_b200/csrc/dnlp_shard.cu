@@ -215,6 +215,7 @@ struct HostCtl {
   HostCell entered[MAXW];            // entered[r]: number of callbacks rank r has entered
   HostCell done[NSPACE][MAXW];       // done[s][r]: callback number of rank r's last finished copy into output s
   HostCell failed;                   // any rank that gives up raises it, so the others stop waiting
+  HostCell cmd_seq, cmd_prog, cmd_sigma;   // worker loop: the root's latest command (sequence number, program, sigma bits)
 };
 struct HostShare {
   double *base = nullptr;            // the global output array (shared mapping, page-locked here)
@@ -256,6 +257,9 @@ struct dnlp_shard {
   std::vector<int64_t> xsrc, xlen, lsrc, llen;   // runs of the global x / lambda this rank sees (dnlp_shard_set_layout)
   HostShare hs[NSPACE];
   HostCtl *ctl = nullptr;
+  double *in_x = nullptr, *in_lam = nullptr;    // worker loop: the root's x / lambda in shared host memory
+  int64_t in_n = 0, in_m = 0;
+  unsigned long long cmd_count = 0;             // commands posted (root) / seen (workers)
   unsigned long long calls = 0;       // callbacks entered (every rank makes the same sequence of calls)
   double host_timeout_s = 30.0;
   std::string err;
@@ -523,6 +527,8 @@ void dnlp_shard_destroy(dnlp_shard *s) {
   for (void *p : s->owned) cudaFree(p);
   // the shared output arrays outlive the handle (the caller may still hold them): dnlp_shard_share_release
   if (s->ctl) munmap(s->ctl, sizeof(HostCtl));
+  if (s->in_x) munmap(s->in_x, (size_t)std::max<int64_t>(s->in_n, 1) * sizeof(double));
+  if (s->in_lam) munmap(s->in_lam, (size_t)std::max<int64_t>(s->in_m, 1) * sizeof(double));
   delete s;
 }
 
@@ -712,6 +718,85 @@ int dnlp_shard_share_output(dnlp_shard *s, int32_t space, const char *shm_name, 
 
 int dnlp_shard_share_unlink(const char *shm_name) { return shm_unlink(shm_name) == 0 ? 0 : 1; }
 
+// ---- worker loop: one solver process, the other ranks follow --------------------------------------------
+// The reference's callbacks are driven by ONE solver (ipopt_nlpif.py:143-170).  With these three calls only the
+// root runs it: the root posts every callback (program id, x, lambda, sigma) into shared host memory before it
+// evaluates, the other ranks sit in dnlp_shard_wait_command and make the same dnlp_shard_eval call on the shared
+// copies.  The collective delivery at the end of every callback is also what tells the root that everybody has
+// staged the posted point, so the next command may overwrite it.
+int dnlp_shard_share_inputs(dnlp_shard *s, const char *shm_x, const char *shm_lam, int32_t create, int64_t n_global,
+                            int64_t m_global, double **x_host, double **lam_host) {
+  if (!s) { g_comm_error = "shard handle is NULL"; return 1; }
+  std::string &err = s->err;
+  if (!s->ctl) { err = "map the control segment first (dnlp_shard_share_control)"; return 1; }
+  if (s->in_x) { err = "inputs already shared"; return 1; }
+  if (n_global <= 0 || m_global < 0) { err = "bad global sizes"; return 1; }
+  void *px = map_segment(shm_x, (size_t)n_global * sizeof(double), create != 0, err);
+  if (!px) return 1;
+  void *pl = map_segment(shm_lam, (size_t)std::max<int64_t>(m_global, 1) * sizeof(double), create != 0, err);
+  if (!pl) { munmap(px, (size_t)n_global * sizeof(double)); if (create) shm_unlink(shm_x); return 1; }
+  s->in_x = static_cast<double *>(px); s->in_lam = static_cast<double *>(pl);
+  s->in_n = n_global; s->in_m = m_global;
+  *x_host = s->in_x; *lam_host = s->in_lam;
+  return 0;
+}
+
+namespace {
+// dst <- src by a few host threads, touching only the chunks that differ (four of IPOPT's five callbacks repeat x)
+void copy_changed(double *dst, const double *src, int64_t n) {
+  if (n <= 0) return;
+  if (n < (1 << 17)) { if (memcmp(dst, src, (size_t)n * 8) != 0) memcpy(dst, src, (size_t)n * 8); return; }
+  const int T = dnlp_stage_threads();
+  const int64_t chunk = (n + T - 1) / T;
+#pragma omp parallel for num_threads(T) schedule(static, 1)
+  for (int t = 0; t < T; ++t) {
+    const int64_t lo = t * chunk, hi = lo + chunk < n ? lo + chunk : n;
+    if (lo < hi && memcmp(dst + lo, src + lo, (size_t)(hi - lo) * 8) != 0) memcpy(dst + lo, src + lo, (size_t)(hi - lo) * 8);
+  }
+}
+}  // namespace
+
+// root: publish callback `prog` (DNLP_PROG_*; -1 = the workers leave their loop) at (x, lam, sigma)
+int dnlp_shard_post_command(dnlp_shard *s, int32_t prog, const double *x, const double *lam, double sigma) {
+  if (!s) { g_comm_error = "shard handle is NULL"; return 1; }
+  if (!s->in_x) { s->err = "inputs not shared (dnlp_shard_share_inputs)"; return 1; }
+  if (prog >= 0 && x) copy_changed(s->in_x, x, s->in_n);
+  if (prog == DNLP_PROG_HESS && lam) copy_changed(s->in_lam, lam, s->in_m);
+  unsigned long long bits;
+  memcpy(&bits, &sigma, sizeof(bits));
+  s->ctl->cmd_prog.v = (unsigned long long)(long long)prog;
+  s->ctl->cmd_sigma.v = bits;
+  __atomic_store_n(&s->ctl->cmd_seq.v, ++s->cmd_count, __ATOMIC_RELEASE);
+  return 0;
+}
+
+// worker: block until the root posts the next command.  Returns 0 with *prog / *sigma set, 2 when `timeout_s`
+// passed without one (call again), 1 when a rank has failed.  Idle workers back off to short sleeps.
+int dnlp_shard_wait_command(dnlp_shard *s, double timeout_s, int32_t *prog, double *sigma) {
+  if (!s) { g_comm_error = "shard handle is NULL"; return 1; }
+  if (!s->in_x) { s->err = "inputs not shared (dnlp_shard_share_inputs)"; return 1; }
+  const unsigned long long want = s->cmd_count + 1;
+  const auto t0 = std::chrono::steady_clock::now();
+  for (unsigned spins = 0;; ++spins) {
+    if (__atomic_load_n(&s->ctl->cmd_seq.v, __ATOMIC_ACQUIRE) >= want) break;
+    if ((spins & 255u) == 255u) {
+      if (__atomic_load_n(&s->ctl->failed.v, __ATOMIC_ACQUIRE)) { s->err = "a peer gave up"; return 1; }
+      const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      if (dt > timeout_s) return 2;
+      if (dt > 5e-3) std::this_thread::sleep_for(std::chrono::microseconds(50));     // the solver is busy elsewhere
+      else if (dt > 2e-4) std::this_thread::yield();
+    }
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+  }
+  s->cmd_count = want;
+  *prog = (int32_t)(long long)s->ctl->cmd_prog.v;
+  const unsigned long long bits = s->ctl->cmd_sigma.v;
+  memcpy(sigma, &bits, sizeof(bits));
+  return 0;
+}
+
 // Give up shared-host delivery on this handle (a peer could not attach): every output goes back to the
 // device-side route.  Arrays already handed out stay mapped until dnlp_shard_share_release, as after destroy.
 int dnlp_shard_share_reset(dnlp_shard *s) {
@@ -725,7 +810,7 @@ int dnlp_shard_share_reset(dnlp_shard *s) {
 // no longer be evaluated) and nothing reads the array any more.
 int dnlp_shard_share_release(double *host_array, int64_t count) {
   if (!host_array || count <= 0) return 1;
-  cudaHostUnregister(host_array);
+  if (cudaHostUnregister(host_array) != cudaSuccess) cudaGetLastError();   // not an error worth keeping around
   return munmap(host_array, (size_t)count * sizeof(double)) == 0 ? 0 : 1;
 }
 

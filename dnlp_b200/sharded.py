@@ -121,7 +121,7 @@ class _DeviceShard:
 
     DENSE_FRACTION = 0.5
 
-    def __init__(self, owner, store, device, root, nccl):
+    def __init__(self, owner, store, device, root, nccl, workers=False):
         import ctypes as C
 
         from . import _cabi
@@ -167,7 +167,10 @@ class _DeviceShard:
                 int(glen), gconst.ctypes.data_as(_cabi.c_f64p) if self.is_root and glen else None,
                 -1 if dense else int(nd), None if dense else ptr(a[4])))
             info[name] = (dense, int(shared_slots.size), ow_pos, ow_gpos, int(glen))
-        self.shared = self._share_host_arrays(info) if store.world > 1 else {}
+        self.serving, self.x_in, self.lam_in = False, None, None
+        self.shared = self._share_host_arrays(info, bool(workers)) if store.world > 1 else {}
+        if workers and store.world > 1 and not self.serving:
+            raise RuntimeError("the worker loop needs the shared host segments, which could not be set up")
         if self.is_root:
             for name in ("grad", "g", "jac", "hess"):
                 dense, glen = info[name][0], info[name][4]
@@ -200,7 +203,7 @@ class _DeviceShard:
         self.check(L.dnlp_shard_open_root(self.h, table))
         barrier(store)
 
-    def _share_host_arrays(self, info):
+    def _share_host_arrays(self, info, workers=False):
         """Shared-host delivery (csrc/dnlp_shard.cu): every dense output that has no summed entries and whose
         owned entries are a few contiguous runs ON EVERY RANK gets one global array in POSIX shared memory;
         each rank's GPU copies its runs there over its own PCIe link and every rank returns the full array.
@@ -211,10 +214,10 @@ class _DeviceShard:
         from . import _cabi
         from .comm import allgather_array, barrier, bcast
         C, L, store, o = self.C, self._L, self.store, self.o
-        if os.environ.get("DNLP_SHARD_HOST_SHARE", "1") == "0":
+        if os.environ.get("DNLP_SHARD_HOST_SHARE", "1") == "0" and not workers:
             return {}
-        names = ("grad", "g", "jac", "hess")
-        runs, mine = {}, np.zeros(len(names), dtype=np.int32)
+        names = ("grad", "g", "jac", "hess") if os.environ.get("DNLP_SHARD_HOST_SHARE", "1") != "0" else ()
+        runs, mine = {}, np.zeros(4, dtype=np.int32)
         for j, name in enumerate(names):
             dense, n_shared, ow_pos, ow_gpos, glen = info[name]
             if dense and n_shared == 0 and glen > 0:
@@ -223,7 +226,7 @@ class _DeviceShard:
                     runs[name], mine[j] = r, 1
         everyone = np.min(np.stack(allgather_array(store, mine)), axis=0)
         chosen = [name for j, name in enumerate(names) if everyone[j]]
-        if not chosen:
+        if not chosen and not workers:
             return {}
         prefix = os.environ.get("DNLP_SHARD_SHM_PREFIX", "/dnlp")          # POSIX shm name: one leading slash
         tag = bcast(store, ("%s_%d_%06x" % (prefix, os.getpid(), time.time_ns() & 0xFFFFFF)).encode(), self.root).decode()
@@ -241,13 +244,20 @@ class _DeviceShard:
                 self.check(L.dnlp_shard_share_output(self.h, _SPACE[name], seg(name), create, len(r), p64(ls), p64(gd),
                                                      p64(ln), C.byref(base)))
                 arrays[name] = _cabi.shared_view(C.cast(base, C.c_void_p).value, info[name][4])
+            if workers:                                  # the root's x / lambda, for the ranks that follow it
+                xb, lb = _cabi.c_f64p(), _cabi.c_f64p()
+                self.check(L.dnlp_shard_share_inputs(self.h, seg("x"), seg("lam"), create, int(o.n), int(o.m),
+                                                     C.byref(xb), C.byref(lb)))
+                self.x_in = np.ctypeslib.as_array(xb, shape=(int(o.n),))
+                self.lam_in = np.ctypeslib.as_array(lb, shape=(max(int(o.m), 1),))
 
         def give_up(why):
             import sys
             L.dnlp_shard_share_reset(self.h)
             arrays.clear()                            # the views release their mappings as they die
+            self.x_in = self.lam_in = None
             if self.is_root:
-                for name in ["ctl"] + chosen:
+                for name in ["ctl", "x", "lam"] + chosen:
                     L.dnlp_shard_share_unlink(seg(name))
                 sys.stderr.write("dnlp_b200: shared-host delivery not available (%s); owned entries go to the root over "
                                  "NVLink instead\n" % why)
@@ -272,8 +282,9 @@ class _DeviceShard:
         if int(np.min(np.concatenate(allgather_array(store, mine_ok)))) == 0:
             return give_up("a rank could not attach: %s" % status.decode())
         if self.is_root:                                                 # names gone, mappings live on
-            for name in ["ctl"] + chosen:
+            for name in ["ctl"] + (["x", "lam"] if workers else []) + chosen:
                 L.dnlp_shard_share_unlink(seg(name))
+        self.serving = bool(workers)
         for name in chosen:
             o._out[name] = arrays[name]
             if name == "grad":
@@ -305,6 +316,26 @@ class _DeviceShard:
             o._out[name][dyn] = self.compact[name][0][:dyn.size]
         return o._out[name]
 
+    def post(self, name, x, lam=None, sigma=1.0):
+        """Root, worker-loop mode: publish the callback for the ranks in ``serve`` and return the shared copies of
+        (x, lambda) the root itself then evaluates."""
+        from . import _cabi
+        f64p = _cabi.c_f64p
+        self.check(self._L.dnlp_shard_post_command(
+            self.h, -1 if name is None else _PROG[name], None if x is None else x.ctypes.data_as(f64p),
+            None if lam is None else lam.ctypes.data_as(f64p), float(sigma)))
+        return self.x_in, (None if lam is None else self.lam_in)
+
+    def wait(self, timeout_s=1.0):
+        """Worker: the next posted callback as (name, sigma); ``None`` name = leave the loop; ``False`` = nothing yet."""
+        prog, sigma = self.C.c_int32(0), self.C.c_double(0.0)
+        rc = self._L.dnlp_shard_wait_command(self.h, float(timeout_s), self.C.byref(prog), self.C.byref(sigma))
+        if rc == 2:
+            return False, 0.0
+        self.check(rc)
+        names = {v: k for k, v in _PROG.items()}
+        return (None if prog.value < 0 else names[prog.value]), float(sigma.value)
+
     def run_device(self, programs, iters):
         from . import _cabi
         mask = 0
@@ -317,6 +348,10 @@ class _DeviceShard:
     def close(self):
         if getattr(self, "h", None):
             from .comm import barrier
+            if self.serving and self.is_root:
+                self.post(None, None)                 # the workers leave their loop
+            self.serving = False
+            self.x_in = self.lam_in = None
             barrier(self.store)
             self.shared = {}                          # the arrays (owner._out) stay mapped until their last view dies
             self._L.dnlp_shard_destroy(self.h)
@@ -333,7 +368,7 @@ class RowShardedOracles:
     pass the CPU oracle) makes the assembly run on the host through the store."""
 
     def __init__(self, local_problem, layout, global_structure, store=None, oracle_factory=None, device=0,
-                 root=0, nccl=True):
+                 root=0, nccl=True, workers=False):
         self.store = store if store is not None else _SoloStore()
         self.root = int(root)
         gpu = oracle_factory is None
@@ -373,7 +408,9 @@ class RowShardedOracles:
         if len(vr) <= 64 and len(cr) <= 64:
             self._var_runs, self._con_runs = vr, cr
             self._xl, self._ll = np.empty(lay.var_map.size), np.empty(max(lay.con_map.size, 1))
-        self._dev = _DeviceShard(self, self.store, device, self.root, nccl) if gpu else None
+        if workers and not gpu:
+            raise ValueError("the worker loop belongs to the GPU path")
+        self._dev = _DeviceShard(self, self.store, device, self.root, nccl, workers) if gpu else None
 
     @staticmethod
     def _hess_lookup(gs, lay, lhr, lhc):
@@ -426,8 +463,44 @@ class RowShardedOracles:
             raise ValueError("x has %d entries, expected %d" % (x.size, self.n))
         return x
 
+    def _posted(self, name, x, lam=None, sigma=1.0):
+        """Worker-loop mode on the root: publish the callback, continue on the shared copies."""
+        d = self._dev
+        if d is None or not d.serving or not d.is_root:
+            return x, lam
+        x = self._global_x(x)
+        if lam is not None:
+            lam = np.ascontiguousarray(lam, dtype=np.float64).reshape(-1)
+            if lam.size < self.m:
+                raise ValueError("duals has %d entries, expected at least %d" % (lam.size, self.m))
+        return d.post(name, x, lam, sigma)
+
+    def serve(self, poll_s=1.0):
+        """Ranks other than the root, ``workers=True``: follow the root's callbacks until it closes its oracle.
+        Returns the number of callbacks served."""
+        d = self._dev
+        if d is None or not d.serving:
+            raise RuntimeError("serve() needs RowShardedOracles(..., workers=True) on the GPU path")
+        if d.is_root:
+            raise RuntimeError("the root runs the solver; serve() is for the other ranks")
+        served = 0
+        while True:
+            name, sigma = d.wait(poll_s)
+            if name is False:
+                continue
+            if name is None:
+                return served
+            if name == "f":
+                self.objective(d.x_in)
+            elif name == "hess":
+                self.hessian(d.x_in, d.lam_in, sigma)
+            else:
+                self._callback(name, d.x_in)
+            served += 1
+
     def objective(self, x):
         # constants of the objective live in rank 0's local problem (it carries every non-row term)
+        x, _ = self._posted("f", x)
         if self._dev is not None and self._dev.global_inputs:
             return self._dev.eval("f", self._global_x(x))
         xl = self._local_x(x)
@@ -437,6 +510,8 @@ class RowShardedOracles:
         return np.float64(allreduce_sum(self.store, np.array([float(self.local.objective(xl))]))[0])
 
     def _callback(self, name, x, lam=None, sigma=1.0):
+        if name != "hess":                            # the Hessian was posted with its multipliers already
+            x, _ = self._posted(name, x)
         if self._dev is not None and self._dev.global_inputs:
             return self._dev.eval(name, self._global_x(x), lam, sigma)
         xl = self._local_x(x)
@@ -459,6 +534,7 @@ class RowShardedOracles:
         return self.gs.jac_rows, self.gs.jac_cols
 
     def hessian(self, x, duals, obj_factor):
+        x, duals = self._posted("hess", x, duals, obj_factor)
         if self._dev is not None and self._dev.global_inputs:
             lam = np.ascontiguousarray(duals, dtype=np.float64).reshape(-1)
             if lam.size < self.m:

@@ -103,12 +103,68 @@ def _worker(rank, world, port, q, same_gpu, kind, allreduce, host_share=True):
         q.put((rank, "FAIL: %s\n%s" % (e, traceback.format_exc())))
 
 
-def _run(world, same_gpu, kind, allreduce="auto", host_share=True):
+def _worker_loop(rank, world, port, q, same_gpu, kind, allreduce, host_share=True):
+    """Worker-loop mode: ONLY rank 0 issues callbacks (as the one solver process would); the others serve."""
+    try:
+        sys.path.insert(0, ROOT)
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        os.environ["DNLP_SHARD_HOST_SHARE"] = "1" if host_share else "0"
+        from dnlp_b200 import workloads as W
+        from dnlp_b200.comm import SocketStore
+        from dnlp_b200.oracles import GpuOracles
+        from dnlp_b200.sharded import (GlobalStructure, RowShardedOracles, shard_logistic_regression,
+                                       shard_microbench)
+        from golden_util import assert_close
+        dev = 0 if same_gpu else rank
+        store = SocketStore(rank, world, "127.0.0.1", port)
+        if kind == "c3":
+            At, x_init = W.logistic_data(20011, 48, 8, seed=5)
+            glob = W.logistic_regression(At, x_init)
+            local, layout = shard_logistic_regression(At, x_init, rank, world)
+        else:
+            A, x0 = W.microbench_data(4000, 1531, 6, seed=3)
+            glob = W.microbench(A, x0)
+            local, layout = shard_microbench(A, x0, rank, world)
+        o = RowShardedOracles(local, layout, GlobalStructure.from_problem(glob), store=store, device=dev,
+                              nccl=not same_gpu, workers=True)
+        ncalls = 0
+        if rank == 0:
+            ref = GpuOracles(glob, device=dev)
+            rng = np.random.default_rng(23)
+            for it in range(4):
+                x = glob.x0 * (1 + 0.05 * rng.standard_normal(glob.n))
+                lam = rng.standard_normal(glob.m)
+                sigma = float(rng.uniform(0.5, 1.5))
+                # IPOPT's order at an iterate, a line-search style repeat, a Knitro-style list for x
+                assert_close(o.objective(x), ref.objective(x), "f")
+                assert_close(o.constraints(list(x) if it == 2 else x), ref.constraints(x), "g", atol=1e-11)
+                assert_close(o.gradient(x), ref.gradient(x), "grad")
+                assert_close(o.jacobian(x), ref.jacobian(x), "jac")
+                assert_close(o.hessian(x, lam, sigma), ref.hessian(x, lam, sigma), "hess")
+                assert_close(o.hessian(x, 2 * lam, 0.0), ref.hessian(x, 2 * lam, 0.0), "hess, new multipliers")
+                ncalls += 6
+            with pytest.raises(RuntimeError):
+                o.serve()                                    # the root runs the solver
+            ref.close()
+            o.close()                                        # ... and releases the workers
+        else:
+            served = o.serve()
+            assert served == 24, served
+            o.close()
+        store.close()
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put((rank, "FAIL: %s\n%s" % (e, traceback.format_exc())))
+
+
+def _run(world, same_gpu, kind, allreduce="auto", host_share=True, target=None):
     import multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q, same_gpu, kind, allreduce, host_share)) for r in range(world)]
+    procs = [ctx.Process(target=target or _worker, args=(r, world, port, q, same_gpu, kind, allreduce, host_share))
+             for r in range(world)]
     for p in procs:
         p.start()
     import queue
@@ -117,6 +173,8 @@ def _run(world, same_gpu, kind, allreduce="auto", host_share=True):
     while len(results) < world and problem is None:
         try:
             results.append(q.get(timeout=2))
+            if results[-1][1] != "ok":                 # the peers of a failed rank would wait for it: stop them
+                problem = "rank %d: %s" % results[-1]
         except queue.Empty:
             done = {r for r, _ in results}
             dead = [(i, p.exitcode) for i, p in enumerate(procs) if p.exitcode not in (None, 0) and i not in done]
@@ -145,6 +203,13 @@ def test_row_sharded_nvlink_delivery_without_the_shared_host_array():
 
 def test_row_sharded_falls_back_when_the_shared_segment_cannot_be_created():
     _run(2, True, "c3", host_share="broken")
+
+
+@pytest.mark.parametrize("world,kind,host_share", [(2, "c3", True), (3, "c3", True), (2, "c5", True), (2, "c3", False)])
+def test_worker_loop_only_the_root_issues_callbacks(world, kind, host_share):
+    """One solver process (ipopt_nlpif.py:143-170 drives the callbacks from one cyipopt.Problem): rank 0 calls the
+    seven callbacks, the other ranks sit in serve() and follow through the shared host segments."""
+    _run(world, True, kind, host_share=host_share, target=_worker_loop)
 
 
 @pytest.mark.parametrize("kind,allreduce", [("c3", "auto"), ("c5", "auto"), ("c5", "nccl")])
