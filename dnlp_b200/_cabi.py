@@ -161,8 +161,9 @@ def lib():
     L.dnlp_shard_share_reset.argtypes = [vp]
     L.dnlp_shard_share_inputs.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_int32, C.c_int64, C.c_int64,
                                           C.POINTER(c_f64p), C.POINTER(c_f64p)]
-    L.dnlp_shard_post_command.argtypes = [vp, C.c_int32, c_f64p, c_f64p, C.c_double]
-    L.dnlp_shard_wait_command.argtypes = [vp, C.c_double, C.POINTER(C.c_int32), C.POINTER(C.c_double)]
+    L.dnlp_shard_post_command.argtypes = [vp, C.c_int32, c_f64p, c_f64p, C.c_double, C.c_int32, C.POINTER(C.c_int32)]
+    L.dnlp_shard_wait_command.argtypes = [vp, C.c_double, C.POINTER(C.c_int32), C.POINTER(C.c_double),
+                                          C.POINTER(C.c_int32)]
     _lib = L
     return L
 

@@ -588,7 +588,7 @@ int dnlp_oracle::put_lam(const double *lam, double sigma) {
     hlam[0] = sigma;
     CK(cudaMemcpyAsync(V + n, hlam, sizeof(double), cudaMemcpyHostToDevice, stream));
   }
-  if (m > 0) {
+  if (m > 0 && lam != nullptr) {        // NULL: the multipliers of the previous call (sigma may still have changed)
     bool lam_changed = false;
     if (stage_and_upload(hlam + 1, V + n + 1, lam, m, have_last_lam, stream, &lam_changed, err)) return 1;
     if (lam_changed) invalidate(4);
@@ -622,6 +622,7 @@ int dnlp_oracle::put_lam_runs(const double *lg, double sigma, const std::vector<
   }
   int64_t off = 0;
   bool any = false;
+  if (lg == nullptr) { have_last_lam = true; return 0; }   // the multipliers of the previous call
   for (size_t r = 0; r < src.size(); ++r) {
     bool ch = false;
     if (stage_and_upload(hlam + 1 + off, V + n + 1 + off, lg + src[r], len[r], have_last_lam, stream, &ch, err)) return 1;

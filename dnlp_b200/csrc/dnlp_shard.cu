@@ -215,7 +215,8 @@ struct HostCtl {
   HostCell entered[MAXW];            // entered[r]: number of callbacks rank r has entered
   HostCell done[NSPACE][MAXW];       // done[s][r]: callback number of rank r's last finished copy into output s
   HostCell failed;                   // any rank that gives up raises it, so the others stop waiting
-  HostCell cmd_seq, cmd_prog, cmd_sigma;   // worker loop: the root's latest command (sequence number, program, sigma bits)
+  HostCell cmd_seq, cmd_prog, cmd_sigma, cmd_flags;   // worker loop: the root's latest command (sequence number, program,
+                                                      // sigma bits, 1 = x changed | 2 = lambda changed)
 };
 struct HostShare {
   double *base = nullptr;            // the global output array (shared mapping, page-locked here)
@@ -742,37 +743,63 @@ int dnlp_shard_share_inputs(dnlp_shard *s, const char *shm_x, const char *shm_la
 }
 
 namespace {
-// dst <- src by a few host threads, touching only the chunks that differ (four of IPOPT's five callbacks repeat x)
-void copy_changed(double *dst, const double *src, int64_t n) {
-  if (n <= 0) return;
-  if (n < (1 << 17)) { if (memcmp(dst, src, (size_t)n * 8) != 0) memcpy(dst, src, (size_t)n * 8); return; }
-  const int T = dnlp_stage_threads();
+// dst <- src by T host threads, touching only the chunks that differ (four of IPOPT's five callbacks repeat x);
+// returns whether anything differed
+bool copy_changed(double *dst, const double *src, int64_t n, int T) {
+  if (n <= 0) return false;
+  if (n < (1 << 17)) {
+    if (memcmp(dst, src, (size_t)n * 8) == 0) return false;
+    memcpy(dst, src, (size_t)n * 8);
+    return true;
+  }
   const int64_t chunk = (n + T - 1) / T;
-#pragma omp parallel for num_threads(T) schedule(static, 1)
+  int any = 0;
+#pragma omp parallel for num_threads(T) schedule(static, 1) reduction(| : any)
   for (int t = 0; t < T; ++t) {
     const int64_t lo = t * chunk, hi = lo + chunk < n ? lo + chunk : n;
-    if (lo < hi && memcmp(dst + lo, src + lo, (size_t)(hi - lo) * 8) != 0) memcpy(dst + lo, src + lo, (size_t)(hi - lo) * 8);
+    if (lo < hi && memcmp(dst + lo, src + lo, (size_t)(hi - lo) * 8) != 0) {
+      memcpy(dst + lo, src + lo, (size_t)(hi - lo) * 8);
+      any |= 1;
+    }
   }
+  return any != 0;
+}
+// while the root posts, the other ranks only wait for the command: the root may use their share of the cores
+int post_threads(int world) {
+  if (const char *e = getenv("DNLP_STAGE_THREADS")) return atoi(e) > 0 ? atoi(e) : 1;
+  const int hw = (int)std::thread::hardware_concurrency();
+  int ranks = 1;
+  if (const char *e = getenv("LOCAL_WORLD_SIZE")) ranks = atoi(e) > 0 ? atoi(e) : 1;
+  if (ranks < world) ranks = world;           // ranks sharing this host, as far as this process can tell
+  const int t = hw - ranks - 1;
+  return t < 1 ? 1 : (t > 14 ? 14 : t);
 }
 }  // namespace
 
-// root: publish callback `prog` (DNLP_PROG_*; -1 = the workers leave their loop) at (x, lam, sigma)
-int dnlp_shard_post_command(dnlp_shard *s, int32_t prog, const double *x, const double *lam, double sigma) {
+// root: publish callback `prog` (DNLP_PROG_*; -1 = the workers leave their loop) at (x, lam, sigma).
+// *flags: 1 = x differs from the previously posted point, 2 = lambda differs (`force`, same bits: report the vector
+// as changed whatever the compare says, e.g. after calls that bypassed the loop); ranks pass NULL for an unchanged vector to dnlp_shard_eval.
+int dnlp_shard_post_command(dnlp_shard *s, int32_t prog, const double *x, const double *lam, double sigma,
+                            int32_t force, int32_t *flags) {
   if (!s) { g_comm_error = "shard handle is NULL"; return 1; }
   if (!s->in_x) { s->err = "inputs not shared (dnlp_shard_share_inputs)"; return 1; }
-  if (prog >= 0 && x) copy_changed(s->in_x, x, s->in_n);
-  if (prog == DNLP_PROG_HESS && lam) copy_changed(s->in_lam, lam, s->in_m);
+  const int T = post_threads(s->c->world);
+  int32_t fl = 0;
+  if (prog >= 0 && x && (copy_changed(s->in_x, x, s->in_n, T) || (force & 1))) fl |= 1;
+  if (prog == DNLP_PROG_HESS && lam && (copy_changed(s->in_lam, lam, s->in_m, T) || (force & 2))) fl |= 2;
+  if (flags) *flags = fl;
   unsigned long long bits;
   memcpy(&bits, &sigma, sizeof(bits));
   s->ctl->cmd_prog.v = (unsigned long long)(long long)prog;
   s->ctl->cmd_sigma.v = bits;
+  s->ctl->cmd_flags.v = (unsigned long long)fl;
   __atomic_store_n(&s->ctl->cmd_seq.v, ++s->cmd_count, __ATOMIC_RELEASE);
   return 0;
 }
 
 // worker: block until the root posts the next command.  Returns 0 with *prog / *sigma set, 2 when `timeout_s`
 // passed without one (call again), 1 when a rank has failed.  Idle workers back off to short sleeps.
-int dnlp_shard_wait_command(dnlp_shard *s, double timeout_s, int32_t *prog, double *sigma) {
+int dnlp_shard_wait_command(dnlp_shard *s, double timeout_s, int32_t *prog, double *sigma, int32_t *flags) {
   if (!s) { g_comm_error = "shard handle is NULL"; return 1; }
   if (!s->in_x) { s->err = "inputs not shared (dnlp_shard_share_inputs)"; return 1; }
   const unsigned long long want = s->cmd_count + 1;
@@ -792,6 +819,7 @@ int dnlp_shard_wait_command(dnlp_shard *s, double timeout_s, int32_t *prog, doub
   }
   s->cmd_count = want;
   *prog = (int32_t)(long long)s->ctl->cmd_prog.v;
+  if (flags) *flags = (int32_t)s->ctl->cmd_flags.v;
   const unsigned long long bits = s->ctl->cmd_sigma.v;
   memcpy(sigma, &bits, sizeof(bits));
   return 0;
@@ -836,11 +864,14 @@ static int shard_eval_body(dnlp_shard *s, int32_t prog, const double *x_local, c
   const int space = prog + 1;
   ++s->calls;
   if (s->ctl) __atomic_store_n(&s->ctl->entered[s->c->rank].v, s->calls, __ATOMIC_RELEASE);
+  // x_local / lam_local == NULL: "the vector of the previous call" (worker loop: the root has already compared it)
+  if (!x_local && !o->have_last_x) { err = "no point has been staged yet"; return 1; }
+  if (prog == DNLP_PROG_HESS && !lam_local && !o->have_last_lam && o->m > 0) { err = "no multipliers have been staged yet"; return 1; }
   if (!s->xsrc.empty()) {            // global vectors: staged run by run, no gathered host copy
-    if (o->put_x_runs(x_local, s->xsrc, s->xlen)) { err = o->err; return 1; }
+    if (x_local && o->put_x_runs(x_local, s->xsrc, s->xlen)) { err = o->err; return 1; }
     if (prog == DNLP_PROG_HESS && o->put_lam_runs(lam_local, sigma, s->lsrc, s->llen)) { err = o->err; return 1; }
   } else {
-    if (o->put_x(x_local)) { err = o->err; return 1; }
+    if (x_local && o->put_x(x_local)) { err = o->err; return 1; }
     if (prog == DNLP_PROG_HESS && o->put_lam(lam_local, sigma)) { err = o->err; return 1; }
   }
   if (o->run_program(prog, false)) { err = o->err; return 1; }

@@ -167,7 +167,7 @@ class _DeviceShard:
                 int(glen), gconst.ctypes.data_as(_cabi.c_f64p) if self.is_root and glen else None,
                 -1 if dense else int(nd), None if dense else ptr(a[4])))
             info[name] = (dense, int(shared_slots.size), ow_pos, ow_gpos, int(glen))
-        self.serving, self.x_in, self.lam_in = False, None, None
+        self.serving, self.x_in, self.lam_in, self._force_post = False, None, None, 3
         self.shared = self._share_host_arrays(info, bool(workers)) if store.world > 1 else {}
         if workers and store.world > 1 and not self.serving:
             raise RuntimeError("the worker loop needs the shared host segments, which could not be set up")
@@ -307,7 +307,8 @@ class _DeviceShard:
         elif self.is_root:
             out = o._out[name] if self.dense[name] else self.compact[name][0]
         self.check(self._L.dnlp_shard_eval(
-            self.h, _PROG[name], xl.ctypes.data_as(f64p), None if lam is None else lam.ctypes.data_as(f64p),
+            self.h, _PROG[name], None if xl is None else xl.ctypes.data_as(f64p),
+            None if lam is None else lam.ctypes.data_as(f64p),
             float(sigma), None if out is None else out.ctypes.data_as(f64p)))
         if name == "f":
             return np.float64(self._f[0])
@@ -321,20 +322,26 @@ class _DeviceShard:
         (x, lambda) the root itself then evaluates."""
         from . import _cabi
         f64p = _cabi.c_f64p
+        flags = self.C.c_int32(0)
         self.check(self._L.dnlp_shard_post_command(
             self.h, -1 if name is None else _PROG[name], None if x is None else x.ctypes.data_as(f64p),
-            None if lam is None else lam.ctypes.data_as(f64p), float(sigma)))
-        return self.x_in, (None if lam is None else self.lam_in)
+            None if lam is None else lam.ctypes.data_as(f64p), float(sigma), int(self._force_post),
+            self.C.byref(flags)))
+        if name is not None:                          # bit 1: x (every command carries it), bit 2: lambda (Hessian only)
+            self._force_post &= ~(3 if (name == "hess" and lam is not None) else 1)
+        # a vector the root found unchanged is passed on as None: nobody compares it again
+        return (self.x_in if flags.value & 1 else None), (self.lam_in if (lam is not None and flags.value & 2) else None)
 
     def wait(self, timeout_s=1.0):
         """Worker: the next posted callback as (name, sigma); ``None`` name = leave the loop; ``False`` = nothing yet."""
-        prog, sigma = self.C.c_int32(0), self.C.c_double(0.0)
-        rc = self._L.dnlp_shard_wait_command(self.h, float(timeout_s), self.C.byref(prog), self.C.byref(sigma))
+        prog, sigma, flags = self.C.c_int32(0), self.C.c_double(0.0), self.C.c_int32(0)
+        rc = self._L.dnlp_shard_wait_command(self.h, float(timeout_s), self.C.byref(prog), self.C.byref(sigma),
+                                             self.C.byref(flags))
         if rc == 2:
-            return False, 0.0
+            return False, 0.0, 0
         self.check(rc)
         names = {v: k for k, v in _PROG.items()}
-        return (None if prog.value < 0 else names[prog.value]), float(sigma.value)
+        return (None if prog.value < 0 else names[prog.value]), float(sigma.value), int(flags.value)
 
     def run_device(self, programs, iters):
         from . import _cabi
@@ -466,14 +473,27 @@ class RowShardedOracles:
     def _posted(self, name, x, lam=None, sigma=1.0):
         """Worker-loop mode on the root: publish the callback, continue on the shared copies."""
         d = self._dev
-        if d is None or not d.serving or not d.is_root:
-            return x, lam
         x = self._global_x(x)
         if lam is not None:
             lam = np.ascontiguousarray(lam, dtype=np.float64).reshape(-1)
             if lam.size < self.m:
                 raise ValueError("duals has %d entries, expected at least %d" % (lam.size, self.m))
         return d.post(name, x, lam, sigma)
+
+    def set_worker_loop(self, enabled):
+        """Switch between the worker loop (root posts, the others ``serve``) and SPMD calls (every rank makes every
+        call itself) on an oracle created with ``workers=True``; collective: every rank sets the same mode."""
+        d = self._dev
+        if d is None or d.x_in is None:
+            raise RuntimeError("needs RowShardedOracles(..., workers=True) on the GPU path")
+        d.serving = bool(enabled)
+        d._force_post = 3             # calls outside the loop may have moved the point: the next posts re-stage x and lambda
+
+    def release_workers(self):
+        """Root: make the ranks in ``serve`` return (the oracle stays usable; ``close`` does this by itself)."""
+        d = self._dev
+        if d is not None and d.serving and d.is_root:
+            d.post(None, None)
 
     def serve(self, poll_s=1.0):
         """Ranks other than the root, ``workers=True``: follow the root's callbacks until it closes its oracle.
@@ -485,35 +505,49 @@ class RowShardedOracles:
             raise RuntimeError("the root runs the solver; serve() is for the other ranks")
         served = 0
         while True:
-            name, sigma = d.wait(poll_s)
+            name, sigma, flags = d.wait(poll_s)
             if name is False:
                 continue
             if name is None:
                 return served
+            x = d.x_in if flags & 1 else None             # None: the root found it unchanged, keep what is staged
             if name == "f":
-                self.objective(d.x_in)
+                self._objective(x)
             elif name == "hess":
-                self.hessian(d.x_in, d.lam_in, sigma)
+                self._hessian(x, d.lam_in if flags & 2 else None, sigma)
             else:
-                self._callback(name, d.x_in)
+                self._callback(name, x, posted=True)
             served += 1
 
     def objective(self, x):
-        # constants of the objective live in rank 0's local problem (it carries every non-row term)
-        x, _ = self._posted("f", x)
-        if self._dev is not None and self._dev.global_inputs:
-            return self._dev.eval("f", self._global_x(x))
+        if self._serving_root():
+            x, _ = self._posted("f", x)
+            return self._objective(x)
+        return self._objective(self._global_x(x))
+
+    def _objective(self, x):
+        # constants of the objective live in rank 0's local problem (it carries every non-row term);
+        # x is None in the worker loop when the root found the point unchanged
+        if self._dev is not None and (self._dev.global_inputs or x is None):
+            return self._dev.eval("f", x)
         xl = self._local_x(x)
         if self._dev is not None:
             return self._dev.eval("f", xl)
         from .comm import allreduce_sum
         return np.float64(allreduce_sum(self.store, np.array([float(self.local.objective(xl))]))[0])
 
-    def _callback(self, name, x, lam=None, sigma=1.0):
-        if name != "hess":                            # the Hessian was posted with its multipliers already
-            x, _ = self._posted(name, x)
-        if self._dev is not None and self._dev.global_inputs:
-            return self._dev.eval(name, self._global_x(x), lam, sigma)
+    def _serving_root(self):
+        d = self._dev
+        return d is not None and d.serving and d.is_root
+
+    def _callback(self, name, x, lam=None, sigma=1.0, posted=False):
+        if not posted:
+            if self._serving_root():
+                x, _ = self._posted(name, x)
+            else:
+                x = self._global_x(x)
+        if self._dev is not None and (self._dev.global_inputs or x is None):
+            return self._dev.eval(name, x, lam, sigma)
         xl = self._local_x(x)
         if self._dev is not None:
             return self._dev.eval(name, xl, lam, sigma)
@@ -534,13 +568,26 @@ class RowShardedOracles:
         return self.gs.jac_rows, self.gs.jac_cols
 
     def hessian(self, x, duals, obj_factor):
-        x, duals = self._posted("hess", x, duals, obj_factor)
+        if self._serving_root():
+            x, duals = self._posted("hess", x, duals, obj_factor)
+        else:
+            x = self._global_x(x)
+            duals = np.ascontiguousarray(duals, dtype=np.float64).reshape(-1)
+            if duals.size < self.m:
+                raise ValueError("duals has %d entries, expected at least %d" % (duals.size, self.m))
+        return self._hessian(x, duals, obj_factor)
+
+    def _hessian(self, x, lam, sigma):
+        """x / lam: global vectors, or None (worker loop: unchanged since the previous callback)."""
         if self._dev is not None and self._dev.global_inputs:
-            lam = np.ascontiguousarray(duals, dtype=np.float64).reshape(-1)
-            if lam.size < self.m:
-                raise ValueError("duals has %d entries, expected at least %d" % (lam.size, self.m))
-            return self._callback("hess", x, lam, obj_factor)
-        return self._callback("hess", x, self._local_lam(duals), obj_factor)
+            return self._callback("hess", x, lam, sigma, posted=True)
+        if self._dev is not None and x is None and lam is None:
+            return self._dev.eval("hess", None, None, sigma)
+        if self._dev is not None and (x is None or lam is None):
+            # fragmented index maps: the library wants both vectors gathered or neither; re-gather from the shared copies
+            x = self._dev.x_in if x is None else x
+            lam = self._dev.lam_in if lam is None else lam
+        return self._callback("hess", x, self._local_lam(lam), sigma, posted=True)
 
     def hessianstructure(self):
         return self.gs.hess_rows, self.gs.hess_cols

@@ -251,11 +251,13 @@ int dnlp_shard_share_reset(dnlp_shard *s);      /* a peer could not attach: back
  * ipopt_nlpif.py:143-170).  The root posts every callback - program id (-1: leave the loop), x, lambda, sigma -
  * into shared host memory before it evaluates; the other ranks block in dnlp_shard_wait_command (0 = command
  * received, 2 = timeout_s passed, call again, 1 = a rank failed) and then make the same dnlp_shard_eval call on the
- * shared copies *x_host / *lam_host. */
+ * shared copies *x_host / *lam_host - or with NULL for a vector the flags report as unchanged since the previous
+ * command (dnlp_shard_eval then keeps the point / multipliers it has, no compare). */
 int dnlp_shard_share_inputs(dnlp_shard *s, const char *shm_x, const char *shm_lam, int32_t create, int64_t n_global,
                             int64_t m_global, double **x_host, double **lam_host);
-int dnlp_shard_post_command(dnlp_shard *s, int32_t prog, const double *x, const double *lam, double sigma);
-int dnlp_shard_wait_command(dnlp_shard *s, double timeout_s, int32_t *prog, double *sigma);
+int dnlp_shard_post_command(dnlp_shard *s, int32_t prog, const double *x, const double *lam, double sigma,
+                            int32_t force, int32_t *flags);   /* *flags: 1 = x changed | 2 = lambda changed */
+int dnlp_shard_wait_command(dnlp_shard *s, double timeout_s, int32_t *prog, double *sigma, int32_t *flags);
 int dnlp_shard_share_release(double *host_array, int64_t count);   /* unpin + unmap; the array outlives dnlp_shard_destroy */
 
 #ifdef __cplusplus

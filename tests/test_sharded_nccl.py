@@ -145,11 +145,30 @@ def _worker_loop(rank, world, port, q, same_gpu, kind, allreduce, host_share=Tru
                 ncalls += 6
             with pytest.raises(RuntimeError):
                 o.serve()                                    # the root runs the solver
-            ref.close()
-            o.close()                                        # ... and releases the workers
+            o.release_workers()
         else:
             served = o.serve()
             assert served == 24, served
+        # every rank calls for a while (SPMD) at ANOTHER point, then the loop resumes at the point posted last: the
+        # shared copy still holds it, the devices do not - the root must re-stage, not trust the compare
+        from dnlp_b200.comm import barrier
+        rng2 = np.random.default_rng(99)
+        x2 = glob.x0 * (1 + 0.05 * rng2.standard_normal(glob.n))
+        lam2 = rng2.standard_normal(glob.m)
+        o.set_worker_loop(False)
+        barrier(store)
+        f2, h2 = o.objective(x2), o.hessian(x2, lam2, 1.25)
+        o.set_worker_loop(True)
+        if rank == 0:
+            assert_close(f2, ref.objective(x2), "f (SPMD phase)")
+            assert_close(h2, ref.hessian(x2, lam2, 1.25), "hess (SPMD phase)")
+            assert_close(o.objective(x), ref.objective(x), "f after the switch back")
+            assert_close(o.hessian(x, 2 * lam, 0.0), ref.hessian(x, 2 * lam, 0.0), "hess after the switch back")
+            assert_close(o.gradient(x), ref.gradient(x), "grad after the switch back")
+            ref.close()
+            o.close()                                        # ... and releases the workers
+        else:
+            assert o.serve() == 3
             o.close()
         store.close()
         q.put((rank, "ok"))
