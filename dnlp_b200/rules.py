@@ -68,36 +68,45 @@ class Builder:
 
     # ---- emission ----------------------------------------------------------
     def _deps_of_slots(self, slots):
-        slots = np.asarray(slots, dtype=np.int64)
-        slots = slots[slots >= 0]
-        uses_lam = bool(np.any((slots >= self.tape.n) & (slots < self.tape.n + 1 + self.tape.m)))
-        self._last_mask = ((T.DEP_X if np.any(slots < self.tape.n) else 0)
-                           | (T.DEP_SIGMA if np.any(slots == self.tape.n) else 0)
-                           | (T.DEP_LAMBDA if np.any((slots > self.tape.n) & (slots < self.tape.n + 1 + self.tape.m))
-                              else 0)
-                           | (T.DEP_PARAM if np.any((slots >= self.tape.param_slot) & (slots < self.tape.tmp_slot))
-                              else 0))
+        """Which inputs (x / sigma / lambda / parameters) and which earlier instructions the slots read.
+        One binning pass over the slots (they can be 100 M entries): every boundary that matters - the input ranges
+        and the producers' output ranges - is an edge, so an interval between two edges is either inside a range or
+        outside it, and a range was read iff one of its intervals is non-empty."""
+        slots = np.asarray(slots).reshape(-1)
+        tp = self.tape
+        n, m = tp.n, tp.m
+        prod = sorted(self._producers)              # allocation order != emission order
+        edges = [0, n, n + 1, n + 1 + m, tp.param_slot, tp.tmp_slot]
+        for p in prod:
+            edges += [p[0], p[1]]
+        edges = np.unique(np.asarray(edges, dtype=np.int64))
+        if slots.size:
+            which = np.searchsorted(edges, slots, side="right")          # 0: below the first edge (the -1 "no factor")
+            hit = np.bincount(which, minlength=edges.size + 1)[1:] > 0   # hit[j]: some slot in [edges[j], edges[j+1])
+        else:
+            hit = np.zeros(edges.size, dtype=bool)
+        lo = edges
+
+        def any_in(a, b):
+            return bool(np.any(hit & (lo >= a) & (lo < b))) if b > a else False
+        uses_lam = any_in(n, n + 1 + m)
+        self._last_mask = ((T.DEP_X if any_in(0, n) else 0) | (T.DEP_SIGMA if any_in(n, n + 1) else 0)
+                           | (T.DEP_LAMBDA if any_in(n + 1, n + 1 + m) else 0)
+                           | (T.DEP_PARAM if any_in(tp.param_slot, tp.tmp_slot) else 0))
         deps = set()
-        if self._producers and slots.size:
-            prod = sorted(self._producers)          # allocation order != emission order
-            starts = np.array([p[0] for p in prod], dtype=np.int64)
-            ends = np.array([p[1] for p in prod], dtype=np.int64)
-            ids = np.array([p[2] for p in prod], dtype=np.int64)
-            odd = np.array([p[3] for p in prod], dtype=np.int64)
-            tmp = slots[slots >= self.tape.tmp_slot]
-            if tmp.size:
-                k = np.searchsorted(starts, tmp, side="right") - 1
-                ok = (k >= 0) & (tmp < ends[np.maximum(k, 0)])
-                k, tmp = k[ok], tmp[ok]
-                paired = odd[k] != -2                # -2: a plain contiguous range
-                plain = np.bincount(k[~paired], minlength=len(prod)) > 0
-                deps = set(ids[plain].tolist())
-                if paired.any():                     # interleaved region: even slots / odd slots have different writers
-                    par = (tmp[paired] - starts[k[paired]]) & 1
-                    ev = np.bincount(k[paired][par == 0], minlength=len(prod)) > 0
-                    od = np.bincount(k[paired][par == 1], minlength=len(prod)) > 0
-                    deps |= set(int(i) for i in ids[ev].tolist() if i >= 0)
-                    deps |= set(int(i) for i in odd[od].tolist() if i >= 0)
+        for start, end, pid, odd in prod:
+            if start < tp.tmp_slot or not any_in(start, end):
+                continue
+            if odd == -2:                           # a plain contiguous range
+                deps.add(int(pid))
+                continue
+            # interleaved region: even slots / odd slots have different writers
+            inside = slots[(slots >= start) & (slots < end)]
+            par = (inside.astype(np.int64) - start) & 1
+            if pid >= 0 and np.any(par == 0):
+                deps.add(int(pid))
+            if odd >= 0 and np.any(par == 1):
+                deps.add(int(odd))
         return deps, uses_lam
 
     def _finish(self, ins, read_slots):
