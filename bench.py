@@ -578,13 +578,17 @@ def bench_c3_sharded(args, grp, hbm_peak, peak_src):
         grp.barrier()
         dt, E2 = float(grp.max([dt])[0]), int(grp.max([E2])[0])
         h2d = float(grp.sum([8.0 * (layout.var_map.size + layout.con_map.size + 1)])[0])
-        e2e = {"value": args.steps * E2 / dt, "unit": "evals/s", "evals_per_step": E2,
-               "mode": "worker loop: rank 0 alone issues the five callbacks (as the one solver process would), the other "
-                       "ranks follow through shared host memory (RowShardedOracles.serve)",
-               "spmd_value": args.steps * E_spmd / dt_spmd,
-               "spmd_note": "the same loop with every rank issuing every callback itself (no posting of x / lambda)",
-               "h2d_bytes_per_step": int(E2 * h2d),
-               "d2h_bytes_per_step": int(E2 * 8 * (1 + glob.n + glob.m + gs.dynamic["jac"].size + gs.hess_rows.size)),
+        e2e = {"value": args.steps * E_spmd / dt_spmd, "unit": "evals/s", "evals_per_step": E_spmd,
+               "mode": "every rank issues the five callbacks with its own host copies of x / lambda (SPMD, as the C4 "
+                       "ranks do with their slices of the starts)",
+               "one_solver_value": args.steps * E2 / dt,
+               "one_solver_evals_per_step": E2,
+               "one_solver_note": "worker loop: rank 0 ALONE issues the callbacks (what one IPOPT process would do), "
+                                  "posting x / lambda through shared host memory; the other ranks follow in "
+                                  "RowShardedOracles.serve().  The root then reads all of x once per callback instead "
+                                  "of its slice, which is the difference to `value`",
+               "h2d_bytes_per_step": int(E_spmd * h2d),
+               "d2h_bytes_per_step": int(E_spmd * 8 * (1 + glob.n + glob.m + gs.dynamic["jac"].size + gs.hess_rows.size)),
                "api": "RowShardedOracles five callbacks, host buffers; " + (
                    "outputs %s: every GPU copies the runs it owns over its own PCIe link into one host array shared by "
                    "the ranks (every rank returns the full output); the rest is stored into the root's device array over "
