@@ -772,7 +772,7 @@ bool copy_changed(double *dst, const double *src, int64_t n, int T) {
 int dnlp_shard_post_command(dnlp_shard *s, int32_t prog, const double *x, const double *lam, double sigma,
                             int32_t force, int32_t *flags) {
   if (!s) { g_comm_error = "shard handle is NULL"; return 1; }
-  if (!s->in_x) { s->err = "inputs not shared (dnlp_shard_share_inputs)"; return 1; }
+  if (!s->in_x || !s->ctl) { s->err = "inputs not shared (dnlp_shard_share_inputs)"; return 1; }
   // this rank's own share of the cores: the other ranks' staging teams keep spinning for a while after their last
   // parallel region, so borrowing "their" cores oversubscribes the host (measured: 17 ms per evaluation instead of 3)
   const int T = dnlp_stage_threads();
@@ -793,7 +793,7 @@ int dnlp_shard_post_command(dnlp_shard *s, int32_t prog, const double *x, const 
 // passed without one (call again), 1 when a rank has failed.  Idle workers back off to short sleeps.
 int dnlp_shard_wait_command(dnlp_shard *s, double timeout_s, int32_t *prog, double *sigma, int32_t *flags) {
   if (!s) { g_comm_error = "shard handle is NULL"; return 1; }
-  if (!s->in_x) { s->err = "inputs not shared (dnlp_shard_share_inputs)"; return 1; }
+  if (!s->in_x || !s->ctl) { s->err = "inputs not shared (dnlp_shard_share_inputs)"; return 1; }
   const unsigned long long want = s->cmd_count + 1;
   const auto t0 = std::chrono::steady_clock::now();
   for (unsigned spins = 0;; ++spins) {
@@ -822,6 +822,8 @@ int dnlp_shard_wait_command(dnlp_shard *s, double timeout_s, int32_t *prog, doub
 int dnlp_shard_share_reset(dnlp_shard *s) {
   if (!s) { g_comm_error = "shard handle is NULL"; return 1; }
   for (HostShare &H : s->hs) H = HostShare();
+  if (s->in_x) { munmap(s->in_x, (size_t)std::max<int64_t>(s->in_n, 1) * sizeof(double)); s->in_x = nullptr; }
+  if (s->in_lam) { munmap(s->in_lam, (size_t)std::max<int64_t>(s->in_m, 1) * sizeof(double)); s->in_lam = nullptr; }
   if (s->ctl) { munmap(s->ctl, sizeof(HostCtl)); s->ctl = nullptr; }
   return 0;
 }

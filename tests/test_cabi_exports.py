@@ -60,6 +60,22 @@ def test_null_handle_is_an_error_not_a_crash():
     assert L.dnlp_batch_upload(None, p, p, p) != 0
     assert L.dnlp_kernel_launches(None) == -1
     assert b"NULL" in L.dnlp_last_error(None)
+    # the sharded oracle's host-side entry points (shared-host delivery, worker loop) as well
+    import ctypes as C
+    i64 = np.zeros(1, dtype=np.int64)
+    p64 = i64.ctypes.data_as(_cabi.c_i64p)
+    out, out2 = _cabi.c_f64p(), _cabi.c_f64p()
+    prog, flags, sig = C.c_int32(0), C.c_int32(0), C.c_double(0.0)
+    assert L.dnlp_shard_eval(None, 0, p, p, 1.0, q) != 0
+    assert L.dnlp_shard_share_control(None, b"/dnlp_test_none", 0) != 0
+    assert L.dnlp_shard_share_output(None, 2, b"/dnlp_test_none", 0, 1, p64, p64, p64, C.byref(out)) != 0
+    assert L.dnlp_shard_share_inputs(None, b"/dnlp_test_x", b"/dnlp_test_l", 0, 1, 1, C.byref(out), C.byref(out2)) != 0
+    assert L.dnlp_shard_post_command(None, 0, p, p, 1.0, 0, C.byref(flags)) != 0
+    assert L.dnlp_shard_wait_command(None, 0.0, C.byref(prog), C.byref(sig), C.byref(flags)) != 0
+    assert L.dnlp_shard_share_reset(None) != 0
+    assert L.dnlp_shard_share_release(None, 0) != 0
+    assert L.dnlp_shard_share_unlink(b"/dnlp_test_segment_that_does_not_exist") != 0
+    assert b"NULL" in L.dnlp_shard_last_error(None)
 
     class _Dead(_cabi.DeviceTape):
         def __init__(self):
