@@ -817,6 +817,44 @@ class Builder:
         # keep the operand's own shape: SciPy treats a 1-D value as a row, as in the reference
         return tags.reshape(operand.shape, order="F"), sv
 
+    CHAIN_FASTPATH = True
+
+    def _chain_through_diagonal(self, A, a_src, a_rows, a_cols, opval, r, c, v):
+        """``_chain_through`` for an inner Jacobian with at most one entry per row and per column, both index
+        arrays increasing (every elementwise atom of a variable: rows = cols = arange).  Each product entry then
+        has exactly one term, and SciPy's row-by-row SpGEMM (csr_matmat: columns of an output row come out in
+        REVERSE order of first touch, a linked list threaded through the touched columns) lists row i as A's
+        stored entries of row i that meet a non-empty row of the inner Jacobian, last to first - no pattern
+        product, no key matching.  Returns None when the shape of the inner Jacobian is anything else."""
+        r = np.asarray(r, dtype=np.int64)
+        c = np.asarray(c, dtype=np.int64)
+        if r.size == 0 or v.K != r.size or r.size != c.size:
+            return None
+        if r.size > 1 and not (bool(np.all(r[1:] > r[:-1])) and bool(np.all(c[1:] > c[:-1]))):
+            return None
+        if np.any(v.term_counts() != 1):                   # an entry that is a sum (or an exact zero) goes the long way
+            return None
+        slot = np.full(A.shape[1], -1, dtype=np.int64)
+        slot[r] = np.arange(r.size, dtype=np.int64)
+        hit = slot[a_cols]
+        ea = np.flatnonzero(hit >= 0)                      # A's stored entries that produce something, CSR order
+        rows = a_rows[ea]
+        cnt = np.bincount(rows, minlength=A.shape[0])
+        ptr = np.zeros(A.shape[0] + 1, dtype=np.int64)
+        np.cumsum(cnt, out=ptr[1:])
+        dest = ptr[rows] + cnt[rows] - 1 - (np.arange(ea.size, dtype=np.int64) - ptr[rows])
+        rev = np.empty(ea.size, dtype=np.int64)
+        rev[dest] = ea
+        eb = hit[rev]
+        vals = self.mul(opval.gather(a_src[rev]), v.gather(eb))
+        prow, pcol = a_rows[rev], c[eb]
+        cm = vals.is_const_mask()                          # SciPy drops products that are exactly zero
+        drop = cm & (vals.const_values() == 0.0)
+        if drop.any():
+            keep = np.where(~drop)[0]
+            prow, pcol, vals = prow[keep], pcol[keep], vals.gather(keep)
+        return prow, pcol, vals
+
     def _chain_through(self, kron_csr_tags, opval, inner_jac, inner_size):
         """(d @ inner_jac.tocsc()).tocoo() with symbolic values.
 
@@ -831,6 +869,10 @@ class Builder:
         A1 = sp.csr_array((np.ones(A.nnz), A.indices, A.indptr), shape=A.shape)
         for var, (r, c, v) in inner_jac.items():
             ncols = self.var_size[var]
+            fast = self._chain_through_diagonal(A, a_src, a_rows, a_cols, opval, r, c, v) if self.CHAIN_FASTPATH else None
+            if fast is not None:
+                out[var] = fast
+                continue
             B1 = sp.coo_array((np.ones(len(r)), (r, c)), shape=(A.shape[1], ncols)).tocsc()
             B1.data[:] = 1.0
             P = (A1 @ B1).tocoo()
