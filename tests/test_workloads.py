@@ -187,3 +187,44 @@ def test_kron_fast_path_is_scipys_kron_entry_for_entry():
                 np.testing.assert_array_equal(a.coords[0], b.coords[0])
                 np.testing.assert_array_equal(a.coords[1], b.coords[1])
                 np.testing.assert_array_equal(a.data, b.data)
+
+
+def _same_tapes(a, b, path="tape"):
+    if isinstance(a, np.ndarray) or isinstance(b, np.ndarray):
+        assert isinstance(a, np.ndarray) and isinstance(b, np.ndarray), path
+        assert a.dtype == b.dtype and a.shape == b.shape and np.array_equal(a, b, equal_nan=True), path
+    elif isinstance(a, (list, tuple)):
+        assert len(a) == len(b), path
+        for i, (x, y) in enumerate(zip(a, b)):
+            _same_tapes(x, y, "%s[%d]" % (path, i))
+    elif isinstance(a, dict):
+        assert a.keys() == b.keys(), path
+        for k in a:
+            _same_tapes(a[k], b[k], "%s.%s" % (path, k))
+    elif hasattr(a, "__slots__"):
+        for k in a.__slots__:
+            _same_tapes(getattr(a, k, None), getattr(b, k, None), "%s.%s" % (path, k))
+    elif hasattr(a, "__dict__") and not callable(a):
+        for k in a.__dict__:
+            _same_tapes(a.__dict__[k], b.__dict__.get(k), "%s.%s" % (path, k))
+    else:
+        assert a == b or (a != a and b != b), (path, a, b)
+
+
+def test_diagonal_chain_rule_shortcut_emits_the_same_tape(monkeypatch):
+    """rules.Builder._chain_through_diagonal writes SciPy's SpGEMM order down directly (reversed first touch per
+    row); the generic route runs SciPy on the patterns.  Same tape, entry for entry, incl. rows of A with several
+    entries, empty rows and a lifted (log / entr) variant whose inner Jacobians are not all diagonal."""
+    from dnlp_b200.compiler import compile_problem
+    from dnlp_b200.rules import Builder
+    cases = []
+    A, x0 = W.microbench_data(4000, 1531, 6, seed=3)
+    cases.append(W.microbench(A, x0))
+    A2, x2 = W.microbench_data(800, 1200, 3, seed=4)          # more rows than a segment has columns: repeated columns
+    cases.append(W.microbench(A2, x2))
+    for prob in cases:
+        monkeypatch.setattr(Builder, "CHAIN_FASTPATH", True)
+        fast = compile_problem(prob)
+        monkeypatch.setattr(Builder, "CHAIN_FASTPATH", False)
+        generic = compile_problem(prob)
+        _same_tapes(fast, generic)
