@@ -846,7 +846,13 @@ class Builder:
         rev = np.empty(ea.size, dtype=np.int64)
         rev[dest] = ea
         eb = hit[rev]
-        vals = self.mul(opval.gather(a_src[rev]), v.gather(eb))
+        ia = a_src[rev]
+        if opval.is_unit() and v.is_unit() and not np.any(opval.f1 != NONE) and not np.any(opval.f2 != NONE):
+            # constant times one term: what mul() -> mul_simple() builds, without the intermediate vectors
+            F = -np.sort(-np.stack([v.f1[eb], v.f2[eb]], axis=1), axis=1)
+            vals = SymVec(eb.size, np.arange(eb.size, dtype=np.int32), opval.coef[ia] * v.coef[eb], F[:, 0], F[:, 1])
+        else:
+            vals = self.mul(opval.gather(ia), v.gather(eb))
         prow, pcol = a_rows[rev], c[eb]
         cm = vals.is_const_mask()                          # SciPy drops products that are exactly zero
         drop = cm & (vals.const_values() == 0.0)
