@@ -505,8 +505,9 @@ def bench_c3_sharded(args, grp, hbm_peak, peak_src):
     glob = W.logistic_regression(At, x_init)
     local, layout = shard_logistic_regression(At, x_init, rank, world)
     gs = GlobalStructure.from_problem(glob)
-    o = RowShardedOracles(local, layout, gs, store=grp.store, device=grp.local_rank, workers=True)
-    o.set_worker_loop(False)                      # parity check and device-resident loop: every rank calls (SPMD)
+    o = RowShardedOracles(local, layout, gs, store=grp.store, device=grp.local_rank, workers="try")
+    if o.has_worker_loop:
+        o.set_worker_loop(False)                  # parity check and device-resident loop: every rank calls (SPMD)
     setup_s = time.time() - t0
     x, lam, sigma = eval_point(glob, 0)
     # ---- inline parity: the sharded result against the single-GPU oracle of the global problem -------------
@@ -558,8 +559,12 @@ def bench_c3_sharded(args, grp, hbm_peak, peak_src):
         dt_spmd, E_spmd = timed_e2e(five, grp, args.steps)
         # the drop-in shape: ONE solver process (rank 0) issues the callbacks, the other ranks follow in serve()
         grp.barrier()
-        o.set_worker_loop(True)
-        if rank == 0:
+        one_solver = o.has_worker_loop
+        if one_solver:
+            o.set_worker_loop(True)
+        if not one_solver:
+            dt, E2 = 0.0, 0
+        elif rank == 0:
             for i in range(2):
                 five(i)
             t0 = time.perf_counter()
@@ -574,14 +579,15 @@ def bench_c3_sharded(args, grp, hbm_peak, peak_src):
         else:
             o.serve()
             dt, E2 = 0.0, 0
-        o.set_worker_loop(False)
+        if one_solver:
+            o.set_worker_loop(False)
         grp.barrier()
         dt, E2 = float(grp.max([dt])[0]), int(grp.max([E2])[0])
         h2d = float(grp.sum([8.0 * (layout.var_map.size + layout.con_map.size + 1)])[0])
         e2e = {"value": args.steps * E_spmd / dt_spmd, "unit": "evals/s", "evals_per_step": E_spmd,
                "mode": "every rank issues the five callbacks with its own host copies of x / lambda (SPMD, as the C4 "
                        "ranks do with their slices of the starts)",
-               "one_solver_value": args.steps * E2 / dt,
+               "one_solver_value": (args.steps * E2 / dt) if one_solver else None,
                "one_solver_evals_per_step": E2,
                "one_solver_note": "worker loop: rank 0 ALONE issues the callbacks (what one IPOPT process would do), "
                                   "posting x / lambda through shared host memory; the other ranks follow in "

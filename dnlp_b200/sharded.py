@@ -169,7 +169,7 @@ class _DeviceShard:
             info[name] = (dense, int(shared_slots.size), ow_pos, ow_gpos, int(glen))
         self.serving, self.x_in, self.lam_in, self._force_post = False, None, None, 3
         self.shared = self._share_host_arrays(info, bool(workers)) if store.world > 1 else {}
-        if workers and store.world > 1 and not self.serving:
+        if workers is True and store.world > 1 and not self.serving:        # workers="try": carry on without the loop
             raise RuntimeError("the worker loop needs the shared host segments, which could not be set up")
         if self.is_root:
             for name in ("grad", "g", "jac", "hess"):
@@ -479,6 +479,11 @@ class RowShardedOracles:
             if lam.size < self.m:
                 raise ValueError("duals has %d entries, expected at least %d" % (lam.size, self.m))
         return d.post(name, x, lam, sigma)
+
+    @property
+    def has_worker_loop(self):
+        """True when this oracle was created with ``workers=True`` (or ``"try"``) and the shared host segments exist."""
+        return self._dev is not None and self._dev.x_in is not None
 
     def set_worker_loop(self, enabled):
         """Switch between the worker loop (root posts, the others ``serve``) and SPMD calls (every rank makes every
