@@ -193,3 +193,130 @@ def test_pair_runs_follow_both_index_maps():
     assert _pair_runs([0, 1, 2, 3], [10, 11, 20, 21]) == [(0, 10, 2), (2, 20, 2)]
     assert _pair_runs(np.arange(0, 200, 2), np.arange(100)) is None           # too fragmented: NVLink route
     assert len(_pair_runs(np.arange(0, 20, 2), np.arange(10))) == 10
+
+
+# ------------------------------------------------------------------------------------------------
+# worker loop, host logic only: a stand-in for the device shard records what each rank is asked to
+# evaluate (the real one is csrc/dnlp_shard.cu, exercised in tests/test_sharded_nccl.py on a GPU)
+# ------------------------------------------------------------------------------------------------
+class _Bus:
+    def __init__(self, n, m):
+        import queue
+        import threading
+        self.x, self.lam, self.q = np.full(n, np.nan), np.full(max(m, 1), np.nan), queue.Queue()
+        self.both = threading.Barrier(2, timeout=20)     # every evaluation is collective: nobody runs ahead
+
+
+class _FakeDeviceShard:
+    """The attributes and methods RowShardedOracles uses on its device shard.  ``eval`` keeps the vectors it was
+    handed (None = "what you have") and logs (callback, x was resent, lambda was resent)."""
+    global_inputs, shared = True, {}
+
+    def __init__(self, bus, is_root, m):
+        self.bus, self.is_root, self.m = bus, is_root, m
+        self.serving, self._force_post = False, 3
+        self.x_in, self.lam_in = bus.x, bus.lam
+        self.staged_x, self.staged_lam, self.log = None, None, []
+
+    def post(self, name, x, lam=None, sigma=1.0):           # what dnlp_shard_post_command does
+        if name is None:
+            self.bus.q.put((None, 0.0, 0))
+            return None, None
+        flags = 0
+        if (self._force_post & 1) or not np.array_equal(self.bus.x, x):
+            self.bus.x[:] = x
+            flags |= 1
+        if lam is not None and ((self._force_post & 2) or not np.array_equal(self.bus.lam[:self.m], lam[:self.m])):
+            self.bus.lam[:self.m] = lam[:self.m]
+            flags |= 2
+        self._force_post &= ~(3 if (name == "hess" and lam is not None) else 1)
+        self.bus.q.put((name, float(sigma), flags))
+        return (self.x_in if flags & 1 else None), (self.lam_in if (lam is not None and flags & 2) else None)
+
+    def wait(self, timeout_s=1.0):
+        import queue
+        try:
+            return self.bus.q.get(timeout=timeout_s)
+        except queue.Empty:
+            return False, 0.0, 0
+
+    def eval(self, name, x, lam=None, sigma=1.0):
+        if x is not None:
+            self.staged_x = np.array(x, copy=True)
+        if lam is not None:
+            self.staged_lam = np.array(lam[:self.m], copy=True)
+        assert self.staged_x is not None, "asked to keep a point that was never staged"
+        if name == "hess":
+            assert self.staged_lam is not None, "asked to keep multipliers that were never staged"
+        self.log.append((name, x is not None, lam is not None, float(sigma), self.staged_x.copy(),
+                         None if self.staged_lam is None else self.staged_lam.copy()))
+        if self.serving:
+            self.bus.both.wait()
+        return np.float64(0.0) if name == "f" else np.zeros(1)
+
+
+def test_worker_loop_host_logic_with_a_recording_device():
+    """Root posts, worker follows: same callbacks in the same order on the same (x, lambda, sigma); a vector the
+    root found unchanged is resent to nobody; switching to SPMD calls and back re-stages both vectors."""
+    import threading
+
+    from dnlp_b200 import workloads as W
+    from dnlp_b200.sharded import GlobalStructure, RowShardedOracles, shard_logistic_regression
+    from oracle.dnlp_oracle import RefOracles
+    At, x_init = W.logistic_data(60, 6, 3, seed=5)
+    glob = W.logistic_regression(At, x_init)
+    gs = GlobalStructure.from_problem(glob)
+    bus = _Bus(glob.n, glob.m)
+    ranks = []
+    for r in range(2):
+        local, layout = shard_logistic_regression(At, x_init, r, 2)
+        o = RowShardedOracles(local, layout, gs, oracle_factory=RefOracles)
+        o._dev = _FakeDeviceShard(bus, r == 0, glob.m)
+        assert o.has_worker_loop
+        ranks.append(o)
+    root, worker = ranks
+    with pytest.raises(RuntimeError):
+        root.set_worker_loop(True) or root.serve()           # the root runs the solver
+    for o in ranks:
+        o.set_worker_loop(True)
+    served = []
+    t = threading.Thread(target=lambda: served.append(worker.serve(poll_s=0.05)))
+    t.start()
+    rng = np.random.default_rng(0)
+    x1, x2 = glob.x0 * 1.01, glob.x0 * 0.97
+    lam1, lam2 = rng.standard_normal(glob.m), rng.standard_normal(glob.m + glob.n)    # Knitro hands over m + n duals
+    root.objective(x1), root.gradient(x1.copy()), root.constraints(list(x1)), root.jacobian(x1)
+    root.hessian(x1, lam1, 1.0), root.hessian(x1, lam1, 0.5), root.hessian(x1, lam2, 0.5)
+    root.objective(x2), root.hessian(x2, lam2, 0.0)
+    root.release_workers()
+    t.join(timeout=20)
+    assert served == [9]
+    want = [("f", True, False), ("grad", False, False), ("g", False, False), ("jac", False, False),
+            ("hess", False, True), ("hess", False, False), ("hess", False, True), ("f", True, False),
+            ("hess", False, False)]
+    for dev in (root._dev, worker._dev):
+        assert [(e[0], e[1], e[2]) for e in dev.log] == want
+    for a, b in zip(root._dev.log, worker._dev.log):          # both ranks evaluated the same point every time
+        assert a[3] == b[3]
+        np.testing.assert_array_equal(a[4], b[4])
+        if a[0] == "hess":
+            np.testing.assert_array_equal(a[5], b[5])
+    np.testing.assert_array_equal(root._dev.log[-1][4], x2)
+    np.testing.assert_array_equal(root._dev.log[-1][5], lam2[:glob.m])
+    assert [e[3] for e in root._dev.log if e[0] == "hess"] == [1.0, 0.5, 0.5, 0.0]
+    # SPMD calls in between move the devices' point; back in the loop the first posts must re-stage x AND lambda
+    for o in ranks:
+        o.set_worker_loop(False)
+        o.objective(glob.x0), o.hessian(glob.x0, lam1, 2.0)
+        assert o._dev.log[-1][:3] == ("hess", True, True)
+        o.set_worker_loop(True)
+    t = threading.Thread(target=lambda: served.append(worker.serve(poll_s=0.05)))
+    t.start()
+    root.objective(x2), root.hessian(x2, lam2, 0.0)           # the bus still holds x2 / lam2: the compare says "same"
+    root.release_workers()
+    t.join(timeout=20)
+    assert served == [9, 2]
+    for dev in (root._dev, worker._dev):
+        assert [(e[0], e[1], e[2]) for e in dev.log[-2:]] == [("f", True, False), ("hess", False, True)]
+        np.testing.assert_array_equal(dev.log[-1][4], x2)
+        np.testing.assert_array_equal(dev.log[-1][5], lam2[:glob.m])
