@@ -46,11 +46,20 @@ def atom_golden_names():
     return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(ATOMS_DIR, "*.npz")))
 
 
+REFTESTS_DIR = os.path.join(GOLDEN_DIR, "reftests")
+
+
+def reftest_golden_names():
+    """Fixtures of tests/golden/make_golden_reftests.py: every expression the reference's own jacobian / hess_vec
+    unit tests differentiate (INDEX.tsv there names the reference test behind each)."""
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(REFTESTS_DIR, "*.npz")))
+
+
 class AtomGolden:
     """Fixtures written by tests/golden/make_golden_atoms.py (raw rules, no Dnlp2Smooth)."""
 
-    def __init__(self, name):
-        z = np.load(os.path.join(ATOMS_DIR, name + ".npz"), allow_pickle=False)
+    def __init__(self, name, directory=ATOMS_DIR):
+        z = np.load(os.path.join(directory, name + ".npz"), allow_pickle=False)
         self.name = name
         self.jac_error, self.hess_error = str(z["jac_error"]), str(z["hess_error"])
         arrays = {k[3:]: z[k] for k in z.files if k.startswith("ir_a")}

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from dnlp_b200.compiler import compile_problem
-from golden_util import AtomGolden, assert_close, atom_golden_names
+from golden_util import REFTESTS_DIR, AtomGolden, assert_close, atom_golden_names, reftest_golden_names
 from oracle.dnlp_oracle import RefOracles
 from tape_interp import TapeInterp
 
@@ -17,7 +17,17 @@ def _exc(name):
 
 @pytest.mark.parametrize("name", atom_golden_names())
 def test_oracle_rules(name):
-    g = AtomGolden(name)
+    _check_oracle_rules(AtomGolden(name))
+
+
+@pytest.mark.parametrize("name", reftest_golden_names())
+def test_oracle_rules_on_the_reference_suites_own_expressions(name):
+    """Every expression the reference's jacobian_tests / hess_tests differentiate (136 tests, 85 distinct
+    expressions the reference's Oracles can evaluate): tests/golden/make_golden_reftests.py."""
+    _check_oracle_rules(AtomGolden(name, REFTESTS_DIR))
+
+
+def _check_oracle_rules(g):
     o = RefOracles(g.problem)
     if g.jac_error:
         with pytest.raises(_exc(g.jac_error)):
@@ -46,7 +56,19 @@ def test_oracle_rules(name):
 
 @pytest.mark.parametrize("name", atom_golden_names())
 def test_compiler_rules(name):
-    g = AtomGolden(name)
+    _check_compiler_rules(AtomGolden(name))
+
+
+@pytest.mark.parametrize("name", reftest_golden_names())
+def test_compiler_rules_on_the_reference_suites_own_expressions(name):
+    _check_compiler_rules(AtomGolden(name, REFTESTS_DIR))
+
+
+def test_reference_suite_fixtures_are_all_there():
+    assert len(reftest_golden_names()) == 85
+
+
+def _check_compiler_rules(g):
     if g.jac_error:
         with pytest.raises(_exc(g.jac_error)):
             compile_problem(g.problem, with_hessian=False)
