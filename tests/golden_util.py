@@ -14,9 +14,18 @@ def golden_names():
                   for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
 
 
+REFPROBLEMS_DIR = os.path.join(GOLDEN_DIR, "refproblems")
+
+
+def refproblem_golden_names():
+    """Fixtures of tests/golden/make_golden_refproblems.py: the problems of the reference's own NLP test-suite, taken
+    from its test functions at their first ``solve(nlp=True)`` (INDEX.tsv there names the test behind each)."""
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(REFPROBLEMS_DIR, "*.npz")))
+
+
 class Golden:
-    def __init__(self, name):
-        z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False)
+    def __init__(self, name, directory=GOLDEN_DIR):
+        z = np.load(os.path.join(directory, name + ".npz"), allow_pickle=False)
         self.name = name
         arrays = {k[3:]: z[k] for k in z.files if k.startswith("ir_a")}
         self.problem = ir.load_problem(str(z["ir_json"]), arrays)
