@@ -724,7 +724,16 @@ class Builder:
         J = sp.coo_array((tags, (rows, cols)), shape=shape)
         res = (op_matrix @ J).tocoo()
         src = np.rint(res.data).astype(np.int64) - 1
-        return res.coords[0].astype(np.int64), res.coords[1].astype(np.int64), sv.gather(src)
+        prow, pcol, vals = res.coords[0].astype(np.int64), res.coords[1].astype(np.int64), sv.gather(src)
+        # the reference multiplies the VALUES: SciPy's SpGEMM drops a product that is exactly zero, so an entry whose
+        # value is a compile-time zero (x[sel] of c * x with c_sel = 0) never reaches the pattern (only compile-time
+        # constants can be exactly zero at the NaN structure pass; plain slicing, affine/index.py:127-150, keeps them)
+        cm = vals.is_const_mask()
+        drop = cm & (vals.const_values() == 0.0)
+        if drop.any():
+            keep = np.where(~drop)[0]
+            prow, pcol, vals = prow[keep], pcol[keep], vals.gather(keep)
+        return prow, pcol, vals
 
     def _jac_special_index(self, node):                    # affine/index.py:264-280
         arg = node.args[0]

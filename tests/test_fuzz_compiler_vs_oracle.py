@@ -156,7 +156,14 @@ def _check(seed, make_evaluator):
             lam = rng.standard_normal(prob.m)
             sigma = float(rng.uniform(0.5, 1.5))
             assert_close(ev("f", x, lam, sigma), ref.objective(x), "f seed %d" % seed)
-            assert_close(ev("grad", x, lam, sigma), ref.gradient(x), "grad seed %d" % seed)
+            try:
+                want_grad = ref.gradient(x)
+            except IndexError:
+                # an objective whose Jacobian block for some variable came out EMPTY (every entry a dropped zero):
+                # the reference indexes with an empty float array and crashes (nlp_solver.py:232, confirmed on the
+                # live reference); nothing to pin
+                return False
+            assert_close(ev("grad", x, lam, sigma), want_grad, "grad seed %d" % seed)
             if prob.m:
                 assert_close(ev("g", x, lam, sigma), ref.constraints(x), "g seed %d" % seed)
             assert_close(ev("jac", x, lam, sigma), ref.jacobian(x), "jac seed %d" % seed)
@@ -197,3 +204,29 @@ def test_fuzz_gpu_vs_oracle():
     finally:
         while opened:
             opened.pop().close()
+
+
+def test_special_index_drops_compile_time_zero_products():
+    """Found by running this fuzzer over 8000 more seeds: ``(c * x)[[k]]`` with ``c[k] == 0``.  special_index
+    multiplies a selection matrix with the Jacobian VALUES (affine/index.py:264-280) and SciPy's SpGEMM drops exact
+    zeros, so the entry never reaches the pattern; plain slicing (index.py:127-150) keeps it.  The expected
+    structures below are the live reference's (Bounds + Oracles on the same raw problem)."""
+    c1, c2 = np.array([1.0, 0.0, 2.0, 3.0]), np.array([1.5, 2.0, 0.0, 1.0])
+
+    def build(key):
+        x = ir.Variable((4,))
+        inner = ir.multiply(c1, ir.multiply(c2, x))
+        prob = ir.ProblemIR(ir.sum(ir.Node("exp", [x], x.shape)), [ir.index(inner, key), ir.index(ir.Node("exp", [x], x.shape), 0)])
+        prob.x0 = np.array([0.5, 0.6, 0.7, 0.8])
+        return prob
+    for key, rows, cols in (([1], [1], [0]), ([0], [0, 1], [0, 0]), ([2, 1, 3], [2, 3], [3, 0]),
+                            (slice(1, 3), [0, 1, 2], [1, 2, 0])):
+        prob = build(key)
+        ref = RefOracles(prob)
+        tape = compile_problem(prob)
+        for got in (ref.jacobianstructure(), (tape.jac_rows, tape.jac_cols)):
+            np.testing.assert_array_equal(got[0], rows)
+            np.testing.assert_array_equal(got[1], cols)
+        it = TapeInterp(tape)
+        assert_close(it.eval("jac", prob.x0), ref.jacobian(prob.x0), "jac")
+        assert_close(it.eval("g", prob.x0), ref.constraints(prob.x0), "g")
