@@ -666,7 +666,7 @@ class Builder:
         grp = np.cumsum(new) - 1
         return r[new], c[new], sv.gather(order).group_sum(grp, int(grp[-1]) + 1)
 
-    def _merge_dicts(self, parts):
+    def _merge_dicts(self, parts, hessian=False):
         """Shared body of AddExpression._jacobian / _hess_vec (affine/add_expr.py:149-222)."""
         out, need = {}, set()
         for d in parts:
@@ -678,6 +678,17 @@ class Builder:
                 else:
                     out[k] = (np.atleast_1d(r).astype(np.int64), np.atleast_1d(c).astype(np.int64), v)
         for k in need:
+            if hessian:
+                # the reference sums a repeated (var, var) block through coo_matrix(..., shape=(key[0].size, key[0].size))
+                # (add_expr.py:174-176): a cross block whose SECOND variable is the larger one does not fit and SciPy
+                # raises ValueError at the structure pass - e.g. rel_entr(vector, scalar) added to itself
+                r, c, _ = out[k]
+                side = self.var_size[k[0]]
+                for axis, idx in enumerate((r, c)):
+                    if len(idx) and int(np.max(idx)) >= side:
+                        raise ValueError("axis %d index %d exceeds matrix dimension %d" % (axis, int(np.max(idx)), side))
+                    if len(idx) and int(np.min(idx)) < 0:
+                        raise ValueError("negative axis %d index: %d" % (axis, int(np.min(idx))))
             out[k] = self._coo_sum_duplicates(*out[k])
         return out
 
@@ -694,7 +705,7 @@ class Builder:
             if node.attrs["axis"] is None:
                 r = np.zeros(len(c), dtype=np.int64)
             else:
-                m = arg.shape[0]
+                m, _ = arg.shape          # like the reference (sum.py:175): a 1-D argument with an axis is a ValueError
                 r = r // m if node.attrs["axis"] == 0 else r % m
             out[k] = self._coo_sum_duplicates(r, c, v)
         return out
@@ -1021,7 +1032,7 @@ class Builder:
         return getattr(self, "_hv_" + (node.op if node.op not in T.UNARY_TABLE else "unary"))(node, vec)
 
     def _hv_add(self, node, vec):                          # affine/add_expr.py:149-184
-        return self._merge_dicts([self.hv(a, vec) for a in node.args if not a.is_affine()])
+        return self._merge_dicts([self.hv(a, vec) for a in node.args if not a.is_affine()], hessian=True)
 
     def _hv_neg(self, node, vec):                          # affine/unary_operators.py:122-124
         return self.hv(node.args[0], vec.neg())

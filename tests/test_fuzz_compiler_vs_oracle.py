@@ -230,3 +230,37 @@ def test_special_index_drops_compile_time_zero_products():
         it = TapeInterp(tape)
         assert_close(it.eval("jac", prob.x0), ref.jacobian(prob.x0), "jac")
         assert_close(it.eval("g", prob.x0), ref.constraints(prob.x0), "g")
+
+
+def test_rule_errors_the_live_reference_fuzz_found():
+    """tests/golden/fuzz_live_reference.py (random raw problems against the LIVE reference) found two inputs the reference
+    rejects with ValueError at its structure pass and the compiler used to accept:
+    * ``sum(expr, axis=0)`` of a 1-D expression: ``m, _ = self.args[0].shape`` (affine/sum.py:175);
+    * a repeated cross block (vector, scalar) in ``AddExpression._hess_vec``: the duplicates are summed through a
+      ``coo_matrix`` shaped by the FIRST variable only (affine/add_expr.py:174-176).
+    The compiler must raise ValueError too (rule-precondition failures surface at compile time)."""
+    x, s = ir.Variable((3,)), ir.Variable(())
+    ex = ir.Node("exp", [x], x.shape)
+    bad_sum = ir.ProblemIR(ir.sum(ex), [ir.sum(ex, axis=0, keepdims=True)])
+    bad_sum.x0 = np.array([0.5, 0.6, 0.7])
+    twice = ir.rel_entr(x, s)
+    bad_add = ir.ProblemIR(ir.sum(ir.add(twice, twice)), [])
+    bad_add.x0 = np.array([0.5, 0.6, 0.7, 0.8])
+    for prob in (bad_sum, bad_add):
+        with pytest.raises(ValueError):
+            r = RefOracles(prob)
+            r.jacobianstructure(), r.hessianstructure()
+        with pytest.raises(ValueError):
+            compile_problem(prob)
+    # the same sum over a 2-D expression, and a repeated block that fits, stay accepted
+    X = ir.Variable((2, 3))
+    ok = ir.ProblemIR(ir.sum(ir.Node("exp", [X], X.shape)), [ir.sum(ir.Node("exp", [X], X.shape), axis=0, keepdims=True)])
+    ok.x0 = np.full(6, 0.5)
+    compile_problem(ok)
+    y = ir.Variable((3,))
+    both = ir.rel_entr(x, y)
+    ok2 = ir.ProblemIR(ir.sum(ir.add(both, both)), [])
+    ok2.x0 = np.full(6, 0.5)
+    tape, ref = compile_problem(ok2), RefOracles(ok2)
+    np.testing.assert_array_equal(tape.hess_rows, ref.hessianstructure()[0])
+    np.testing.assert_array_equal(tape.hess_cols, ref.hessianstructure()[1])
