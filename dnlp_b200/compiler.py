@@ -215,7 +215,11 @@ def compile_problem(prob, with_hessian=True):
                     HV.append(v)
 
     if with_hessian:
-        parse(b.hv(prob.objective, SymVec.slots([tape.sigma_slot])))
+        b.in_objective_hessian = True
+        try:
+            parse(b.hv(prob.objective, SymVec.slots([tape.sigma_slot])))
+        finally:
+            b.in_objective_hessian = False
         coff = 0
         for con in prob.constraints:
             parse(b.hv(con, SymVec.slot_range(tape.lam_slot + coff, con.size)))

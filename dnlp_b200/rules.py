@@ -838,6 +838,7 @@ class Builder:
         return tags.reshape(operand.shape, order="F"), sv
 
     CHAIN_FASTPATH = True
+    in_objective_hessian = False       # set by the compiler around the objective's hess_vec (see _hv_broadcast_to)
 
     def _chain_through_diagonal(self, A, a_src, a_rows, a_cols, opval, r, c, v):
         """``_chain_through`` for an inner Jacobian with at most one entry per row and per column, both index
@@ -1081,6 +1082,12 @@ class Builder:
     def _hv_broadcast_to(self, node, vec):                 # affine/broadcast_to.py:181-192
         m, n = node.shape
         kind = self._broadcast_type(node)
+        if self.in_objective_hessian and node.args[0].op == "broadcast_to":
+            # reference quirk: broadcast_to caches its type when the jacobian()/hess_vec() WRAPPER visits it
+            # (broadcast_to.py:84-110) and this rule calls the child's _hess_vec directly; in the OBJECTIVE no wrapper
+            # has visited an inner broadcast_to by the time hessianstructure() runs (its Jacobian is only taken in
+            # gradient(), nlp_solver.py:218-235), so the reference ends in broadcast_to.py:192.  Reject it the same way.
+            raise NotImplementedError("hess-vec not implemented for broadcast_to.")
         e = np.arange(vec.K)
         if kind == "row":
             return self._hv_inner(node.args[0], vec.group_sum(e // m, n))

@@ -566,6 +566,13 @@ def _hv_promote(node, vec, env):           # affine/promote.py:120-121
 def _hv_broadcast(node, vec, env):         # affine/broadcast_to.py:181-192
     m, n = node.shape
     kind = _broadcast_type(node)
+    if env.get("_broadcast_types_unset") and node.args[0].op == "broadcast_to":
+        # broadcast_to caches its type lazily in _verify_jacobian_args (broadcast_to.py:84-110), i.e. when the
+        # jacobian()/hess_vec() WRAPPER visits it; the rule below calls the child's _hess_vec directly, so an inner
+        # broadcast_to the wrapper has never seen still has type None and falls through to NotImplementedError
+        # (broadcast_to.py:192).  That is the state of the OBJECTIVE at the structure pass: its Jacobian is only taken
+        # in gradient() (nlp_solver.py:218-235), after hessianstructure().
+        raise NotImplementedError("hess-vec not implemented for broadcast_to.")
     if kind == "row":
         return _hv_inner(node.args[0], vec.reshape(n, m).sum(axis=1), env)
     if kind == "col":
@@ -748,6 +755,7 @@ class RefOracles:
         env = self._env(x)
         self.grad_obj.fill(0)
         gd = jacobian(self.prob.objective, env)
+        self._objective_jacobian_taken = True      # the wrappers have now visited every node of the objective
         off = 0
         for v in self.vars:
             if v.attrs["id"] in gd:
@@ -826,7 +834,11 @@ class RefOracles:
                         C.append(np.asarray(c) + offs[key[1]])
                         V.append(np.asarray(d, dtype=np.float64).reshape(-1))
 
-        parse(hess_vec(self.prob.objective, np.array([obj_factor]), env))
+        env["_broadcast_types_unset"] = not getattr(self, "_objective_jacobian_taken", False)
+        try:
+            parse(hess_vec(self.prob.objective, np.array([obj_factor]), env))
+        finally:
+            env["_broadcast_types_unset"] = False
         coff = 0
         for con in self.prob.constraints:
             parse(hess_vec(con, duals[coff:coff + con.size], env))

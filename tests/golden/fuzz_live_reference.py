@@ -30,6 +30,8 @@ from golden_util import assert_close  # noqa: E402
 from oracle.dnlp_oracle import RefOracles  # noqa: E402
 from tape_interp import TapeInterp  # noqa: E402
 
+MAXDIM = int(os.environ.get("FUZZ_MAXDIM", "4"))       # vectors up to MAXDIM, matrices up to (MAXDIM-1) x (MAXDIM-1)
+WRAPS = int(os.environ.get("FUZZ_WRAPS", "3"))         # up to WRAPS-1 affine atoms stacked on every term
 UNARY = [cp.exp, cp.log, cp.entr, cp.logistic, cp.sin, cp.cos, cp.tan, cp.sinh, cp.tanh, cp.asinh, cp.atanh, cp.xexp]
 
 
@@ -122,7 +124,7 @@ def affine_wrap(rng, e):
 
 def random_problem(seed):
     rng = np.random.default_rng(seed)
-    shapes = [(int(rng.integers(2, 5)),), (int(rng.integers(2, 4)), int(rng.integers(2, 4))), ()]
+    shapes = [(int(rng.integers(2, MAXDIM + 1)),), (int(rng.integers(2, MAXDIM)), int(rng.integers(2, MAXDIM))), ()]
     nvars = int(rng.integers(1, 4))
     variables = []
     for i in range(nvars):
@@ -158,7 +160,7 @@ def random_problem(seed):
             e = UNARY[int(rng.integers(0, len(UNARY)))](inner)
         if e is None:
             e = atom(rng, v)
-        for _ in range(int(rng.integers(0, 3))):
+        for _ in range(int(rng.integers(0, WRAPS))):
             e = affine_wrap(rng, e)
         return e
 

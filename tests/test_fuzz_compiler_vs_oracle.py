@@ -264,3 +264,27 @@ def test_rule_errors_the_live_reference_fuzz_found():
     tape, ref = compile_problem(ok2), RefOracles(ok2)
     np.testing.assert_array_equal(tape.hess_rows, ref.hessianstructure()[0])
     np.testing.assert_array_equal(tape.hess_cols, ref.hessianstructure()[1])
+
+
+def test_nested_broadcast_in_the_objective_is_rejected_like_the_reference():
+    """Found by tests/golden/fuzz_live_reference.py with deeper nesting: ``broadcast_to(broadcast_to(...))`` inside the
+    OBJECTIVE.  The reference caches a broadcast_to's type only when a jacobian()/hess_vec() wrapper visits it and the
+    outer rule calls the inner ``_hess_vec`` directly (broadcast_to.py:181-192): at hessianstructure() no wrapper has seen
+    the objective's inner node yet, and the reference raises NotImplementedError.  Inside a constraint the Jacobian pass
+    has been there first and the same expression is fine."""
+    x = ir.Variable((1, 1))
+    nested = ir.broadcast_to(ir.broadcast_to(ir.Node("exp", [x], x.shape), (3, 1)), (3, 2))
+    in_objective = ir.ProblemIR(ir.sum(nested), [])
+    in_objective.x0 = np.array([0.5])
+    with pytest.raises(NotImplementedError):
+        compile_problem(in_objective)
+    with pytest.raises(NotImplementedError):
+        RefOracles(in_objective).hessianstructure()
+    in_constraint = ir.ProblemIR(ir.sum(ir.Node("exp", [x], x.shape)), [nested])
+    in_constraint.x0 = np.array([0.5])
+    tape, ref = compile_problem(in_constraint), RefOracles(in_constraint)
+    ref.jacobianstructure()
+    np.testing.assert_array_equal(tape.hess_rows, ref.hessianstructure()[0])
+    it = TapeInterp(tape)
+    lam = np.arange(1.0, 7.0)
+    assert_close(it.eval("hess", in_constraint.x0, lam, 1.0), ref.hessian(in_constraint.x0, lam, 1.0), "hess")
