@@ -1,0 +1,115 @@
+"""TEST INFRASTRUCTURE (CPU tier only): a stand-in for ``dnlp_b200._cabi.DeviceTape`` that executes the compiled tape
+with the NumPy tape interpreter (tests/tape_interp.py) behind the SAME C entry-point names and ctypes arguments the
+real library takes.  It exists so that the host logic of ``GpuOracles`` - constant-entry elision and the compact
+dynamic transfers, the sigma-keyed Hessian entries, reused output buffers and return types, parameter re-arming,
+argument checks - runs in ``-m "not gpu"`` too.  The product never imports this module: without the CUDA library or a
+device, creating an oracle raises (dnlp_b200/_cabi.py)."""
+import numpy as np
+
+from tape_interp import TapeInterp
+
+_SPACE_OF_PROG = {0: 1, 1: 2, 2: 3, 3: 4, 4: 5}
+_NAME = {1: "f", 2: "grad", 3: "g", 4: "jac", 5: "hess"}
+
+
+def _arr(ptr, count):
+    return None if not ptr else np.ctypeslib.as_array(ptr, shape=(max(int(count), 1),))[:int(count)]
+
+
+class _InterpLib:
+    """The entry points ``GpuOracles`` calls, one instance per oracle (the handle argument is ignored)."""
+
+    def __init__(self, tape):
+        self.tape, self.it = tape, TapeInterp(tape)
+        self.n, self.m = tape.n, tape.m
+        self.len = {1: 1, 2: tape.n, 3: tape.m, 4: int(tape.jac_rows.size), 5: int(tape.hess_rows.size)}
+        self.dyn, self.lam, self.sigma, self.calls = {}, np.zeros(tape.m), 1.0, []
+        self.error = b""
+
+    def _eval(self, space, x, lam=None, sigma=None):
+        if lam is not None:
+            self.lam, self.sigma = np.array(lam[:self.m], copy=True), float(sigma)
+        self.calls.append(_NAME[space])
+        with np.errstate(all="ignore"):
+            if space == 5:
+                return np.asarray(self.it.eval("hess", x, self.lam, self.sigma), dtype=np.float64).reshape(-1)
+            return np.asarray(self.it.eval(_NAME[space], x), dtype=np.float64).reshape(-1)
+
+    def _deliver(self, space, x, out, lam=None, sigma=None):
+        if out is not None:
+            _arr(out, self.len[space])[:] = self._eval(space, _arr(x, self.n), None if lam is None else _arr(lam, self.m), sigma)
+        return 0
+
+    def dnlp_eval_f(self, h, x, out):
+        return self._deliver(1, x, out)
+
+    def dnlp_eval_grad(self, h, x, out):
+        return self._deliver(2, x, out)
+
+    def dnlp_eval_g(self, h, x, out):
+        return self._deliver(3, x, out)
+
+    def dnlp_eval_jac(self, h, x, out):
+        return self._deliver(4, x, out)
+
+    def dnlp_eval_hess(self, h, x, lam, sigma, out):
+        return self._deliver(5, x, out, lam, sigma)
+
+    def dnlp_eval_all(self, h, x, lam, sigma, f, grad, g, jac, hess):
+        for space, out in ((1, f), (2, grad), (3, g), (4, jac)):
+            self._deliver(space, x, out)
+        return self._deliver(5, x, hess, lam, sigma)
+
+    def dnlp_set_dynamic(self, h, space, pos, count):
+        self.dyn[int(space)] = np.array(np.ctypeslib.as_array(pos, shape=(max(int(count), 1),))[:int(count)], dtype=np.int64)
+        return 0
+
+    def dnlp_eval_dyn(self, h, prog, x, lam, sigma, compact):
+        space = _SPACE_OF_PROG[int(prog)]
+        if space not in self.dyn:
+            self.error = b"no dynamic positions registered for this output"
+            return 1
+        full = self._eval(space, _arr(x, self.n), None if not lam else _arr(lam, self.m), sigma)
+        pos = self.dyn[space]
+        _arr(compact, pos.size)[:] = full[pos]
+        return 0
+
+    def dnlp_set_params(self, h, values, count):
+        if int(count) != self.tape.n_params:
+            self.error = b"wrong number of parameter values"
+            return 1
+        self.it.set_params(np.array(_arr(values, count), copy=True))
+        return 0
+
+    def dnlp_last_error(self, h):
+        return self.error
+
+
+class InterpDeviceTape:
+    """Drop-in for ``_cabi.DeviceTape`` in CPU tests: ``monkeypatch.setattr(_cabi, "DeviceTape", InterpDeviceTape)``."""
+
+    def __init__(self, tape, device=0):
+        self.tape, self.h, self._L = tape, 1, _InterpLib(tape)
+        self.bound = None
+
+    def check(self, rc):
+        if rc != 0:
+            raise RuntimeError("dnlp_b200: %s" % self._L.dnlp_last_error(self.h).decode())
+
+    def set_params(self, values):
+        self.check(self._L.dnlp_set_params(self.h, values.ctypes.data_as(__import__("dnlp_b200")._cabi.c_f64p), int(values.size)))
+
+    def bind_outputs(self, f, grad, g, jac, eager):
+        self.bound = (f, grad, g, jac, bool(eager))       # eager delivery is a device feature: the arrays are only recorded
+
+    def close(self):
+        self.h = None
+
+
+def install(monkeypatch):
+    """Route ``GpuOracles`` to the interpreter-backed stand-in for the duration of a test."""
+    import types
+
+    from dnlp_b200 import _cabi
+    monkeypatch.setattr(_cabi, "DeviceTape", InterpDeviceTape)
+    monkeypatch.setattr(_cabi, "pinned_empty", lambda k: (np.empty(int(k)), types.SimpleNamespace(free=lambda: None)))
