@@ -10,7 +10,8 @@ import pytest
 
 import host_logic_device
 from dnlp_b200.oracles import GpuOracles
-from golden_util import AtomGolden, Golden, assert_close, atom_golden_names, golden_names
+from golden_util import (REFPROBLEMS_DIR, REFTESTS_DIR, AtomGolden, Golden, assert_close, atom_golden_names, golden_names,
+                         refproblem_golden_names, reftest_golden_names)
 
 
 @pytest.fixture
@@ -27,7 +28,7 @@ def oracles(monkeypatch):
         o.close()
 
 
-def _check_golden(o, g):
+def _check_golden(o, g, g_atol=1e-12):
     np.testing.assert_array_equal(o.jacobianstructure()[0], g.jac_rows)
     np.testing.assert_array_equal(o.jacobianstructure()[1], g.jac_cols)
     np.testing.assert_array_equal(o.hessianstructure()[0], g.hess_rows)
@@ -35,12 +36,12 @@ def _check_golden(o, g):
     for p in g.points + g.points[::-1]:                     # forwards and back: every output array is reused
         assert_close(o.objective(p["x"]), p["f"], "f")
         assert_close(o.gradient(p["x"]), p["grad"], "grad")
-        assert_close(o.constraints(p["x"]), p["g"], "g")
+        assert_close(o.constraints(p["x"]), p["g"], "g", atol=g_atol)
         assert_close(o.jacobian(p["x"]), p["jac"], "jac")
         assert_close(o.hessian(p["x"], p["lam"], float(p["sigma"])), p["hess"], "hess")
         res = o.eval_all(p["x"], p["lam"], float(p["sigma"]))
         for k in ("f", "grad", "g", "jac", "hess"):
-            assert_close(res[k], p[k], "eval_all/" + k)
+            assert_close(res[k], p[k], "eval_all/" + k, atol=g_atol if k == "g" else 1e-12)
 
 
 @pytest.mark.parametrize("name", golden_names())
@@ -58,9 +59,26 @@ def test_callbacks_match_the_reference_fixtures(name, elide, oracles, monkeypatc
     _check_golden(o, g)
 
 
+@pytest.mark.parametrize("name", refproblem_golden_names())
+def test_callbacks_on_the_reference_suites_own_problems(name, oracles, monkeypatch):
+    """The 79 problems harvested from the reference's problem-level tests, compact path forced on."""
+    monkeypatch.setattr(GpuOracles, "ELIDE_MIN", 1)
+    monkeypatch.setattr(GpuOracles, "ELIDE_MAX_FRACTION", 1.0)
+    g = Golden(name, REFPROBLEMS_DIR)
+    _check_golden(oracles(g.problem), g, g_atol=1e-9)
+
+
 @pytest.mark.parametrize("name", atom_golden_names())
 def test_raw_rules_through_the_oracle_object(name, oracles):
-    g = AtomGolden(name)
+    _check_raw_rules(AtomGolden(name), oracles)
+
+
+@pytest.mark.parametrize("name", reftest_golden_names())
+def test_reference_suite_expressions_through_the_oracle_object(name, oracles):
+    _check_raw_rules(AtomGolden(name, REFTESTS_DIR), oracles)
+
+
+def _check_raw_rules(g, oracles):
     if g.jac_error:
         with pytest.raises(getattr(builtins, g.jac_error)):
             oracles(g.problem, with_hessian=False)
