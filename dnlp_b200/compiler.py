@@ -193,9 +193,11 @@ def compile_problem(prob, with_hessian=True):
     tape.jac_is_list = not permutation_needed
     if permutation_needed and R.size:
         key = R * max(n, 1) + C
-        uniq, inv = np.unique(key, return_inverse=True)
-        if uniq.size != key.size:                       # quirk Q4: repeats receive the full sum
+        srt = np.sort(key)                              # repeats are rare: look for them before paying for the inverse map
+        if srt.size > 1 and bool(np.any(srt[1:] == srt[:-1])):     # quirk Q4: repeats receive the full sum
+            uniq, inv = np.unique(key, return_inverse=True)
             jv = jv.group_sum(inv, uniq.size).gather(inv)
+        del srt
     tape.jac_const, jac_ins = _emit_output(b, jv, T.DST_JAC)
 
     # ---- Hessian of the Lagrangian ----------------------------------------------
