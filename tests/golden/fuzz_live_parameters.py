@@ -29,6 +29,7 @@ from dnlp_b200.frontend_cvxpy import data_to_ir  # noqa: E402
 from golden_util import assert_close  # noqa: E402
 from tape_interp import TapeInterp  # noqa: E402
 
+FROZEN = bool(int(os.environ.get("FUZZ_FROZEN", "0")))   # also put parameters where they cannot be slots (matrix of a product)
 SMOOTH = [cp.exp, cp.log, cp.entr, cp.logistic, cp.sin, cp.cos, cp.tanh, cp.square, cp.sqrt, lambda e: cp.power(e, 3)]
 
 
@@ -58,6 +59,13 @@ def random_problem(seed):
             arg = cp.multiply(new_param(v.shape), v)
         elif u < 0.55:
             arg = new_param(()) * v
+        elif u < 0.65 and v.ndim == 1 and FROZEN:      # COEFFICIENT position: the frontend freezes the value into the tape
+            arg = new_param((int(rng.integers(1, 4)), v.shape[0])) @ v
+        if FROZEN and v.ndim == 1 and rng.random() < 0.1:
+            P = new_param((v.shape[0], v.shape[0]), 0.1, 1.0)
+            if rng.random() < 0.5:
+                return cp.quad_form(v, P, assume_PSD=True)          # the matrix of a quad_form
+            return cp.sum(P @ v)
         e = SMOOTH[int(rng.integers(0, len(SMOOTH)))](arg)
         w = rng.random()
         if w < 0.25 and e.ndim >= 1:                   # ... and outside
@@ -135,11 +143,21 @@ def check(seed):
                 p.value = np.asarray(rng.uniform(lo, hi, p.shape if p.shape != () else None), dtype=np.float64)
             data2 = mg.reference_data(prob)
             pir2 = data_to_ir(data2)
+            if FROZEN and fingerprint(pir2) != fp:
+                # a parameter in a coefficient position is part of the tape: its new value is a new fingerprint, which
+                # is what makes the compile cache recompile instead of serving stale coefficients
+                tape2 = compile_problem(pir2)
+                compare(seed, data2, tape2, TapeInterp(tape2), rng, setting)
+                recompiled[0] += 1
+                continue
             assert fingerprint(pir2) == fp, "seed %d: new parameter VALUES changed the fingerprint" % seed
             assert pir2.n_params == tape.n_params
             it.set_params(pir2.param_values())          # no recompile: the same tape, new slot values
             compare(seed, data2, tape, it, rng, setting)
         return True, tape.n_params
+
+
+recompiled = [0]
 
 
 if __name__ == "__main__":
@@ -158,3 +176,6 @@ if __name__ == "__main__":
     print("live-reference parameter fuzz, seeds %d..%d: %d problems compiled once and identical to the reference at three "
           "parameter settings each (%d parameter slots in total; fingerprint unchanged, structures bit-exact, values rel "
           "1e-10), %d not DNLP / rejected, %d FAILURES, %.0f s" % (lo, hi, accepted, slots, skipped, failed, time.time() - t0))
+    if FROZEN:
+        print("  FUZZ_FROZEN=1: parameters also in coefficient positions (matrix of a product): %d settings changed the "
+              "fingerprint and were recompiled, the others reused the tape" % recompiled[0])
