@@ -47,6 +47,7 @@ METRIC = "oracle evals/s (f, grad f, g, J, Hess L)"
 FP64_TENSOR_PEAK = 35.4
 FP64_TENSOR_PEAK_SRC = "measured: cuBLAS DGEMM 4096^3 on this pool (profiles/r01_cublas_dgemm.txt); nominal 40"
 TARGET_TIMED_S = 1.0          # the K timed steps should last about this long (device leg)
+HBM_SPEC_GBS = 8000.0            # the nominal figure north_star quotes next to the measured copy bandwidth
 TARGET_E2E_S = 0.6
 
 
@@ -418,7 +419,8 @@ def roofline_of(o, name, sizes, hbm_peak, peak_src):
     achieved = alg / (per[top] * 1e-3) / 1e9 if per[top] > 0 else 0.0
     traffic, tsrc = load_traffic(name, kname)
     return {"bound": "hbm", "kernel": "%s (instr %d, %d rows, %d terms)" % (kname, top, ins.count, nterms),
-            "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
+            "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+            "frac_of_8tbs_spec": achieved / HBM_SPEC_GBS, "traffic": traffic,
             "traffic_source": tsrc, "algorithmic_bytes": int(alg), "algorithmic_bytes_source": src,
             "ms": float(per[top]), "peak_source": peak_src, "share_of_step": float(per[top] / max(per.sum(), 1e-12))}
 
@@ -460,7 +462,8 @@ def bench_single(name, args, grp, hbm_peak, peak_src):
            "algorithmic_bytes_per_eval": total_8d, "algorithmic_bytes_per_quantity": sb,
            "algorithmic_bytes_source": "SURVEY.md 8(d)",
            "hbm_gbs_whole_eval": total_8d / (per_eval_ms * 1e-3) / 1e9,
-           "hbm_frac_whole_eval": total_8d / (per_eval_ms * 1e-3) / 1e9 / hbm_peak}
+           "hbm_frac_whole_eval": total_8d / (per_eval_ms * 1e-3) / 1e9 / hbm_peak,
+           "hbm_frac_whole_eval_of_8tbs_spec": total_8d / (per_eval_ms * 1e-3) / 1e9 / HBM_SPEC_GBS}
     if not args.device_only:
         rng = np.random.default_rng(7)
         npts = 4
@@ -612,6 +615,7 @@ def bench_c3_sharded(args, grp, hbm_peak, peak_src):
                "algorithmic_bytes_per_eval": total_8d, "algorithmic_bytes_source": "SURVEY.md 8(d)",
                "hbm_gbs_whole_eval": total_8d / (per_eval_ms * 1e-3) / 1e9,
                "hbm_frac_whole_eval": total_8d / (per_eval_ms * 1e-3) / 1e9 / (hbm_peak * world),
+               "hbm_frac_whole_eval_of_8tbs_spec": total_8d / (per_eval_ms * 1e-3) / 1e9 / (HBM_SPEC_GBS * world),
                "hbm_frac_note": "against %d x the per-GPU measured peak" % world,
                "roofline": dict(roof, note="rank 0's local tape (its rows)"),
                "exchange": {"shared_entries": "f (1 double); everything else is owned by one rank",
@@ -701,7 +705,8 @@ def bench_multistart(args, grp, hbm_peak, peak_src):
             roof = {"bound": "hbm", "kernel": "batched Hessian fill bsmallk_kernel (instr %d, %d rows x %d starts)"
                     % (top, ins.count, B),
                     "achieved": nb / (per[top] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": nb / (per[top] * 1e-3) / 1e9 / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "frac": nb / (per[top] * 1e-3) / 1e9 / hbm_peak,
+                    "frac_of_8tbs_spec": nb / (per[top] * 1e-3) / 1e9 / HBM_SPEC_GBS, "traffic": None, "peak_source": peak_src,
                     "algorithmic_bytes": int(nb), "algorithmic_bytes_source": "SURVEY 8(d) C4: 8 * nnzH * B output bytes",
                     "ms": float(per[top])}
         roof["share_of_step"] = float(per[top] / max(per.sum(), 1e-12))
