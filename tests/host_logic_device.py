@@ -84,6 +84,36 @@ class _InterpLib:
     def dnlp_last_error(self, h):
         return self.error
 
+    # ---- measurement hooks of bench.py: no device, so no timings - fixed figures that keep the control flow going ----
+    def dnlp_upload_point(self, h, x, lam, sigma):
+        self.lam = np.zeros(self.m) if not lam else np.array(_arr(lam, self.m), copy=True)
+        self.sigma, self.launches = float(sigma), getattr(self, "launches", 0)
+        return 0
+
+    def dnlp_run_device(self, h, mask, iters, ms_out):
+        self.launches = getattr(self, "launches", 0) + int(iters) * len(self.tape.programs["all"])
+        ms_out._obj.value = 0.05 * int(iters)
+        return 0
+
+    def dnlp_profile_instrs(self, h, prog, iters, out):
+        k = max(len(self.tape.instrs), 1)
+        np.ctypeslib.as_array(out, shape=(k,))[:] = 0.01
+        return 0
+
+    def dnlp_kernel_launches(self, h):
+        return getattr(self, "launches", 0)
+
+    def dnlp_instr_kernel(self, h, instr):
+        return b"tape_interpreter"
+
+    def dnlp_read_output(self, h, space, out):
+        return 1
+
+    def dnlp_set_graphs(self, h, on):
+        return 0
+
+    dnlp_set_parallel = dnlp_set_windows = dnlp_set_cache = dnlp_set_graphs
+
 
 class InterpDeviceTape:
     """Drop-in for ``_cabi.DeviceTape`` in CPU tests: ``monkeypatch.setattr(_cabi, "DeviceTape", InterpDeviceTape)``."""
