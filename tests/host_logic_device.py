@@ -136,10 +136,78 @@ class InterpDeviceTape:
         self.h = None
 
 
+class _InterpBatchLib:
+    """Batched entry points (``BatchedOracles``): every start through the interpreter, one after the other."""
+
+    def __init__(self, tape, batch):
+        self.tape, self.B, self.it = tape, int(batch), TapeInterp(tape)
+        self.n, self.m = tape.n, tape.m
+        self.len = {"f": 1, "grad": tape.n, "g": tape.m, "jac": int(tape.jac_rows.size), "hess": int(tape.hess_rows.size)}
+        self.launches, self.error = 0, b""
+
+    def _mat(self, ptr, cols):
+        return None if not ptr else np.ctypeslib.as_array(ptr, shape=(self.B * max(int(cols), 1),))[:self.B * int(cols)].reshape(self.B, int(cols))
+
+    def dnlp_batch_eval(self, h, X, LAM, SIGMA, f, grad, g, jac, hess):
+        X = self._mat(X, self.n)
+        LAM = self._mat(LAM, self.m) if self.m else None
+        SIG = None if not SIGMA else np.ctypeslib.as_array(SIGMA, shape=(self.B,))
+        outs = {k: self._mat(p, self.len[k]) for k, p in (("f", f), ("grad", grad), ("g", g), ("jac", jac), ("hess", hess))}
+        with np.errstate(all="ignore"):
+            for b in range(self.B):
+                for k, out in outs.items():
+                    if out is None or self.len[k] == 0:
+                        continue
+                    if k == "hess":
+                        lam = LAM[b] if LAM is not None else np.zeros(0)
+                        out[b] = np.asarray(self.it.eval("hess", X[b], lam, float(SIG[b]))).reshape(-1)
+                    else:
+                        out[b] = np.asarray(self.it.eval(k, X[b])).reshape(-1)
+        return 0
+
+    def dnlp_batch_upload(self, h, X, LAM, SIGMA):
+        return 0
+
+    def dnlp_batch_run_device(self, h, mask, iters, ms_out):
+        self.launches += int(iters) * len(self.tape.programs["all"])
+        ms_out._obj.value = 0.05 * int(iters)
+        return 0
+
+    def dnlp_batch_profile_instrs(self, h, prog, iters, out):
+        np.ctypeslib.as_array(out, shape=(max(len(self.tape.instrs), 1),))[:] = 0.01
+        return 0
+
+    def dnlp_batch_profile_groups(self, h, iters, ms, flops, cap):
+        np.ctypeslib.as_array(ms, shape=(int(cap),))[0] = 0.02
+        np.ctypeslib.as_array(flops, shape=(int(cap),))[0] = 1e9
+        return 1
+
+    def dnlp_batch_kernel_launches(self, h):
+        return self.launches
+
+    def dnlp_batch_last_error(self, h):
+        return self.error
+
+
+class InterpDeviceBatch:
+    """Drop-in for ``_cabi.DeviceBatch`` in CPU tests."""
+
+    def __init__(self, tape, batch, device=0):
+        self.tape, self.batch, self.h, self._L = tape, int(batch), 1, _InterpBatchLib(tape, batch)
+
+    def check(self, rc):
+        if rc != 0:
+            raise RuntimeError("dnlp_b200: %s" % self._L.dnlp_batch_last_error(self.h).decode())
+
+    def close(self):
+        self.h = None
+
+
 def install(monkeypatch):
     """Route ``GpuOracles`` to the interpreter-backed stand-in for the duration of a test."""
     import types
 
     from dnlp_b200 import _cabi
     monkeypatch.setattr(_cabi, "DeviceTape", InterpDeviceTape)
+    monkeypatch.setattr(_cabi, "DeviceBatch", InterpDeviceBatch)
     monkeypatch.setattr(_cabi, "pinned_empty", lambda k: (np.empty(int(k)), types.SimpleNamespace(free=lambda: None)))
