@@ -320,3 +320,77 @@ def test_worker_loop_host_logic_with_a_recording_device():
         assert [(e[0], e[1], e[2]) for e in dev.log[-2:]] == [("f", True, False), ("hess", False, True)]
         np.testing.assert_array_equal(dev.log[-1][4], x2)
         np.testing.assert_array_equal(dev.log[-1][5], lam2[:glob.m])
+
+
+# ------------------------------------------------------------------------------------------------
+# host assembly over many layouts at once: ranks as threads of this process (no rendezvous cost)
+# ------------------------------------------------------------------------------------------------
+class _ThreadStore:
+    """``allgather`` among the threads of one process: the store interface without sockets."""
+
+    def __init__(self, world):
+        import threading
+        self.world, self.bar, self.slots = world, threading.Barrier(world, timeout=60), [None] * world
+
+    def view(self, rank):
+        import types
+        st = self
+
+        def allgather(payload):
+            st.slots[rank] = bytes(payload)
+            st.bar.wait()
+            out = list(st.slots)
+            st.bar.wait()
+            return out
+        return types.SimpleNamespace(rank=rank, world=st.world, allgather=allgather)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_row_sharded_assembly_over_random_layouts_including_empty_shards(seed):
+    """World sizes 1..6, both shard builders, row counts down to ONE (so some ranks own no rows at all): every rank's
+    five outputs equal the global oracle's (400 such cases were run offline; six seeds x four cases stay here)."""
+    import threading
+    import traceback
+
+    from dnlp_b200 import workloads as W
+    from dnlp_b200.sharded import GlobalStructure, RowShardedOracles, shard_logistic_regression, shard_microbench
+    from golden_util import assert_close
+    from oracle.dnlp_oracle import RefOracles
+    rng = np.random.default_rng(100 + seed)
+    for case in range(4):
+        kind = "c3" if (seed + case) % 2 == 0 else "c5"
+        world = int(rng.integers(1, 7))
+        m = 1 if case == 0 else int(rng.integers(2, 30))          # case 0: fewer rows than ranks
+        if kind == "c3":
+            n = int(rng.integers(2, 10))
+            At, x_init = W.logistic_data(m, n, int(rng.integers(1, min(n, 4) + 1)), seed=int(rng.integers(0, 10 ** 6)))
+            glob = W.logistic_regression(At, x_init)
+            make = lambda r: shard_logistic_regression(At, x_init, r, world)          # noqa: E731
+        else:
+            A, x0 = W.microbench_data(8 * int(rng.integers(1, 4)), m, int(rng.integers(1, 4)), seed=int(rng.integers(0, 10 ** 6)))
+            glob = W.microbench(A, x0)
+            make = lambda r: shard_microbench(A, x0, r, world)                       # noqa: E731
+        gs = GlobalStructure.from_problem(glob)
+        ref = RefOracles(glob)
+        ref.jacobianstructure(), ref.hessianstructure()
+        x = glob.x0 * (1 + 0.05 * rng.standard_normal(glob.n))
+        lam = rng.standard_normal(glob.m)
+        want = {"f": ref.objective(x), "grad": ref.gradient(x).copy(), "g": np.array(ref.constraints(x)),
+                "jac": np.array(ref.jacobian(x)), "hess": np.array(ref.hessian(x, lam, 0.7))}
+        st, errs = _ThreadStore(world), []
+
+        def worker(r):
+            try:
+                local, layout = make(r)
+                o = RowShardedOracles(local, layout, gs, store=st.view(r), oracle_factory=RefOracles)
+                got = {"f": o.objective(x), "grad": o.gradient(x), "g": o.constraints(x), "jac": o.jacobian(x),
+                       "hess": o.hessian(x, lam, 0.7)}
+                for key in got:
+                    assert_close(got[key], want[key], "%s on rank %d of %d (%s, m=%d)" % (key, r, world, kind, m), atol=1e-11)
+            except Exception:           # noqa: BLE001
+                errs.append(traceback.format_exc())
+                st.bar.abort()
+        threads = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+        [t.start() for t in threads]
+        [t.join(timeout=120) for t in threads]
+        assert not errs, errs[0]
