@@ -403,14 +403,14 @@ class Builder:
             return SymVec.slot_range(self.param_off[node.attrs["id"]], node.size)   # whose value lives in V
         a = node.args
         if op == "add":                                    # affine/add_expr.py:72-73
-            out = None
+            parts = []
             for arg in a:
                 v = self.value(arg)
                 if v.K != node.size:
                     I = np.broadcast_to(self._index_array(arg), node.shape)
                     v = v.gather(_flatF(I))
-                out = v if out is None else out.add(v)
-            return out
+                parts.append(v)
+            return SymVec.add_many(parts)
         if op == "neg":                                    # affine/unary_operators.py:37
             return self.value(a[0]).neg()
         if op == "sum":                                    # affine/sum.py:93-101

@@ -210,6 +210,19 @@ class SymVec:
                               np.concatenate([self.f1, other.f1]),
                               np.concatenate([self.f2, other.f2]))
 
+    @staticmethod
+    def add_many(parts):
+        """``parts[0].add(parts[1]).add(parts[2])...`` in one pass: a stable sort of the whole concatenation leaves
+        the terms of an entry in part order, each part's own order kept - exactly what the chain of pairwise
+        stable sorts produces, without re-sorting the growing prefix once per part."""
+        parts = list(parts)
+        if len(parts) == 1:
+            return parts[0]
+        K = parts[0].K
+        assert all(p.K == K for p in parts)
+        return _sorted_by_row(K, np.concatenate([p.row for p in parts]), np.concatenate([p.coef for p in parts]),
+                              np.concatenate([p.f1 for p in parts]), np.concatenate([p.f2 for p in parts]))
+
     def linear_map(self, out_rows, in_idx, weights, n_out):
         """sum_j M[i, j] * self[j] for a constant sparse M given as COO (out_rows, in_idx, weights)."""
         g = self.gather(in_idx).scale(weights)
