@@ -212,8 +212,16 @@ def compile_problem(prob, with_hessian=True):
                         # what scipy's coo_matrix raises inside sum_coo (nlp_solver.py:359-364) when a
                         # rule emits ragged triplets, e.g. multiply(promote(s), x) (binary_operators.py:529-535)
                         raise ValueError("row, column, and data array must all be the same length")
-                    HR.append(np.asarray(r, np.int64) + off[v1])
-                    HC.append(np.asarray(c, np.int64) + off[v2])
+                    r = np.asarray(r, np.int64) + off[v1]
+                    c = np.asarray(c, np.int64) + off[v2]
+                    # sum_coo, then the lower triangle (nlp_solver.py:359-372).  Duplicates share their (row, col),
+                    # so masking block by block BEFORE the sum gives the same entries in the same order and halves
+                    # what a dense quad_form Hessian has to concatenate and sort.
+                    low = np.flatnonzero(r >= c)
+                    if low.size != r.size:
+                        r, c, v = r[low], c[low], v.gather(low)
+                    HR.append(r)
+                    HC.append(c)
                     HV.append(v)
 
     if with_hessian:
@@ -228,8 +236,6 @@ def compile_problem(prob, with_hessian=True):
             coff += con.size
     if HR:
         hr, hc, hv = Builder._coo_sum_duplicates(np.concatenate(HR), np.concatenate(HC), SymVec.concat(HV))
-        low = np.where(hr >= hc)[0]
-        hr, hc, hv = hr[low], hc[low], hv.gather(low)
     else:
         hr = hc = np.zeros(0, np.int64)
         hv = SymVec.zeros(0)

@@ -639,6 +639,34 @@ class Builder:
             kind = "scalar"
         return kind
 
+    MERGE_MAX_RUNS = 8
+
+    @staticmethod
+    def _merge_sorted_runs(key):
+        """``np.argsort(key, kind="stable")`` for a key made of at most ``MERGE_MAX_RUNS`` non-decreasing runs (the
+        blocks the rules emit are sorted one by one: a dense quad_form Hessian of 67 M entries followed by 8 192
+        diagonal entries must not pay for a 67 M-entry sort).  Runs are folded left to right; the shorter side is
+        located in the longer one by binary search (ties: the earlier run first) and spliced in with ``np.insert``.
+        Returns None when there are more runs than that."""
+        n = key.size
+        brk = np.flatnonzero(key[1:] < key[:-1]) + 1
+        if brk.size == 0:
+            return np.arange(n, dtype=np.int64)
+        if brk.size >= Builder.MERGE_MAX_RUNS or n < (1 << 12):
+            return None
+        bounds = np.concatenate([[0], brk, [n]])
+        idx = np.arange(bounds[0], bounds[1], dtype=np.int64)
+        k = key[bounds[0]:bounds[1]]
+        for a, b in zip(bounds[1:-1], bounds[2:]):
+            kb, ib = key[a:b], np.arange(a, b, dtype=np.int64)
+            if kb.size <= k.size:                         # later run into the merged prefix: after its equals
+                at = np.searchsorted(k, kb, side="right")
+                idx, k = np.insert(idx, at, ib), np.insert(k, at, kb)
+            else:                                         # merged prefix into the later run: before its equals
+                at = np.searchsorted(kb, k, side="left")
+                idx, k = np.insert(ib, at, idx), np.insert(kb, at, k)
+        return idx
+
     @staticmethod
     def _coo_sum_duplicates(rows, cols, sv):
         """``coo_matrix.sum_duplicates``: sort by (row, col), merge equal pairs.  One int64 key and a
@@ -652,7 +680,10 @@ class Builder:
         if key.size < 2 or bool(np.all(key[1:] > key[:-1])):
             return rows, cols, sv
         nr, nc = int(rows.max()) + 1, int(cols.max()) + 1
-        if key.size >= (1 << 16) and max(nr, nc) <= 4 * key.size:
+        order = Builder._merge_sorted_runs(key)          # a few pre-sorted blocks (one per atom): merge, do not sort
+        if order is not None:
+            pass
+        elif key.size >= (1 << 16) and max(nr, nc) <= 4 * key.size:
             o1 = stable_order(cols, nc)                  # LSD radix: columns first, then rows
             order = o1[stable_order(rows[o1], nr)]
         else:
@@ -1195,6 +1226,25 @@ class Builder:
 
     def _hv_quad_form(self, node, vec):                    # quad_form.py:143-149
         x, Q = node.args
-        Qc = sp.coo_matrix(Q.attrs["value"])
-        vals = vec.gather(np.zeros(Qc.nnz, dtype=np.int64)).scale(2.0 * Qc.data)
-        return {(x.attrs["id"], x.attrs["id"]): (Qc.row.astype(np.int64), Qc.col.astype(np.int64), vals)}
+        Qv = Q.attrs["value"]
+        if isinstance(Qv, np.ndarray) and Qv.ndim == 2:
+            # coo_matrix(dense) lists the non-zeros row-major (M.nonzero()); the same entries without SciPy's
+            # index-array copies (n = 8192: 67 M entries)
+            if np.count_nonzero(Qv) == Qv.size:
+                rows = np.repeat(np.arange(Qv.shape[0], dtype=np.int64), Qv.shape[1])
+                cols = np.tile(np.arange(Qv.shape[1], dtype=np.int64), Qv.shape[0])
+                data = Qv.reshape(-1)
+            else:
+                flat = np.flatnonzero(Qv)
+                rows, cols = np.divmod(flat, Qv.shape[1])
+                data = Qv.reshape(-1)[flat]
+        else:
+            Qc = sp.coo_matrix(Qv)
+            rows, cols, data = Qc.row.astype(np.int64), Qc.col.astype(np.int64), Qc.data
+        nnz = rows.size
+        if vec.K == 1 and vec.nterms == 1:               # one term broadcast over the pattern, then scaled
+            vals = SymVec(nnz, np.arange(nnz, dtype=np.int32), vec.coef[0] * (2.0 * data),
+                          np.full(nnz, vec.f1[0], dtype=np.int32), np.full(nnz, vec.f2[0], dtype=np.int32))
+        else:
+            vals = vec.gather(np.zeros(nnz, dtype=np.int64)).scale(2.0 * data)
+        return {(x.attrs["id"], x.attrs["id"]): (rows, cols, vals)}

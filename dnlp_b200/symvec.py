@@ -196,9 +196,19 @@ class SymVec:
         parts = list(parts)
         if not parts:
             return SymVec.zeros(0)
-        offs = np.cumsum([0] + [p.K for p in parts])
-        return SymVec(offs[-1],
-                      np.concatenate([p.row.astype(np.int64) + o for p, o in zip(parts, offs[:-1])]),
+        if len(parts) == 1:
+            return parts[0]
+        offs = [0]
+        for p in parts:
+            offs.append(offs[-1] + p.K)
+        if offs[-1] >= 2 ** 31:
+            raise ValueError("vector of %d entries exceeds the int32 index range" % offs[-1])
+        row = np.empty(sum(p.nterms for p in parts), dtype=np.int32)
+        at = 0
+        for p, o in zip(parts, offs[:-1]):               # one pass per part, no int64 round trip
+            np.add(p.row, np.int32(o), out=row[at:at + p.nterms])
+            at += p.nterms
+        return SymVec(offs[-1], row,
                       np.concatenate([p.coef for p in parts]),
                       np.concatenate([p.f1 for p in parts]),
                       np.concatenate([p.f2 for p in parts]))

@@ -107,3 +107,61 @@ def test_coo_sum_duplicates_radix_path_equals_key_sort():
     np.testing.assert_array_equal(out.row, grp)
     np.testing.assert_array_equal(out.coef, sv.coef[order])
     np.testing.assert_array_equal(out.f1, sv.f1[order])
+
+
+def test_merge_of_sorted_runs_is_the_stable_argsort(monkeypatch):
+    """``Builder._merge_sorted_runs``: keys made of a few non-decreasing runs (one block per atom) are merged instead
+    of sorted; must be the stable permutation, ties between runs resolved in favour of the earlier run."""
+    from dnlp_b200.rules import Builder
+    rng = np.random.default_rng(2)
+    for trial in range(60):
+        nruns = int(rng.integers(1, 8))
+        sizes = rng.integers(1, 6000, nruns) if trial % 3 else np.r_[rng.integers(5000, 9000), rng.integers(1, 40, nruns - 1)]
+        span = int(rng.choice([5, 300, 10 ** 6]))                      # many ties ... none
+        key = np.concatenate([np.sort(rng.integers(0, span, int(s))) for s in sizes]).astype(np.int64)
+        got = Builder._merge_sorted_runs(key)
+        if got is None:
+            assert key.size < (1 << 12) or np.count_nonzero(key[1:] < key[:-1]) >= Builder.MERGE_MAX_RUNS
+            continue
+        np.testing.assert_array_equal(got, np.argsort(key, kind="stable"))
+    many = np.tile(np.arange(10, dtype=np.int64), 1000)                # 1000 runs: not this routine's job
+    assert Builder._merge_sorted_runs(many) is None
+    np.testing.assert_array_equal(Builder._merge_sorted_runs(np.arange(5000, dtype=np.int64)), np.arange(5000))
+
+
+def test_coo_sum_duplicates_merge_path_equals_key_sort():
+    """A long sorted block followed by short ones (dense quad_form Hessian + diagonal blocks) through the merge path:
+    same entries, same order of the terms inside every merged entry as the key sort."""
+    from dnlp_b200.rules import Builder
+    rng = np.random.default_rng(3)
+    n = 90
+    R, C = np.divmod(np.arange(n * n), n)                              # dense block, row-major
+    d = np.arange(n)
+    rows, cols = np.concatenate([R, d, d[::2]]), np.concatenate([C, d, d[::2]])
+    N = rows.size
+    sv = SymVec(N, np.arange(N), rng.standard_normal(N), rng.integers(0, 50, N), np.full(N, -1))
+    r, c, out = Builder._coo_sum_duplicates(rows, cols, sv)
+    key = rows * n + cols
+    order = np.argsort(key, kind="stable")
+    uniq = np.unique(key)
+    np.testing.assert_array_equal(r * n + c, uniq)
+    np.testing.assert_array_equal(out.row, np.searchsorted(uniq, key[order]))
+    np.testing.assert_array_equal(out.coef, sv.coef[order])
+    np.testing.assert_array_equal(out.f1, sv.f1[order])
+
+
+def test_concat_and_add_many_equal_their_pairwise_forms():
+    rng = np.random.default_rng(4)
+
+    def rand(K, nt):
+        return SymVec(K, np.sort(rng.integers(0, K, nt)), rng.standard_normal(nt), rng.integers(-1, 9, nt), rng.integers(-1, 9, nt))
+    parts = [rand(7, 12), rand(3, 0), rand(5, 9), rand(1, 1)]
+    cat = SymVec.concat(parts)
+    assert cat.K == 16 and cat.row.dtype == np.int32
+    np.testing.assert_array_equal(cat.row, np.concatenate([p.row.astype(np.int64) + o for p, o in zip(parts, (0, 7, 10, 15))]))
+    np.testing.assert_array_equal(cat.coef, np.concatenate([p.coef for p in parts]))
+    same = [rand(6, 10), rand(6, 4), rand(6, 0), rand(6, 13)]
+    chain = same[0].add(same[1]).add(same[2]).add(same[3])
+    many = SymVec.add_many(same)
+    for name in ("row", "coef", "f1", "f2"):
+        np.testing.assert_array_equal(getattr(many, name), getattr(chain, name))
