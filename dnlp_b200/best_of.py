@@ -94,12 +94,25 @@ def best_of_lockstep(problem_ir, X0, device=0, evaluator=None, tol=1e-12, max_it
     return out
 
 
-def solve_best_of(prob, best_of, solver="lockstep", device=0, evaluator_factory=None, **solver_opts):
+def _pick(smooth_objs, maximize, faithful):
+    """Index of the start the loop keeps.  ``smooth_objs``: objective of the smooth MINIMISATION problem per start."""
+    if maximize and faithful:              # the reference compares the un-flipped objective with `<`
+        return int(np.argmin(-smooth_objs))
+    return int(np.argmin(smooth_objs))
+
+
+def solve_best_of(prob, best_of, solver="lockstep", device=0, evaluator_factory=None, faithful=True, **solver_opts):
     """The reference's ``best_of`` loop (problem.py:1249-1275) with one compile and batched solves.
     ``prob`` is a cvxpy Problem of the installed reference; returns ``prob.value`` and leaves variable values,
     ``prob.solver_stats.extra_stats['all_objs_from_best_of']`` exactly where the reference's loop leaves them.
     ``solver``: "lockstep" (equality-constrained problems, all starts at once on the GPU) or "ipopt"
-    (per-start ``solve_via_data`` on the shared resident oracle; needs cyipopt)."""
+    (per-start ``solve_via_data`` on the shared resident oracle; needs cyipopt).
+
+    ``faithful`` (default): the reference's loop ranks the starts by ``self.objective.value`` with ``<`` whatever the
+    sense (problem.py:1262-1268), so for a Maximize problem it keeps the start with the SMALLEST objective, and it
+    then reports ``all_objs_from_best_of`` negated (problem.py:1270-1272).  Reproduced as is, so that switching
+    changes no result; ``faithful=False`` keeps the best start in the problem's own sense and reports the objective
+    values with their own sign."""
     import cvxpy as cp
     from cvxpy.reductions.cvx_attr2constr import CvxAttr2Constr
     from cvxpy.reductions.dnlp2smooth.dnlp2smooth import Dnlp2Smooth
@@ -126,7 +139,7 @@ def solve_best_of(prob, best_of, solver="lockstep", device=0, evaluator_factory=
             d = dict(data, x0=x0)
             sols.append(chain.solver.solve_via_data(d, False, False, solver_opts=solver_opts))
         objs = np.array([s["obj_val"] for s in sols])
-        best = int(np.argmin(objs))
+        best = _pick(objs, maximize, faithful)
         best_solution = sols[best]
     else:
         if np.any(np.asarray(data["cu"]) != np.asarray(data["cl"])) or np.any(np.isfinite(data["lb"])) \
@@ -136,10 +149,12 @@ def solve_best_of(prob, best_of, solver="lockstep", device=0, evaluator_factory=
         pir = data_to_ir(data)
         ev = evaluator_factory(pir, best_of) if evaluator_factory is not None else None
         out = best_of_lockstep(pir, np.stack(starts), device=device, evaluator=ev, **solver_opts)
-        objs, best = out["all_objs"], out["best"]
+        objs = out["all_objs"]
+        best = _pick(np.asarray(objs), maximize, faithful)
         best_solution = {"status": 0 if out["converged"][best] else -1, "x": out["x"][best], "obj_val": float(objs[best]),
                          "mult_g": out["lam"][best], "iterations": int(out["iterations"][best])}
-    all_objs = -np.asarray(objs) if maximize else np.asarray(objs)
+    true_objs = -np.asarray(objs) if maximize else np.asarray(objs)      # self.objective.value at every start's solution
+    all_objs = -true_objs if (maximize and faithful) else true_objs
     best_solution["all_objs_from_best_of"] = all_objs
     prob.unpack_results(best_solution, chain, inverse_data)
     return prob.value

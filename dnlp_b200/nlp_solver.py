@@ -40,7 +40,49 @@ def gpu_oracles(problem, initial_point, num_constraints):
     oracle, hit = ORACLE_CACHE.get(pir, lambda p: GpuOracles(p, device=DEVICE), extra_key=(("device", DEVICE),))
     if hit:
         oracle.rearm(pir)
+    oracle._cvx_problem = problem          # for write_back_point(): the smooth problem of THIS chain application
     return oracle
+
+
+def write_back_point(oracle):
+    """The reference's ``Oracles.set_variable_value`` (nlp_solver.py:205-210) runs inside every callback, so after a
+    solve every Variable of the smooth problem - the user's own Variables among them - holds the LAST point the solver
+    evaluated.  The ``best_of`` loop depends on that side effect: it ranks the starts by ``self.objective.value`` read
+    right after ``solve_via_data`` (problems/problem.py:1262-1268), before any solution is unpacked.  The GPU oracle
+    never touches Variable objects during the solve (that is the Python cost it removes); this writes the last
+    evaluated point back once, when the solver returns."""
+    x = getattr(oracle, "_x_ref", None)
+    problem = getattr(oracle, "_cvx_problem", None)
+    if x is None or problem is None:
+        return
+    offset = 0
+    for var in problem.variables():
+        size = var.size
+        value = x[offset:offset + size].reshape(var.shape, order="F")
+        try:
+            var.value = value              # the validating setter the reference goes through (leaf.py:486-491)
+        except ValueError:                 # the reference would have raised inside the callback; keep the point
+            var.save_value(value)
+        offset += size
+
+
+def _wrap_solve_via_data(key, module, cls_name):
+    try:
+        cls = getattr(importlib.import_module(module), cls_name)
+    except Exception:                      # a solver interface this copy of the reference does not ship
+        return
+    if key in _saved:
+        return
+    orig = cls.solve_via_data
+    _saved[key] = (cls, orig)
+
+    def solve_via_data(self, data, *args, **kwargs):
+        try:
+            return orig(self, data, *args, **kwargs)
+        finally:
+            if isinstance(data, dict) and isinstance(data.get("oracles"), GpuOracles):
+                write_back_point(data["oracles"])
+    cls.solve_via_data = solve_via_data
 
 
 def install(device=0, duals=True):
@@ -54,6 +96,8 @@ def install(device=0, duals=True):
     if "Oracles" not in _saved:
         _saved["Oracles"] = mod.Oracles
     mod.Oracles = gpu_oracles
+    _wrap_solve_via_data("solve_ipopt", "cvxpy.reductions.solvers.nlp_solvers.ipopt_nlpif", "IPOPT")
+    _wrap_solve_via_data("solve_knitro", "cvxpy.reductions.solvers.nlp_solvers.knitro_nlpif", "KNITRO")
     if duals:
         install_dual_recovery()
     return mod
@@ -90,6 +134,10 @@ def uninstall():
         mod.Oracles = _saved.pop("Oracles")
     if "prepare" in _saved:
         mod.NLPsolver._prepare_data_and_inv_data = _saved.pop("prepare")
+    for key in ("solve_ipopt", "solve_knitro"):
+        if key in _saved:
+            cls, orig = _saved.pop(key)
+            cls.solve_via_data = orig
     if "invert" in _saved:
         importlib.import_module("cvxpy.reductions.solvers.nlp_solvers.ipopt_nlpif").IPOPT.invert = _saved.pop("invert")
     ORACLE_CACHE.clear()

@@ -103,6 +103,7 @@ class GpuOracles:
         self.problem = problem_ir
         self.initial_point = problem_ir.x0
         self.iterations = 0
+        self._x_ref = None                 # no point of THIS solve has been evaluated yet
         if self.tape.n_params:
             self.set_parameters(problem_ir.param_values())
 
