@@ -1,0 +1,107 @@
+"""Differential fuzzing of the WHOLE user-facing call (build container only):
+
+    python tests/golden/fuzz_live_solve.py [first_seed last_seed]
+
+Random DNLP problems written the way a user would (the generator of fuzz_live_chain.py) are solved with
+``prob.solve(nlp=True, solver=cp.IPOPT)`` twice: through the unmodified reference, and after
+``dnlp_b200.nlp_solver.install()`` (GpuOracles on the interpreter-backed stand-in device of the CPU tier; no GPU here).
+cyipopt does not exist in this image: tests/cyipopt_standin.py stands where it would be (protocol-faithful, NOT IPOPT).
+Because both arms talk to the same deterministic solver, everything the user sees must agree: the exception type when
+the solve raises, the status, the iteration count, the number of calls of each callback, the optimal value (1e-8
+relative), the variable values and - install() adds them - nothing else.  Summary of the last run:
+fuzz_live_solve.log."""
+import os
+import sys
+import time
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(HERE))
+import fuzz_live_chain as chain_fuzz  # noqa: E402  (loads the reference and the generator)
+from make_golden import cp  # noqa: E402
+
+import cyipopt_standin  # noqa: E402
+import host_logic_device  # noqa: E402
+import dnlp_b200.nlp_solver as gpu  # noqa: E402
+from dnlp_b200.oracles import GpuOracles  # noqa: E402
+
+
+class _Setter:
+    def setattr(self, obj, name, value):
+        setattr(obj, name, value)
+
+
+def solve(seed, ours):
+    prob, _ = chain_fuzz.random_problem(seed)
+    made = []
+    ctor = cyipopt_standin.Problem.__init__
+
+    def spy(p, *a, **k):
+        ctor(p, *a, **k)
+        made.append(p)
+    cyipopt_standin.Problem.__init__ = spy
+    out = {"error": None}
+    try:
+        if ours:
+            with gpu.gpu_oracle():
+                prob.solve(nlp=True, solver=cp.IPOPT, max_iter=150)
+        else:
+            prob.solve(nlp=True, solver=cp.IPOPT, max_iter=150)
+    except Exception as e:          # noqa: BLE001
+        out["error"] = type(e).__name__
+    finally:
+        cyipopt_standin.Problem.__init__ = ctor
+    out["status"] = prob.status
+    out["value"] = prob.value
+    out["iters"] = prob.solver_stats.num_iters if prob.solver_stats is not None else None
+    out["x"] = [None if v.value is None else np.array(v.value, dtype=float) for v in prob.variables()]
+    out["calls"] = made[0].calls if made else None
+    out["cls"] = type(made[0].obj) if made else None
+    return out
+
+
+def check(seed):
+    """'same' | 'same-unsolved' | 'skipped' ; raises AssertionError on a discrepancy."""
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        prob, _ = chain_fuzz.random_problem(seed)
+        try:
+            if not prob.is_dnlp():
+                return "skipped"
+        except Exception:          # noqa: BLE001
+            return "skipped"
+        a = solve(seed, ours=False)
+        b = solve(seed, ours=True)
+    assert a["error"] == b["error"], "seed %d: reference raises %s, ours %s" % (seed, a["error"], b["error"])
+    if a["error"] is not None:      # same exception type; the reference raises at its first structure pass inside the
+        return "same-rejected"      # solver, the compiler when the oracle is created (SURVEY 8b "Errors")
+    assert b["cls"] is GpuOracles and a["cls"].__name__ == "Oracles", "seed %d: wrong oracle class" % seed
+    assert a["status"] == b["status"], "seed %d: status %s vs %s" % (seed, a["status"], b["status"])
+    if a["status"] not in ("optimal", "optimal_inaccurate"):
+        return "same-unsolved"
+    assert a["iters"] == b["iters"], "seed %d: iterations %s vs %s" % (seed, a["iters"], b["iters"])
+    assert a["calls"] == b["calls"], "seed %d: callback counts %r vs %r" % (seed, a["calls"], b["calls"])
+    assert abs(a["value"] - b["value"]) <= 1e-8 * max(1.0, abs(a["value"])), "seed %d: value %r vs %r" % (seed, a["value"], b["value"])
+    for xa, xb in zip(a["x"], b["x"]):
+        np.testing.assert_allclose(xb, xa, rtol=0, atol=1e-6, err_msg="seed %d variable values" % seed)
+    return "same"
+
+
+if __name__ == "__main__":
+    first, last = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (0, 2000)
+    cyipopt_standin.install()
+    host_logic_device.install(_Setter())
+    counts, failures, t0 = {}, [], time.time()
+    for seed in range(first, last):
+        try:
+            r = check(seed)
+        except AssertionError as e:
+            r = "FAILED"
+            failures.append(str(e).splitlines()[0][:300])
+            print(failures[-1], flush=True)
+        counts[r] = counts.get(r, 0) + 1
+    print("seeds %d..%d in %.0f s: %s" % (first, last, time.time() - t0, ", ".join("%s %d" % kv for kv in sorted(counts.items()))))
+    sys.exit(1 if failures else 0)

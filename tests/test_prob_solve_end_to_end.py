@@ -210,3 +210,46 @@ def test_solve_best_of_with_per_start_solver_instances(cp, monkeypatch):
     np.testing.assert_allclose(got, want, rtol=1e-8, atol=1e-9)
     assert abs(value - pr.value) <= 1e-8 * max(1.0, abs(pr.value))
     np.testing.assert_allclose(xo.value, xr.value, atol=1e-7)
+
+
+def test_parameter_sweep_solves_without_recompiling(cp, monkeypatch):
+    """A user's parameter sweep: the same Problem solved at three Parameter values.  The reference re-reads
+    ``Parameter.value`` inside its rules on every callback (expressions/constants/parameter.py:35); with install()
+    the values are slots of the resident tape: ONE compile, the same optimum / iteration count per setting."""
+    import host_logic_device
+
+    import dnlp_b200.nlp_solver as gpu
+    from dnlp_b200 import oracles as oracles_mod
+
+    def build():
+        rng = np.random.default_rng(2)
+        A = rng.standard_normal((8, 5))
+        b = cp.Parameter(8)
+        w = cp.Parameter(5, nonneg=True)        # (a 0-d Parameter crashes the reference's own multiply._hess_vec)
+        x = cp.Variable(5, bounds=[-4, 4])
+        x.value = np.zeros(5)
+        prob = cp.Problem(cp.Minimize(cp.sum(cp.logistic(A @ x - b)) + cp.sum(cp.multiply(w, cp.square(x)))), [cp.sum(x) == 1])
+        return prob, x, b, w
+    settings = [(np.linspace(-1, 1, 8), 0.5), (np.linspace(1, -2, 8), 0.1), (np.full(8, 0.3), 2.0)]
+
+    def sweep(prob, x, b, w):
+        out = []
+        for bv, wv in settings:
+            b.value, w.value = bv, np.full(5, wv)
+            x.value = np.zeros(5)
+            prob.solve(nlp=True, solver=cp.IPOPT)
+            out.append((prob.status, prob.value, prob.solver_stats.num_iters, np.array(x.value)))
+        return out
+    want = sweep(*build())
+    host_logic_device.install(monkeypatch)
+    compiles = []
+    orig = oracles_mod.compile_problem
+    monkeypatch.setattr(oracles_mod, "compile_problem", lambda *a, **k: (compiles.append(1), orig(*a, **k))[1])
+    with gpu.gpu_oracle():
+        got = sweep(*build())
+    assert len(compiles) == 1
+    for (s1, v1, i1, x1), (s2, v2, i2, x2) in zip(want, got):
+        assert s1 == s2 == "optimal" and i1 == i2
+        assert abs(v1 - v2) <= 1e-8 * max(1.0, abs(v1))
+        np.testing.assert_allclose(x2, x1, atol=1e-7)
+    assert len({round(v, 6) for _, v, _, _ in got}) == 3           # the three settings really differ
