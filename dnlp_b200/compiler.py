@@ -127,12 +127,61 @@ def fuse_spmv_jacobian(b, g_ins, jac_ins):
     return F
 
 
+def _first_rejection_in_reference_order(prob, with_hessian):
+    """The exception the REFERENCE raises first for a problem the rules reject.  Its oracle meets the rules in the
+    order cyipopt asks: ``jacobianstructure`` (constraints in order, nlp_solver.py:309-335), ``hessianstructure``
+    (objective, then constraints, :374-392), and only then values and the gradient; the compiler emits the value
+    programs first.  A problem with two different defects (say ``quad_form`` of an affine expression - ValueError -
+    and an atom without rules - NotImplementedError) must fail with the one the reference meets first.  Replayed on a
+    scratch builder, only after the real compilation has failed."""
+    b = Builder(prob)
+    tape = b.tape
+    steps = [lambda c=c: b.jac(c) for c in prob.constraints]
+    if with_hessian:
+        def hess_objective():
+            b.in_objective_hessian = True
+            try:
+                b.hv(prob.objective, SymVec.slots([tape.sigma_slot]))
+            finally:
+                b.in_objective_hessian = False
+        steps.append(hess_objective)
+        coff = 0
+        for con in prob.constraints:
+            steps.append(lambda con=con, coff=coff: b.hv(con, SymVec.slot_range(tape.lam_slot + coff, con.size)))
+            coff += con.size
+    steps.append(lambda: b.value(prob.objective))
+    steps.append(lambda: b.jac(prob.objective))
+    steps += [lambda c=c: b.value(c) for c in prob.constraints]
+    for step in steps:
+        try:
+            step()
+        except Exception as e:          # noqa: BLE001
+            return e
+    return None
+
+
 def compile_problem(prob, with_hessian=True):
     """ProblemIR -> Tape (host arrays only; ``GpuOracles`` uploads it through the C-ABI).
 
     ``with_hessian=False`` skips the Hessian program (the reference can serve first-order
     callbacks for expressions whose ``hess_vec`` rule rejects them; cyipopt then falls back to
-    L-BFGS when the object has no usable ``hessian``)."""
+    L-BFGS when the object has no usable ``hessian``).
+
+    Rule-precondition failures raise what the reference raises (ValueError / NotImplementedError with its message,
+    SURVEY 8b "Errors"), and when a problem has several, the one the reference's evaluation order meets first."""
+    try:
+        return _compile_problem(prob, with_hessian)
+    except (ValueError, NotImplementedError, AttributeError, UnboundLocalError, TypeError, IndexError) as first:
+        try:
+            ref_first = _first_rejection_in_reference_order(prob, with_hessian)
+        except Exception:               # noqa: BLE001
+            ref_first = None
+        if ref_first is None or (type(ref_first) is type(first) and str(ref_first) == str(first)):
+            raise
+        raise ref_first from first
+
+
+def _compile_problem(prob, with_hessian=True):
     b = Builder(prob)
     tape = b.tape
     if tape.n_params:

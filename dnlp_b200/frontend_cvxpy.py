@@ -129,8 +129,10 @@ def expr_to_ir(expr, memo, parent=None):
             node = ir.Node("power", args, expr.shape,
                            p=float(p), p_rational=expr.p_rational)
         else:
-            raise NotImplementedError(
-                "Atom %s does not have a Jacobian, or it has not been implemented yet." % cls)
+            # no NLP rules in the reference (atoms/atom.py:587-593).  The reference only finds out when a structure
+            # pass reaches the atom, AFTER whatever it meets earlier in its own evaluation order: keep the node and
+            # let the compiler raise there (compiler.compile_problem replays that order when a problem is rejected)
+            node = ir.Node("unsupported", args, expr.shape, cls=cls, affine=bool(expr.is_affine()))
         if node.is_affine() != bool(expr.is_affine()):
             raise AssertionError("affine classification differs from the reference for %s" % cls)
     memo[key] = node

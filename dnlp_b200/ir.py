@@ -36,7 +36,8 @@ AFFINE_OPS = (
 )
 BILINEAR_OPS = ("multiply", "matmul")
 OTHER_SMOOTH = ("quad_form", "quad_over_lin", "rel_entr")
-ALL_OPS = ("var", "const", "param") + AFFINE_OPS + BILINEAR_OPS + ELEMENTWISE_UNARY + OTHER_SMOOTH
+# "unsupported": an atom of the reference without NLP rules, kept so that the compiler raises where the reference would
+ALL_OPS = ("var", "const", "param", "unsupported") + AFFINE_OPS + BILINEAR_OPS + ELEMENTWISE_UNARY + OTHER_SMOOTH
 
 _var_ids = itertools.count(1)
 
@@ -126,6 +127,10 @@ class Node:
         if self.op == "power":
             # power(x, 1) is DCP-affine; power_canon removes it before the oracle sees it
             return self.attrs["p"] == 1 and self.args[0].is_affine()
+        if self.op == "unsupported":
+            # an atom of the reference without NLP rules (frontend_cvxpy.py): it only exists so that the compiler can
+            # raise NotImplementedError WHERE the reference would (rules.Builder.jac / hv), not at conversion time
+            return bool(self.attrs.get("affine", False))
         return False
 
     @property

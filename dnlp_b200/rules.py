@@ -464,6 +464,9 @@ class Builder:
             self._reject_param_operands(node)
             xv = self.value(a[0])
             return self.mul(xv, self.quad_form_Qx(node)).sum_all()
+        if op == "unsupported":                            # the reference can evaluate it but not differentiate it
+            raise NotImplementedError("Atom %s does not have a Jacobian, or it has not been implemented yet."
+                                      % node.attrs["cls"])
         raise NotImplementedError(op)
 
     def _reject_param_operands(self, node):
@@ -564,6 +567,9 @@ class Builder:
             return {node.attrs["id"]: (r, r, SymVec.const(np.ones(node.size)))}
         if node.is_constant():                             # atoms/atom.py:504-505
             return {}
+        if node.op == "unsupported":                       # atoms/atom.py:591-593
+            raise NotImplementedError("Atom %s does not have a Jacobian, or it has not been implemented yet."
+                                      % node.attrs["cls"])
         if not self._verify_jac(node):                     # atoms/atom.py:509-510
             raise ValueError("Argument error in jacobian for atom %s." % node.op)
         if node.op not in ir.AFFINE_OPS and node.op != "multiply":
@@ -1054,6 +1060,9 @@ class Builder:
             raise ValueError("Dimension mismatch in hess_vec. vec.size != phi(x).size")
         if node.is_affine():                               # atoms/atom.py:551-552
             return {}
+        if node.op == "unsupported":                       # atoms/atom.py:586-588
+            raise NotImplementedError("Atom %s does not have a Hessian, or it has not been implemented yet."
+                                      % node.attrs["cls"])
         if not self._verify_hess(node):                    # atoms/atom.py:556-559
             raise ValueError("Argument error in hess_vec for atom %s." % node.op)
         return self._hv_inner(node, vec)

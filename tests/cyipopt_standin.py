@@ -187,6 +187,9 @@ class _BarrierSolver:
         linear solver): D is block diagonal with 1x1 and 2x2 blocks."""
         _, d, _ = sla.ldl(K, lower=True, hermitian=True, check_finite=False)
         diag, off = np.diag(d).copy(), np.diag(d, -1)
+        # a pivot that is zero up to rounding counts as zero (-> wrong inertia -> regularise): the decision must not
+        # hinge on whether an exactly cancelling Hessian entry arrives as 0.0 or as 1e-17
+        diag[np.abs(diag) <= 1e-11 * max(1.0, float(np.abs(diag).max(initial=0.0)))] = 0.0
         pos = neg = 0
         i, n = 0, diag.size
         while i < n:

@@ -288,3 +288,39 @@ def test_nested_broadcast_in_the_objective_is_rejected_like_the_reference():
     it = TapeInterp(tape)
     lam = np.arange(1.0, 7.0)
     assert_close(it.eval("hess", in_constraint.x0, lam, 1.0), ref.hessian(in_constraint.x0, lam, 1.0), "hess")
+
+
+def test_a_problem_with_two_defects_fails_with_the_one_the_reference_meets_first():
+    """Found by tests/golden/fuzz_live_solve.py (``prob.solve(nlp=True)`` on both oracles): ``quad_form`` of an affine
+    expression (ValueError, atoms/atom.py:509-510) in one constraint and an atom without NLP rules (NotImplementedError,
+    atoms/atom.py:591-593) in another.  The reference meets the rules in cyipopt's order - constraint Jacobians in
+    order, then the Hessians, then values and the gradient - and raises whichever defect comes first there; the
+    compiler emits the value programs first, so on a rejected problem it replays the reference's order
+    (compiler._first_rejection_in_reference_order).  An atom without rules used to be rejected at conversion time,
+    before anything else."""
+    x = ir.Variable((3,))
+    P = np.array([[2.0, 0.3, 0.0], [0.3, 1.5, 0.2], [0.0, 0.2, 1.0]])
+    shifted = ir.add(ir.multiply(ir.Constant(np.full(3, 0.8)), x), ir.Constant(np.full(3, 0.1)))
+    bad_arg = ir.Node("quad_form", [shifted, ir.Constant(P)], ())                   # argument is not a Variable
+    no_rules = ir.sum(ir.Node("unsupported", [x], x.shape, cls="nonneg_wrap", affine=False))
+    obj = ir.sum(ir.Node("exp", [x], x.shape))
+
+    def problem(cons, objective=obj):
+        p = ir.ProblemIR(objective, cons)
+        p.x0 = np.array([0.5, 0.6, 0.7])
+        return p
+    with pytest.raises(ValueError, match="Argument error in jacobian for atom quad_form"):
+        compile_problem(problem([bad_arg, no_rules]))
+    with pytest.raises(NotImplementedError, match="Atom nonneg_wrap does not have a Jacobian"):
+        compile_problem(problem([no_rules, bad_arg]))
+    # a defect in the objective shows up at the Hessian pass, after every constraint Jacobian
+    with pytest.raises(ValueError):
+        compile_problem(problem([bad_arg], objective=no_rules))
+    with pytest.raises(NotImplementedError, match="does not have a Hessian"):
+        compile_problem(problem([ir.sum(x)], objective=no_rules))
+    # alone, each raises its own exception; without either the problem compiles
+    with pytest.raises(NotImplementedError):
+        compile_problem(problem([no_rules]))
+    with pytest.raises(ValueError):
+        compile_problem(problem([bad_arg]))
+    compile_problem(problem([ir.sum(x)]))
