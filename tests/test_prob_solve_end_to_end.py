@@ -253,3 +253,24 @@ def test_parameter_sweep_solves_without_recompiling(cp, monkeypatch):
         assert abs(v1 - v2) <= 1e-8 * max(1.0, abs(v1))
         np.testing.assert_allclose(x2, x1, atol=1e-7)
     assert len({round(v, 6) for _, v, _, _ in got}) == 3           # the three settings really differ
+
+
+def test_install_and_uninstall_leave_the_reference_as_they_found_it(cp):
+    """install() rebinds ``Oracles`` and wraps ``solve_via_data`` (write-back of the last evaluated point) / ``invert``
+    / ``_prepare_data_and_inv_data`` (dual recovery); uninstall() must restore every one of them."""
+    import importlib
+
+    import dnlp_b200.nlp_solver as gpu
+    mod = importlib.import_module("cvxpy.reductions.solvers.nlp_solvers.nlp_solver")
+    ipopt = importlib.import_module("cvxpy.reductions.solvers.nlp_solvers.ipopt_nlpif").IPOPT
+    knitro = importlib.import_module("cvxpy.reductions.solvers.nlp_solvers.knitro_nlpif").KNITRO
+    before = (mod.Oracles, mod.NLPsolver._prepare_data_and_inv_data, ipopt.solve_via_data, ipopt.invert,
+              knitro.solve_via_data)
+    with gpu.gpu_oracle():
+        assert mod.Oracles is gpu.gpu_oracles
+        assert ipopt.solve_via_data is not before[2] and knitro.solve_via_data is not before[4]
+        with gpu.gpu_oracle():                    # nested / repeated install keeps ONE layer of wrapping
+            pass
+    after = (mod.Oracles, mod.NLPsolver._prepare_data_and_inv_data, ipopt.solve_via_data, ipopt.invert,
+             knitro.solve_via_data)
+    assert after == before
