@@ -52,6 +52,7 @@ def solve(seed, ours):
             prob.solve(nlp=True, solver=cp.IPOPT, max_iter=150)
     except Exception as e:          # noqa: BLE001
         out["error"] = type(e).__name__
+        out["message"] = str(e)
     finally:
         cyipopt_standin.Problem.__init__ = ctor
     out["status"] = prob.status
@@ -75,6 +76,14 @@ def check(seed):
             return "skipped"
         a = solve(seed, ours=False)
         b = solve(seed, ours=True)
+    if a["error"] == "ValueError" and "must be" in a.get("message", "") and b["error"] != "ValueError":
+        # Quirk Q8: the reference validates x against the Variables' declared attributes inside EVERY
+        # callback (leaf.py:526-610 through Oracles.set_variable_value) and raises when the solver evaluates a point
+        # outside them.  With the lb / ub the reference hands the solver that can only happen when those vectors are
+        # misaligned with the oracle's variable order: Bounds takes the order of the problem BEFORE
+        # lower_ineq_to_nonneg rewrites `a <= b` as `b - a >= 0`, Oracles the order after (nlp_solver.py:84 vs :201).
+        # GpuOracles does not validate points (an O(n) host pass per callback); flagged, not reproduced.
+        return "reference-validates-point"
     assert a["error"] == b["error"], "seed %d: reference raises %s, ours %s" % (seed, a["error"], b["error"])
     if a["error"] is not None:      # same exception type; the reference raises at its first structure pass inside the
         return "same-rejected"      # solver, the compiler when the oracle is created (SURVEY 8b "Errors")
