@@ -22,6 +22,8 @@ The reference is imported lazily so the rest of the package works without it.
 import contextlib
 import importlib
 
+import numpy as np
+
 from .compile_cache import OracleCache
 from .frontend_cvxpy import problem_to_ir
 from .oracles import GpuOracles
@@ -32,8 +34,26 @@ DEVICE = 0
 ORACLE_CACHE = OracleCache(capacity=2)
 
 
+def _validate_initial_point(problem, initial_point):
+    """The reference validates EVERY point the solver evaluates against the Variables' declared attributes
+    (``Oracles.set_variable_value`` -> the ``value`` setter, leaf.py:486-491,526-610) and raises ValueError when one
+    is violated.  With the lb / ub it hands the solver that happens in one situation: ``Bounds`` lays out lb / ub / x0
+    in the variable order of the problem BEFORE ``lower_ineq_to_nonneg`` rewrites ``a <= b`` as ``b - a >= 0``
+    (nlp_solver.py:84), ``Oracles`` reads x in the order after (nlp_solver.py:201); when the two differ, a bounded
+    Variable sits on another Variable's slots and the very first callback fails.  Validating each point would put an
+    O(n) host pass into every callback; the initial point is validated once, with the reference's own validator and
+    message, which reproduces that failure where it occurs (found by tests/golden/fuzz_live_solve.py)."""
+    offset = 0
+    x0 = np.asarray(initial_point, dtype=np.float64).reshape(-1)
+    for var in problem.variables():
+        size = var.size
+        var._validate_value(x0[offset:offset + size].reshape(var.shape, order="F"))
+        offset += size
+
+
 def gpu_oracles(problem, initial_point, num_constraints):
     """Same signature as ``Oracles.__init__`` (nlp_solver.py:182)."""
+    _validate_initial_point(problem, initial_point)
     pir = problem_to_ir(problem, x0=initial_point)
     if pir.m != num_constraints:
         raise ValueError("constraint count mismatch: IR has %d rows, caller says %d" % (pir.m, num_constraints))

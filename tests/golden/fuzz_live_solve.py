@@ -82,7 +82,8 @@ def check(seed):
         # outside them.  With the lb / ub the reference hands the solver that can only happen when those vectors are
         # misaligned with the oracle's variable order: Bounds takes the order of the problem BEFORE
         # lower_ineq_to_nonneg rewrites `a <= b` as `b - a >= 0`, Oracles the order after (nlp_solver.py:84 vs :201).
-        # GpuOracles does not validate points (an O(n) host pass per callback); flagged, not reproduced.
+        # GpuOracles does not validate every point (an O(n) host pass per callback); install() validates the initial
+        # one, which reproduces the misaligned case.  What is left here is a LATER iterate leaving the attributes.
         return "reference-validates-point"
     assert a["error"] == b["error"], "seed %d: reference raises %s, ours %s" % (seed, a["error"], b["error"])
     if a["error"] is not None:      # same exception type; the reference raises at its first structure pass inside the

@@ -274,3 +274,28 @@ def test_install_and_uninstall_leave_the_reference_as_they_found_it(cp):
     after = (mod.Oracles, mod.NLPsolver._prepare_data_and_inv_data, ipopt.solve_via_data, ipopt.invert,
              knitro.solve_via_data)
     assert after == before
+
+
+def test_misaligned_bounds_of_the_reference_fail_the_same_way(cp, monkeypatch):
+    """Reference quirk Q8 (found by tests/golden/fuzz_live_solve.py): ``Bounds`` lays out lb / ub /
+    x0 in the variable order of the problem BEFORE ``lower_ineq_to_nonneg`` rewrites ``a <= b`` as ``b - a >= 0``,
+    ``Oracles`` reads x in the order after.  Here that puts the bounded ``v1`` on an auxiliary variable's slots; the
+    reference's validating setter then raises ValueError in the first callback.  install() validates the initial
+    point once with the reference's own validator: the same exception type and message."""
+    import host_logic_device
+
+    import dnlp_b200.nlp_solver as gpu
+
+    def build():
+        v1 = cp.Variable((3, 3), name="v1", bounds=[0.1, 2.0])
+        v2 = cp.Variable(name="v2")
+        v2.value = 0.5
+        return cp.Problem(cp.Minimize(cp.atanh(0.9 * v2 + 0.08)),
+                          [0.11 <= cp.minimum(v1, 0.7), 0.12 <= cp.asinh(1.18 * v2 + 0.1), 0.05 <= v1])
+    with pytest.raises(ValueError, match="Variable value must be in bounds") as ref:
+        build().solve(nlp=True, solver=cp.IPOPT)
+    host_logic_device.install(monkeypatch)
+    with gpu.gpu_oracle():
+        with pytest.raises(ValueError, match="Variable value must be in bounds") as ours:
+            build().solve(nlp=True, solver=cp.IPOPT)
+    assert str(ours.value) == str(ref.value)
