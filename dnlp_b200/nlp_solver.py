@@ -53,13 +53,15 @@ def _validate_initial_point(problem, initial_point):
 
 def gpu_oracles(problem, initial_point, num_constraints):
     """Same signature as ``Oracles.__init__`` (nlp_solver.py:182)."""
-    _validate_initial_point(problem, initial_point)
     pir = problem_to_ir(problem, x0=initial_point)
     if pir.m != num_constraints:
         raise ValueError("constraint count mismatch: IR has %d rows, caller says %d" % (pir.m, num_constraints))
     oracle, hit = ORACLE_CACHE.get(pir, lambda p: GpuOracles(p, device=DEVICE), extra_key=(("device", DEVICE),))
     if hit:
         oracle.rearm(pir)
+    # after the compile: the reference's structure passes run at x = NaN, which its validator lets through
+    # (leaf.py:604-606), so a rule violation is reported before a point outside a Variable's attributes
+    _validate_initial_point(problem, initial_point)
     oracle._cvx_problem = problem          # for write_back_point(): the smooth problem of THIS chain application
     return oracle
 
