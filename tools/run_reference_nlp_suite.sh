@@ -10,7 +10,7 @@ cd /tmp
 for arm in reference ours; do
   PYTHONPATH="$ROOT/tools:$ROOT/tests" DNLP_REFSUITE_ORACLE=$arm DNLP_REFSUITE_LOG="$OUT/refsuite_prob_solve.$arm.log" \
     timeout 3000 python -m pytest /root/reference/cvxpy/tests/NLP_tests/test_*.py -p refsuite_plugin -p no:cacheprovider \
-    --import-mode=importlib -q --tb=no --timeout 600 -rA 2>&1 | grep -E "^(PASSED|FAILED|SKIPPED|ERROR)|passed|failed" \
+    --import-mode=importlib -q --tb=no --timeout 900 -rA 2>&1 | grep -E "^(PASSED|FAILED|SKIPPED|ERROR)|passed|failed" \
     | sed -e 's#\.\./root/reference/cvxpy/tests/NLP_tests/##' > "$OUT/refsuite_prob_solve.$arm.outcomes"
   tail -1 "$OUT/refsuite_prob_solve.$arm.outcomes"
 done
