@@ -6,7 +6,8 @@
 every return value, ``intermediate`` / ``iterations``, options, the info dict, dual recovery - and that swapping the
 oracle changes nothing the user sees: same status, same iteration count, optimum within 1e-8.
 
-CPU tier: GpuOracles on the interpreter-backed stand-in device.  GPU tier: the real device.
+CPU tier: GpuOracles on the interpreter-backed stand-in device.  GPU tier (the real device):
+tests/test_zz_gpu_prob_solve.py.
 The whole reference test-suite goes through the same path in tools/run_reference_nlp_suite.sh (build container only);
 its last run is tests/golden/refsuite_prob_solve.*.log."""
 import os
@@ -169,16 +170,6 @@ def test_best_of_loop_of_the_reference_compiles_once(cp, monkeypatch):
     np.testing.assert_allclose(b, a, rtol=1e-8, atol=1e-10)
     assert len(ours.nlps) == 4 and len({id(p.obj) for p in ours.nlps}) == 1      # one resident oracle, re-armed
     assert len(compiles) <= 1
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("name", sorted(CASES))
-def test_gpu_prob_solve_is_unchanged_by_the_oracle_swap(name, cp, monkeypatch):
-    """The same on the real device: the CUDA path behind the reference's own solver interface."""
-    ref, ours = _both_arms(cp, CASES[name], monkeypatch, standin_device=False)
-    assert ours.nlps[0].obj.kernel_launches() > 0
-    if name == "readme_toy":
-        assert abs(ours.value - README_OPTIMUM) < 1e-7
 
 
 def test_solve_best_of_with_per_start_solver_instances(cp, monkeypatch):
